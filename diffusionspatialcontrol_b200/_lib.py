@@ -1,0 +1,74 @@
+"""ctypes binding of libdsc_b200.so -- the C-ABI boundary declared in include/dsc_b200.h.
+
+There is deliberately no fallback: if the library is missing the import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+from .build import LIB_PATH
+
+DTYPE_F16 = 0
+DTYPE_BF16 = 1
+MAX_KEYS = 80
+ERR_INVALID_ARGUMENT, ERR_UNSUPPORTED, ERR_LAYOUT, ERR_SHAPE = -1, -2, -3, -4
+
+# symbol -> (restype, argtypes); kept in the order of include/dsc_b200.h
+SIGNATURES = {
+    "dsc_version": (c_int, []),
+    "dsc_last_error": (c_char_p, []),
+    "dsc_sm_count": (c_int, []),
+    "dsc_xattn_workspace_bytes": (c_int, [c_int] * 5 + [POINTER(c_size_t)]),
+    "dsc_xattn_stats": (
+        c_int,
+        [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p]
+        + [c_int] * 5 + [c_float, c_int, c_void_p, c_void_p],
+    ),
+    "dsc_xattn_forward": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), c_void_p, c_int,
+         c_void_p, c_float, c_void_p, c_void_p, POINTER(c_int64)]
+        + [c_int] * 5 + [c_float, c_int, c_void_p],
+    ),
+    "dsc_region_downsample": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]),
+    "dsc_region_accumulate": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+         c_void_p, c_void_p],
+    ),
+    "dsc_dpmpp2m_step": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double, c_int, c_int,
+         c_void_p],
+    ),
+}
+
+
+class DscError(RuntimeError):
+    """Non-zero return from libdsc_b200 (negative: DSC_ERR_*, positive: cudaError_t)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libdsc_b200 error {code}: {message}")
+        self.code = code
+
+
+def _load() -> ctypes.CDLL:
+    if not LIB_PATH.is_file():
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built and there is no fallback path. "
+            "Build it with `python diffusionspatialcontrol_b200/build.py` (needs nvcc; no GPU required)."
+        )
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+lib = _load()
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise DscError(code, lib.dsc_last_error().decode("utf-8", "replace"))

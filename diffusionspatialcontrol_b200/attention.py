@@ -1,0 +1,146 @@
+"""Functional entry points of the hot path: thin Python over the C ABI (include/dsc_b200.h).
+
+``region_attention`` has the call shape of the reference's
+``scaled_dot_product_attention_regionstate(query, key, value, ..., region_state=, sigma=)``
+(reference source/modules/attention_modify.py:74-103) with ``weight_func`` fixed to the reference's
+``w * sigma * qk.std()`` (reference source/app.py:1004).  PyTorch is used for device memory and the
+current stream only; all arithmetic happens in libdsc_b200.so.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Union
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_I64x4 = ctypes.c_int64 * 4
+_I64x3 = ctypes.c_int64 * 3
+_DTYPES = {torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
+_WORKSPACES: dict = {}
+
+
+def workspace_bytes(B: int = 1, H: int = 1, L: int = 1, D: int = 40, S: int = 77) -> int:
+    n = ctypes.c_size_t(0)
+    check(lib.dsc_xattn_workspace_bytes(B, H, L, D, S, ctypes.byref(n)))
+    return int(n.value)
+
+
+def get_workspace(device: torch.device) -> torch.Tensor:
+    """One zero-initialised workspace per (device, stream); calls on a stream are serialised, so all
+    layers can share it.  Allocated through PyTorch's caching allocator (CUDA-graph friendly)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        ws = torch.zeros(workspace_bytes(), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _as_bhxd(x: torch.Tensor, name: str) -> torch.Tensor:
+    """Return x ([B,H,rows,D]) in the layout the kernels stream: a view of [B, rows, H*D]."""
+    if x.dim() != 4:
+        raise ValueError(f"{name} must be [B, H, rows, D], got {tuple(x.shape)}")
+    B, H, R, D = x.shape
+    s = x.stride()
+    ok = s[3] == 1 and s[1] == D and s[2] % 8 == 0 and s[0] % 8 == 0 and x.data_ptr() % 16 == 0
+    if not ok:  # e.g. a contiguous [B,H,rows,D] tensor: re-lay it out once (plumbing, not arithmetic)
+        x = x.transpose(1, 2).contiguous().transpose(1, 2)
+    return x
+
+
+def _stream_ptr(device: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_inputs(query, key):
+    if not query.is_cuda:
+        raise RuntimeError("diffusionspatialcontrol_b200 has no CPU path: tensors must live on a CUDA device")
+    if query.dtype not in _DTYPES:
+        raise TypeError(f"query dtype {query.dtype} not supported (float16 / bfloat16)")
+    if key.dtype != query.dtype:
+        raise TypeError("query/key/value must share one dtype")
+
+
+def score_stats(query: torch.Tensor, key: torch.Tensor, scale: Optional[float] = None,
+                workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Pass 1 alone.  Returns the workspace (uint8); bytes 8..12 hold the fp32 unbiased std of
+    ``scale * Q K^T`` over the whole call, see ``read_stats``.  Asynchronous."""
+    _check_inputs(query, key)
+    q, k = _as_bhxd(query, "query"), _as_bhxd(key, "key")
+    B, H, L, D = q.shape
+    S = k.shape[2]
+    scale = 1.0 / math.sqrt(D) if scale is None else float(scale)
+    ws = get_workspace(q.device) if workspace is None else workspace
+    with torch.cuda.device(q.device):
+        check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), _I64x4(*q.stride()), _I64x4(*k.stride()), None,
+                                  B, H, L, D, S, scale, _DTYPES[q.dtype], ws.data_ptr(), _stream_ptr(q.device)))
+    return ws
+
+
+def read_stats(workspace: torch.Tensor) -> dict:
+    """Synchronising debug/test helper: decode the dsc_xattn_stats_t header."""
+    raw = workspace[:48].cpu().numpy().tobytes()
+    import struct
+
+    ticket, n_part, std, mean, s, ss, n = struct.unpack("<IIffddd", raw[:40])
+    return {"ticket": ticket, "n_partials": n_part, "std": std, "mean": mean, "sum": s, "sumsq": ss, "n": n}
+
+
+def region_attention(
+    query: torch.Tensor,  # [B, H, L, D]
+    key: torch.Tensor,  # [B, H, S, D]
+    value: torch.Tensor,  # [B, H, S, D]
+    region_state: torch.Tensor,  # fp32 [B', L, S] on the same device
+    sigma: Union[float, torch.Tensor],
+    attn_mask: Optional[torch.Tensor] = None,
+    scale: Optional[float] = None,
+    workspace: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """softmax(scale*QK^T + sigma*std(scale*QK^T)*W) V  ->  [B, H, L, D] (a view of a fresh [B, L, H*D])."""
+    _check_inputs(query, key)
+    if attn_mask is not None:
+        raise NotImplementedError("additive attention masks are not implemented on the region path "
+                                  "(SD-1.5 cross-attention never passes one)")
+    q, k, v = _as_bhxd(query, "query"), _as_bhxd(key, "key"), _as_bhxd(value, "value")
+    B, H, L, D = q.shape
+    S = k.shape[2]
+    W = region_state
+    if W.dim() != 3 or W.shape[1] != L or W.shape[2] != S:
+        raise ValueError(f"region_state must be [B', L={L}, S={S}], got {tuple(W.shape)}")
+    if (B * H) % W.shape[0] != 0:
+        raise ValueError(f"region_state batch {W.shape[0]} does not divide B*H={B * H}")  # reference: shape error at :97
+    if B % W.shape[0] != 0:
+        raise NotImplementedError(f"region_state batch {W.shape[0]} must divide the attention batch {B}")
+    if W.dtype != torch.float32 or not W.is_contiguous() or W.device != q.device:
+        W = W.to(device=q.device, dtype=torch.float32).contiguous()
+    scale = 1.0 / math.sqrt(D) if scale is None else float(scale)
+    ws = get_workspace(q.device) if workspace is None else workspace
+    out = torch.empty((B, L, H * D), dtype=q.dtype, device=q.device)
+
+    sigma_ptr, sigma_host = None, 0.0
+    if isinstance(sigma, torch.Tensor):
+        if sigma.is_cuda:  # never .item() a device sigma: pass its address
+            if sigma.dtype != torch.float32 or sigma.device != q.device:
+                sigma = sigma.to(device=q.device, dtype=torch.float32)
+            sigma_keepalive = sigma.reshape(-1)
+            sigma_ptr = sigma_keepalive.data_ptr()
+        else:
+            sigma_host = float(sigma)
+    else:
+        sigma_host = float(sigma)
+
+    dt = _DTYPES[q.dtype]
+    st = _stream_ptr(q.device)
+    qs, ks, vs = _I64x4(*q.stride()), _I64x4(*k.stride()), _I64x4(*v.stride())
+    with torch.cuda.device(q.device):
+        check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), qs, ks, None, B, H, L, D, S, scale, dt,
+                                  ws.data_ptr(), st))
+        check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), W.shape[0],
+                                    sigma_ptr, sigma_host, ws.data_ptr(), out.data_ptr(), _I64x3(*out.stride()),
+                                    B, H, L, D, S, scale, dt, st))
+    return out.view(B, L, H, D).transpose(1, 2)

@@ -1,0 +1,193 @@
+"""Drop-in attention processor: install with ``unet.set_attn_processor(RegionAttnProcessor())`` exactly
+where the reference installs its own (reference source/app.py:479-481).
+
+Mirrors ``AttnProcessor2_0.__call__`` of the reference (source/modules/attention_modify.py:414-503):
+same signature (the kwarg names matter -- diffusers drops cross_attention_kwargs the processor does
+not name), same dispatch rule (region path iff cross-attention AND region_prompt given AND
+region_state is a dict, :437-442,:479), same projections / head split / merge / out-proj / residual.
+Only the body of ``scaled_dot_product_attention_regionstate`` (:74-103) is replaced by the two CUDA
+passes in libdsc_b200.so.  Self-attention and region-less calls go to
+``F.scaled_dot_product_attention`` like the reference (:483-485).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Callable, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .attention import region_attention
+
+
+def _is_reference_weight_func(fn: Callable) -> bool:
+    """The kernels hard-wire ``w * sigma * qk.std()`` (reference app.py:1004); probe the callable."""
+    try:
+        qk = torch.tensor([0.0, 1.0, 3.0, -2.0])
+        w = torch.tensor([[[1.0, -0.5]]])
+        got = fn(w, torch.tensor(2.0), qk)
+        want = w * 2.0 * qk.std()
+        return bool(torch.allclose(got, want, rtol=1e-6, atol=0))
+    except Exception:
+        return False
+
+
+class RegionAttnProcessor:
+    r"""B200-native replacement for the reference's ``AttnProcessor2_0``.
+
+    cache_kv: reuse ``to_k/to_v(encoder_hidden_states)`` while the same text-embedding tensor is passed
+    (numerically identical, the reference recomputes them on each of the 25 steps).
+    """
+
+    def __init__(self, cache_kv: bool = False, max_cached_maps: int = 16):
+        if not hasattr(F, "scaled_dot_product_attention"):
+            raise ImportError("RegionAttnProcessor requires PyTorch 2.0")
+        self.cache_kv = cache_kv
+        self._w_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+        self._max_cached_maps = max_cached_maps
+        self._checked_funcs: dict = {}
+        self._sigma_cache: Optional[tuple] = None
+        self._kv_cache: dict = {}
+
+    # -- small caches (all keyed so that a changed tensor is never served stale) ----------------
+    def _device_map(self, w: torch.Tensor, device: torch.device) -> torch.Tensor:
+        key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype, str(device))
+        hit = self._w_cache.get(key)
+        if hit is not None and hit[0] is w:
+            self._w_cache.move_to_end(key)
+            return hit[1]
+        dev = w.to(device=device, dtype=torch.float32, non_blocking=False).contiguous()
+        self._w_cache[key] = (w, dev)  # keeps `w` alive, so data_ptr cannot be recycled under the key
+        while len(self._w_cache) > self._max_cached_maps:
+            self._w_cache.popitem(last=False)
+        return dev
+
+    def _check_weight_func(self, fn: Callable) -> None:
+        ok = self._checked_funcs.get(id(fn))
+        if ok is None or ok[0] is not fn:
+            ok = (fn, _is_reference_weight_func(fn))
+            if len(self._checked_funcs) > 64:
+                self._checked_funcs.clear()
+            self._checked_funcs[id(fn)] = ok
+        if not ok[1]:
+            raise NotImplementedError(
+                "RegionAttnProcessor implements weight_func = w * sigma * qk.std() (reference app.py:1004); "
+                "the callable passed in region_prompt['weight_func'] computes something else"
+            )
+
+    def _sigma_arg(self, sigma, device: torch.device):
+        if isinstance(sigma, torch.Tensor) and sigma.is_cuda:
+            if sigma.dtype == torch.float32 and sigma.device == device:
+                return sigma
+            c = self._sigma_cache
+            if c is not None and c[0] is sigma and c[1] == sigma._version:
+                return c[2]
+            conv = sigma.detach().to(device=device, dtype=torch.float32)  # one tiny cast per step, no host sync
+            self._sigma_cache = (sigma, sigma._version, conv)
+            return conv
+        return float(sigma)
+
+    def _project_kv(self, attn, ehs: torch.Tensor, args):
+        if not self.cache_kv:
+            return attn.to_k(ehs, *args), attn.to_v(ehs, *args)
+        key = id(attn)
+        hit = self._kv_cache.get(key)
+        if hit is not None and hit[0] is ehs and hit[1] == ehs._version:
+            return hit[2], hit[3]
+        k, v = attn.to_k(ehs, *args), attn.to_v(ehs, *args)
+        self._kv_cache[key] = (ehs, ehs._version, k, v)
+        return k, v
+
+    def clear_caches(self) -> None:
+        self._w_cache.clear()
+        self._kv_cache.clear()
+        self._sigma_cache = None
+
+    # -- processor protocol ---------------------------------------------------------------------
+    def __call__(
+        self,
+        attn,
+        hidden_states: torch.Tensor,
+        encoder_hidden_states: Optional[torch.Tensor] = None,
+        attention_mask: Optional[torch.Tensor] = None,
+        temb: Optional[torch.Tensor] = None,
+        scale: float = 1.0,
+        region_prompt=None,
+        ip_adapter_masks=None,
+    ) -> torch.Tensor:
+        residual = hidden_states
+        img_sequence_length = hidden_states.shape[1]
+        if getattr(attn, "spatial_norm", None) is not None:
+            hidden_states = attn.spatial_norm(hidden_states, temb)
+
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:
+            batch_size, channel, height, width = hidden_states.shape
+            hidden_states = hidden_states.view(batch_size, channel, height * width).transpose(1, 2)
+
+        is_xattn = False
+        region_state = weight_func = sigma = None
+        if encoder_hidden_states is not None and region_prompt is not None:
+            is_xattn = True
+            region_state = region_prompt["region_state"]
+            weight_func = region_prompt["weight_func"]
+            sigma = region_prompt["sigma"]
+
+        batch_size, sequence_length, _ = (
+            hidden_states.shape if encoder_hidden_states is None else encoder_hidden_states.shape
+        )
+        if attention_mask is not None:
+            attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
+            attention_mask = attention_mask.view(batch_size, attn.heads, -1, attention_mask.shape[-1])
+
+        if getattr(attn, "group_norm", None) is not None:
+            hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+
+        args = ()  # diffusers >= 0.26 with the PEFT backend: Linear takes no scale argument (reference :457)
+        query = attn.to_q(hidden_states, *args)
+
+        cross = encoder_hidden_states is not None
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+        elif getattr(attn, "norm_cross", None):
+            encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
+
+        if cross and is_xattn:
+            key, value = self._project_kv(attn, encoder_hidden_states, args)
+        else:
+            key = attn.to_k(encoder_hidden_states, *args)
+            value = attn.to_v(encoder_hidden_states, *args)
+
+        inner_dim = key.shape[-1]
+        head_dim = inner_dim // attn.heads
+        query = query.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        key = key.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        value = value.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+
+        if is_xattn and isinstance(region_state, dict):
+            self._check_weight_func(weight_func)
+            w = region_state[img_sequence_length]  # KeyError for an unknown resolution, like the reference (:481)
+            hidden_states = region_attention(
+                query, key, value,
+                self._device_map(w, query.device),
+                self._sigma_arg(sigma, query.device),
+                attn_mask=attention_mask,
+                scale=None,  # the reference always uses 1/sqrt(head_dim) here (:77), not attn.scale
+            )
+        else:
+            hidden_states = F.scaled_dot_product_attention(
+                query, key, value, attn_mask=attention_mask, dropout_p=0.0, is_causal=False
+            )
+
+        hidden_states = hidden_states.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim)
+        hidden_states = hidden_states.to(query.dtype)
+
+        hidden_states = attn.to_out[0](hidden_states, *args)
+        hidden_states = attn.to_out[1](hidden_states)
+
+        if input_ndim == 4:
+            hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)
+        if getattr(attn, "residual_connection", False):
+            hidden_states = hidden_states + residual
+        hidden_states = hidden_states / getattr(attn, "rescale_output_factor", 1.0)
+        return hidden_states

@@ -1,0 +1,214 @@
+// extern "C" surface of libdsc_b200.so (see include/dsc_b200.h for the contract of every entry point).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "dsc_internal.h"
+
+namespace dsc {
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+  return static_cast<int>(e);
+}
+
+int sm_count_cached() {
+  static thread_local int dev_cached = -1, sms = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != dev_cached) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms = v;
+    dev_cached = dev;
+  }
+  return sms;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Shared validation of one [B,H,rows,D] operand viewed inside [B,rows,H*D].
+static int check_bhxd(const char* name, const void* ptr, const int64_t s[4], int D) {
+  if (!ptr || !s) return fail(DSC_ERR_INVALID_ARGUMENT, "%s: null pointer", name);
+  if (!aligned16(ptr)) return fail(DSC_ERR_LAYOUT, "%s: base pointer must be 16-byte aligned", name);
+  if (s[3] != 1) return fail(DSC_ERR_LAYOUT, "%s: stride(D) must be 1 (got %lld)", name, (long long)s[3]);
+  if (s[1] != D) return fail(DSC_ERR_LAYOUT, "%s: stride(H) must equal D=%d (got %lld)", name, D, (long long)s[1]);
+  if (s[2] % 8 != 0 || s[0] % 8 != 0)
+    return fail(DSC_ERR_LAYOUT, "%s: stride(B)=%lld and stride(rows)=%lld must be multiples of 8 elements", name,
+                (long long)s[0], (long long)s[2]);
+  return DSC_OK;
+}
+
+static int check_dims(int B, int H, int L, int D, int S, int dtype) {
+  if (B <= 0 || H <= 0 || L <= 0 || D <= 0 || S <= 0)
+    return fail(DSC_ERR_INVALID_ARGUMENT, "non-positive dimension (B=%d H=%d L=%d D=%d S=%d)", B, H, L, D, S);
+  if (dtype != DSC_DTYPE_F16 && dtype != DSC_DTYPE_BF16) return fail(DSC_ERR_INVALID_ARGUMENT, "bad dtype code %d", dtype);
+  if (heads_per_group(D) == 0) return fail(DSC_ERR_UNSUPPORTED, "head dim %d not in {40,64,80,128,160}", D);
+  if (S > DSC_MAX_KEYS) return fail(DSC_ERR_UNSUPPORTED, "S=%d keys > %d", S, DSC_MAX_KEYS);
+  return DSC_OK;
+}
+
+static void fill_partition(XattnParams& p, int B, int H, int L, int D, int S) {
+  const int G = heads_per_group(D);
+  p.B = B;
+  p.H = H;
+  p.L = L;
+  p.S = S;
+  p.n_hg = (H + G - 1) / G;
+  p.n_sl = (L + 15) / 16;
+  p.total = static_cast<long long>(B) * p.n_hg * p.n_sl;
+}
+
+}  // namespace dsc
+
+using namespace dsc;
+
+extern "C" {
+
+int dsc_version(void) { return DSC_VERSION; }
+
+const char* dsc_last_error(void) { return g_err; }
+
+int dsc_sm_count(void) { return sm_count_cached(); }
+
+int dsc_xattn_workspace_bytes(int B, int H, int L, int D, int S, size_t* out) {
+  if (!out) return fail(DSC_ERR_INVALID_ARGUMENT, "out is null");
+  if (B <= 0 || H <= 0 || L <= 0 || D <= 0 || S <= 0) return fail(DSC_ERR_INVALID_ARGUMENT, "non-positive dimension");
+  *out = static_cast<size_t>(kWorkspaceHeader) + sizeof(double) * 2 * kMaxPartials;
+  return DSC_OK;
+}
+
+int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const int64_t k_str[4],
+                    const void* mask_or_null, int B, int H, int L, int D, int S, float scale, int dtype,
+                    void* workspace, void* stream) {
+  int rc = check_dims(B, H, L, D, S, dtype);
+  if (rc) return rc;
+  if (mask_or_null) return fail(DSC_ERR_UNSUPPORTED, "additive attention masks are not implemented");
+  if (!workspace) return fail(DSC_ERR_INVALID_ARGUMENT, "workspace is null");
+  if ((rc = check_bhxd("q", q, q_str, D))) return rc;
+  if ((rc = check_bhxd("k", k, k_str, D))) return rc;
+  XattnParams p{};
+  fill_partition(p, B, H, L, D, S);
+  p.q = q;
+  p.k = k;
+  p.q_sb = q_str[0];
+  p.q_sl = q_str[2];
+  p.k_sb = k_str[0];
+  p.k_ss = k_str[2];
+  p.scale = scale;
+  p.ws = static_cast<Workspace*>(workspace);
+  if (stats_grid(p.total) > kMaxPartials) return fail(DSC_ERR_UNSUPPORTED, "grid exceeds workspace partial slots");
+  cudaError_t e = run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_stats");
+}
+
+int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],
+                      const int64_t v_str[4], const float* W, int Bw, const float* sigma_dev_or_null, float sigma_host,
+                      const void* workspace, void* out, const int64_t o_str[3], int B, int H, int L, int D, int S,
+                      float scale, int dtype, void* stream) {
+  int rc = check_dims(B, H, L, D, S, dtype);
+  if (rc) return rc;
+  if (!workspace || !W || !out || !o_str) return fail(DSC_ERR_INVALID_ARGUMENT, "null pointer");
+  if (Bw <= 0 || B % Bw != 0)
+    return fail(DSC_ERR_SHAPE, "region map batch Bw=%d must divide the attention batch B=%d", Bw, B);
+  if ((rc = check_bhxd("q", q, q_str, D))) return rc;
+  if ((rc = check_bhxd("k", k, k_str, D))) return rc;
+  if ((rc = check_bhxd("v", v, v_str, D))) return rc;
+  if (!aligned16(out) || o_str[2] != 1 || o_str[1] % 8 != 0 || o_str[0] % 8 != 0)
+    return fail(DSC_ERR_LAYOUT, "out: need 16-byte base, unit inner stride, row/batch strides multiple of 8");
+  if ((reinterpret_cast<uintptr_t>(W) & 3) != 0) return fail(DSC_ERR_LAYOUT, "W must be 4-byte aligned");
+  XattnParams p{};
+  fill_partition(p, B, H, L, D, S);
+  p.q = q;
+  p.k = k;
+  p.v = v;
+  p.out = out;
+  p.W = W;
+  p.Bw = Bw;
+  p.sigma_dev = sigma_dev_or_null;
+  p.sigma_host = sigma_host;
+  p.scale = scale;
+  p.q_sb = q_str[0];
+  p.q_sl = q_str[2];
+  p.k_sb = k_str[0];
+  p.k_ss = k_str[2];
+  p.v_sb = v_str[0];
+  p.v_ss = v_str[2];
+  p.o_sb = o_str[0];
+  p.o_sl = o_str[1];
+  p.ws = const_cast<Workspace*>(static_cast<const Workspace*>(workspace));
+  cudaError_t e = run_forward(p, D, dtype, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_forward");
+}
+
+int dsc_region_downsample(const uint8_t* maps, int R, int Hpx, int Wpx, int w_r, int h_r, uint8_t* ds,
+                          uint32_t* any_set, void* stream) {
+  if (R < 0 || Hpx <= 0 || Wpx <= 0 || w_r <= 0 || h_r <= 0) return fail(DSC_ERR_INVALID_ARGUMENT, "bad size");
+  if (R == 0) return DSC_OK;
+  if (!maps || !ds || !any_set) return fail(DSC_ERR_INVALID_ARGUMENT, "null pointer");
+  cudaError_t e = run_region_downsample(maps, R, Hpx, Wpx, w_r, h_r, ds, any_set, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_region_downsample");
+}
+
+int dsc_region_accumulate(const uint8_t* ds, const uint32_t* any_set, int R, int L_r, const double* weight,
+                          const double* mask_outsides, const int32_t* span_region, const int32_t* span_start,
+                          const int32_t* span_len, int n_spans, int n_tok, float* W_out, void* stream) {
+  if (R < 0 || L_r <= 0 || n_tok <= 0 || n_spans < 0) return fail(DSC_ERR_INVALID_ARGUMENT, "bad size");
+  if (!W_out) return fail(DSC_ERR_INVALID_ARGUMENT, "W_out is null");
+  if (n_spans > 0 && (!ds || !any_set || !weight || !mask_outsides || !span_region || !span_start || !span_len))
+    return fail(DSC_ERR_INVALID_ARGUMENT, "null pointer");
+  cudaError_t e = run_region_accumulate(ds, any_set, R, L_r, weight, mask_outsides, span_region, span_start, span_len,
+                                        n_spans, n_tok, W_out, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_region_accumulate");
+}
+
+int dsc_dpmpp2m_step(float* x, const void* eps_uc, float* den_prev, void* unet_in_next_or_null, int64_t n_elem,
+                     double sigma_prev, double sigma, double sigma_next, double cfg, int first, int dtype,
+                     void* stream) {
+  if (!x || !eps_uc || !den_prev) return fail(DSC_ERR_INVALID_ARGUMENT, "null pointer");
+  if (n_elem < 0) return fail(DSC_ERR_INVALID_ARGUMENT, "negative n_elem");
+  if (dtype != DSC_DTYPE_F16 && dtype != DSC_DTYPE_BF16) return fail(DSC_ERR_INVALID_ARGUMENT, "bad dtype code %d", dtype);
+  if (!(sigma > 0.0) || sigma_next < 0.0) return fail(DSC_ERR_INVALID_ARGUMENT, "need sigma > 0 and sigma_next >= 0");
+  StepCoef c{};
+  const bool first_order = first != 0 || sigma_next == 0.0;
+  if (!first_order && !(sigma_prev > sigma)) return fail(DSC_ERR_INVALID_ARGUMENT, "need sigma_prev > sigma");
+  // t = -ln(sigma); h = t_next - t = ln(sigma / sigma_next)
+  double c_x, c_d;
+  if (sigma_next == 0.0) {
+    c_x = 0.0;  // sigma_next / sigma
+    c_d = 1.0;  // -expm1(-inf)
+  } else {
+    const double h = log(sigma / sigma_next);
+    c_x = sigma_next / sigma;
+    c_d = -expm1(-h);
+  }
+  double c_den = 1.0, c_prev = 0.0;
+  if (!first_order) {
+    const double h = log(sigma / sigma_next);
+    const double h_last = log(sigma_prev / sigma);
+    const double r = h_last / h;
+    c_den = 1.0 + 1.0 / (2.0 * r);
+    c_prev = -1.0 / (2.0 * r);
+  }
+  c.c_x = static_cast<float>(c_x);
+  c.c_d = static_cast<float>(c_d);
+  c.c_den = static_cast<float>(c_den);
+  c.c_prev = static_cast<float>(c_prev);
+  c.sigma = static_cast<float>(sigma);
+  c.cfg = static_cast<float>(cfg);
+  c.c_in_next = static_cast<float>(1.0 / sqrt(sigma_next * sigma_next + 1.0));
+  cudaError_t e = run_dpmpp2m_step(x, eps_uc, den_prev, unet_in_next_or_null, n_elem, c, dtype,
+                                   static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_dpmpp2m_step");
+}
+
+}  // extern "C"

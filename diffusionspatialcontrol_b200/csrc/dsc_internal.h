@@ -1,0 +1,60 @@
+// Internal (non-ABI) declarations shared by the kernels and the C-ABI translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dsc_b200.h"
+
+namespace dsc {
+
+// Head of the workspace == dsc_xattn_stats_t (include/dsc_b200.h); per-CTA fp64 partials follow.
+using Workspace = dsc_xattn_stats_t;
+constexpr int kWorkspaceHeader = 64;
+constexpr int kMaxPartials = 1024;
+static_assert(sizeof(Workspace) <= kWorkspaceHeader, "workspace header");
+
+struct XattnParams {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  const float* W;
+  const float* sigma_dev;
+  float sigma_host;
+  float scale;
+  long long q_sb, q_sl;  // element strides: batch, row (heads are contiguous D-wide column groups)
+  long long k_sb, k_ss;
+  long long v_sb, v_ss;
+  long long o_sb, o_sl;
+  int B, H, L, S, Bw;
+  int n_hg;         // head groups per batch row
+  int n_sl;         // 16-row slices per (batch, head-group)
+  long long total;  // B * n_hg * n_sl
+  Workspace* ws;
+};
+
+int sm_count_cached();
+int heads_per_group(int D);  // 0 if D is unsupported
+int stats_grid(long long total);
+cudaError_t run_stats(const XattnParams& p, int D, int dtype, cudaStream_t st);
+cudaError_t run_forward(const XattnParams& p, int D, int dtype, cudaStream_t st);
+
+cudaError_t run_region_downsample(const uint8_t* maps, int R, int Hpx, int Wpx, int w_r, int h_r, uint8_t* ds,
+                                  uint32_t* any_set, cudaStream_t st);
+cudaError_t run_region_accumulate(const uint8_t* ds, const uint32_t* any_set, int R, int L_r, const double* weight,
+                                  const double* mask_outsides, const int32_t* span_region, const int32_t* span_start,
+                                  const int32_t* span_len, int n_spans, int n_tok, float* W_out, cudaStream_t st);
+
+struct StepCoef {
+  float c_x;       // sigma_next / sigma
+  float c_d;       // -expm1(-h)
+  float c_den;     // 1 + 1/(2r)   (1 for the first-order update)
+  float c_prev;    // -1/(2r)      (0 for the first-order update)
+  float sigma;     // den = x - sigma * eps
+  float cfg;
+  float c_in_next;  // 1/sqrt(sigma_next^2 + 1)
+};
+cudaError_t run_dpmpp2m_step(float* x, const void* eps_uc, float* den_prev, void* unet_in_next, long long n_elem,
+                             const StepCoef& c, int dtype, cudaStream_t st);
+
+}  // namespace dsc

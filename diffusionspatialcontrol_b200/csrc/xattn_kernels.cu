@@ -1,0 +1,564 @@
+// Region-masked cross-attention for SD-1.5 cross-attention layers on B200 (sm_100a).
+//
+//   pass 1  xattn_stats_kernel    a = scale*QK^T over the whole call -> sum / sum-of-squares -> std
+//   pass 2  xattn_forward_kernel  recompute QK^T, + beta*W, softmax (registers + quad shuffles), PV
+//
+// Replaces scaled_dot_product_attention_regionstate (reference source/modules/attention_modify.py:74-103)
+// with weight_func = w*sigma*qk.std() (reference source/app.py:1004).
+//
+// Data layout in HBM (no copies, exactly what the reference processor produces, attention_modify.py:471-474):
+//   Q, O : [B, L, H*D]  (heads are column groups of one row)       K, V : [B, S, H*D]      W : fp32 [Bw, L, S]
+//
+// Decomposition.  The call is cut into "slices" of 16 query rows x one head-group (G heads, G*D = 320
+// or 256 columns = 640/512 contiguous bytes per row).  A persistent CTA (one per SM, 8 warps) owns a
+// contiguous range of slices of the (batch, head-group)-major slice list; the K and V head-group of the
+// current batch row stay resident in shared memory, each warp streams its own slices:
+//   TMA bulk copies (cp.async.bulk, one per row -> padded pitch, ldmatrix conflict-free) + mbarrier,
+//   QK^T and PV on the tensor cores (mma.sync m16n8k16 / m16n8k8, fp32 accumulate),
+//   the 77-key score rows live in registers (10 n-tiles x 4), softmax row reductions are quad shuffles,
+//   the W tile is read once per slice and reused by all heads of the group,
+//   O overwrites the warp's Q slice in shared memory and leaves through TMA bulk stores.
+#include "dsc_device.cuh"
+#include "dsc_internal.h"
+
+namespace dsc {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <int D>
+struct Tile {
+  static_assert(D == 40 || D == 64 || D == 80 || D == 128 || D == 160, "unsupported head dim");
+  static constexpr int G = (D == 40) ? 8 : (D == 64) ? 5 : (D == 80) ? 4 : 2;  // heads per group
+  static constexpr int GW = G * D;                                             // columns per group
+  static constexpr int PITCH = GW * 2 + 16;  // bytes; == 16 (mod 128) -> ldmatrix rows hit distinct banks
+  static constexpr int KV_ROWS = 80;         // keys padded to 10 n-tiles
+  static constexpr int NT = 10;
+  static constexpr int WARPS = 8;
+  static constexpr int ROWS = 16;  // query rows per slice (one m16 tile per warp)
+  static constexpr int KV_BYTES = KV_ROWS * PITCH;
+  static constexpr int QS_BYTES = ROWS * PITCH;
+  static constexpr int WS_BYTES = ROWS * KV_ROWS * 4;
+  static constexpr int DCH = (D > 80) ? D / 2 : D;  // PV is done in column chunks of <= 80
+  static constexpr int NCH = D / DCH;
+  static constexpr int ND = DCH / 8;
+  static_assert((GW * 2) % 128 == 0, "pitch rule");
+  // forward: K + V + 8 x (Q slice + W slice) + 9 mbarriers
+  static constexpr int FWD_SMEM = 2 * KV_BYTES + WARPS * (QS_BYTES + WS_BYTES) + 128;
+  // stats: K + 8 x 2 Q slices + 17 mbarriers
+  static constexpr int STATS_SMEM = KV_BYTES + WARPS * 2 * QS_BYTES + 256;
+};
+
+// ---------------------------------------------------------------------------------------------
+// S tile = Q_h K_h^T for one warp: 16 rows x 80 keys, fp32 accumulators in the mma C layout
+//   acc[j][0..1] -> row g,   keys 8j+2t, 8j+2t+1        acc[j][2..3] -> row g+8      (g = lane/4, t = lane%4)
+// q_base / k_base: shared addresses of row 0 of the slice / of K, already offset to the head's columns.
+template <typename T, int D>
+__device__ __forceinline__ void qk_tile(float (&acc)[10][4], uint32_t q_base, uint32_t k_base, int lane) {
+  constexpr int PITCH = Tile<D>::PITCH;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  // A (x4): lanes 0-7 rows 0-7 | 8-15 rows 8-15 | 16-23 rows 0-7, +8 cols | 24-31 rows 8-15, +8 cols
+  const uint32_t a_addr = q_base + ((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16;
+  // B (x4): lanes 0-7 keys 0-7 | 8-15 keys 0-7, +8 cols | 16-23 keys 8-15 | 24-31 keys 8-15, +8 cols
+  const uint32_t b_addr = k_base + ((lane & 7) + ((lane >> 4) & 1) * 8) * PITCH + ((lane >> 3) & 1) * 16;
+#pragma unroll
+  for (int ks = 0; ks < D / 16; ++ks) {
+    uint32_t a[4];
+    ldsm_x4(a, a_addr + ks * 32);
+#pragma unroll
+    for (int jp = 0; jp < 5; ++jp) {
+      uint32_t b[4];
+      ldsm_x4(b, b_addr + jp * 16 * PITCH + ks * 32);
+      Mma<T>::k16(acc[2 * jp], a, b[0], b[1]);
+      Mma<T>::k16(acc[2 * jp + 1], a, b[2], b[3]);
+    }
+  }
+  if constexpr (D % 16 == 8) {  // k8 tail (D = 40): no zero padding of the contraction dim
+    constexpr int k0 = (D / 16) * 16;
+    uint32_t a2[2];
+    ldsm_x2(a2, q_base + (lane & 15) * PITCH + k0 * 2);
+#pragma unroll
+    for (int q4 = 0; q4 < 2; ++q4) {
+      uint32_t b[4];
+      ldsm_x4(b, k_base + (q4 * 32 + lane) * PITCH + k0 * 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Mma<T>::k8(acc[4 * q4 + i], a2[0], a2[1], b[i]);
+    }
+    uint32_t b2[2];
+    ldsm_x2(b2, k_base + (64 + (lane & 15)) * PITCH + k0 * 2);
+    Mma<T>::k8(acc[8], a2[0], a2[1], b2[0]);
+    Mma<T>::k8(acc[9], a2[0], a2[1], b2[1]);
+  }
+}
+
+// O chunk = P V_h[:, chunk] : 16 rows x (ND*8) columns.  pa = P in the mma A layout (5 k-steps of 16 keys).
+template <typename T, int D>
+__device__ __forceinline__ void pv_tile(float (&o)[Tile<D>::ND][4], const uint32_t (&pa)[5][4], uint32_t v_base,
+                                        int lane) {
+  constexpr int PITCH = Tile<D>::PITCH;
+  constexpr int ND = Tile<D>::ND;
+#pragma unroll
+  for (int n = 0; n < ND; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  // B (x4.trans): lanes 0-7 keys 0-7 | 8-15 keys 8-15 | 16-23 keys 0-7, +8 cols | 24-31 keys 8-15, +8 cols
+  const uint32_t v_addr = v_base + ((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16;
+#pragma unroll
+  for (int kk = 0; kk < 5; ++kk) {
+#pragma unroll
+    for (int np = 0; np < ND / 2; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(b, v_addr + kk * 16 * PITCH + np * 32);
+      Mma<T>::k16(o[2 * np], pa[kk], b[0], b[1]);
+      Mma<T>::k16(o[2 * np + 1], pa[kk], b[2], b[3]);
+    }
+    if constexpr (ND % 2 == 1) {
+      uint32_t b2[2];
+      ldsm_x2_t(b2, v_base + (kk * 16 + (lane & 15)) * PITCH + (ND - 1) * 16);
+      Mma<T>::k16(o[ND - 1], pa[kk], b2[0], b2[1]);
+    }
+  }
+}
+
+// Segment bookkeeping shared by both passes: the slice list is (batch, head-group)-major.
+struct Seg {
+  int b, hg, nheads;
+  long long end;  // first slice index after this segment, clipped to the CTA's range
+};
+template <int D>
+__device__ __forceinline__ Seg seg_of(long long idx, long long cta_end, int n_sl, int n_hg, int H) {
+  Seg s;
+  const long long seg = idx / n_sl;
+  s.b = static_cast<int>(seg / n_hg);
+  s.hg = static_cast<int>(seg % n_hg);
+  s.nheads = min(Tile<D>::G, H - s.hg * Tile<D>::G);
+  const long long e = (seg + 1) * n_sl;
+  s.end = e < cta_end ? e : cta_end;
+  return s;
+}
+
+// =============================================================================================
+// pass 1
+// =============================================================================================
+template <typename T, int D>
+__global__ void __launch_bounds__(256, 1) xattn_stats_kernel(const XattnParams p) {
+  using TL = Tile<D>;
+  constexpr int PITCH = TL::PITCH;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sK = smem_u32(smem);
+  const uint32_t sQ = sK + TL::KV_BYTES + warp * 2 * TL::QS_BYTES;  // two stages per warp
+  const uint32_t bars = sK + TL::KV_BYTES + TL::WARPS * 2 * TL::QS_BYTES;
+  const uint32_t kbar = bars;
+  const uint32_t qbar = bars + 8 + warp * 16;  // [stage]
+
+  // zero the K pad rows (keys S..79): their scores are exactly 0 and drop out of both sums
+  for (int i = tid; i < (TL::KV_ROWS - p.S) * (PITCH / 16); i += 256)
+    reinterpret_cast<uint4*>(smem + p.S * PITCH)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(kbar, 1);
+    for (int w = 0; w < TL::WARPS; ++w) {
+      mbar_init(bars + 8 + w * 16, 1);
+      mbar_init(bars + 8 + w * 16 + 8, 1);
+    }
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  const long long total = p.total;
+  const long long cta_begin = total * blockIdx.x / gridDim.x;
+  const long long cta_end = total * (blockIdx.x + 1) / gridDim.x;
+  const T* __restrict__ q = reinterpret_cast<const T*>(p.q);
+  const T* __restrict__ k = reinterpret_cast<const T*>(p.k);
+  const uint64_t pol_q = policy_evict_last();  // Q is read again by pass 2: ask L2 to keep it
+
+  double dsum = 0.0, dsq = 0.0;
+  uint32_t it = 0, kphase = 0;
+
+  for (long long idx = cta_begin; idx < cta_end;) {
+    const Seg sg = seg_of<D>(idx, cta_end, p.n_sl, p.n_hg, p.H);
+    const uint32_t row_bytes = sg.nheads * D * 2;
+    __syncthreads();  // every warp is done with the previous K
+    if (tid == 0) mbar_arrive_expect_tx(kbar, row_bytes * p.S);
+    __syncthreads();
+    for (int r = tid; r < p.S; r += 256)
+      bulk_g2s(sK + r * PITCH, k + sg.b * p.k_sb + r * p.k_ss + sg.hg * TL::GW, row_bytes, kbar);
+
+    auto issue = [&](long long sl_idx, uint32_t stage) {
+      const int l0 = static_cast<int>(sl_idx % p.n_sl) * TL::ROWS;
+      const int rows = min(TL::ROWS, p.L - l0);
+      const uint32_t bar = qbar + stage * 8;
+      if (lane == 0) mbar_arrive_expect_tx(bar, rows * row_bytes);
+      __syncwarp();
+      if (lane < rows)
+        bulk_g2s_hint(sQ + stage * TL::QS_BYTES + lane * PITCH,
+                      q + sg.b * p.q_sb + static_cast<long long>(l0 + lane) * p.q_sl + sg.hg * TL::GW, row_bytes, bar,
+                      pol_q);
+    };
+
+    const long long first = idx + warp;
+    if (first < sg.end) issue(first, it & 1);
+    bool k_ready = false;
+    for (long long sl = first; sl < sg.end; sl += TL::WARPS) {
+      if (sl + TL::WARPS < sg.end) issue(sl + TL::WARPS, (it + 1) & 1);
+      mbar_wait(qbar + (it & 1) * 8, (it >> 1) & 1);
+      if (!k_ready) {
+        mbar_wait(kbar, kphase);
+        k_ready = true;
+      }
+      const int l0 = static_cast<int>(sl % p.n_sl) * TL::ROWS;
+      const int rows = min(TL::ROWS, p.L - l0);
+      const uint32_t qs = sQ + (it & 1) * TL::QS_BYTES;
+      const float m0 = ((lane >> 2) < rows) ? 1.f : 0.f;      // row g valid
+      const float m1 = ((lane >> 2) + 8 < rows) ? 1.f : 0.f;  // row g+8 valid
+      for (int h = 0; h < sg.nheads; ++h) {
+        float acc[10][4];
+        qk_tile<T, D>(acc, qs + h * D * 2, sK + h * D * 2, lane);
+        float fs = 0.f, fq = 0.f;
+        if (rows == TL::ROWS) {
+#pragma unroll
+          for (int j = 0; j < 10; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              fs += acc[j][i];
+              fq = fmaf(acc[j][i], acc[j][i], fq);
+            }
+        } else {  // tail slice: rows beyond L hold stale shared memory
+#pragma unroll
+          for (int j = 0; j < 10; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float v = (i < 2 ? m0 : m1) != 0.f ? acc[j][i] : 0.f;
+              fs += v;
+              fq = fmaf(v, v, fq);
+            }
+        }
+        dsum += static_cast<double>(fs);
+        dsq += static_cast<double>(fq);
+      }
+      __syncwarp();  // all lanes have consumed this stage before it is refilled
+      ++it;
+    }
+    kphase ^= 1;
+    idx = sg.end;
+  }
+
+  // CTA partial (raw, unscaled) in a fixed order -> workspace; the last CTA folds all partials.
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    dsq += __shfl_xor_sync(0xffffffffu, dsq, o);
+  }
+  __shared__ double red[2 * 8];
+  __shared__ unsigned int s_last;
+  if (lane == 0) {
+    red[warp] = dsum;
+    red[8 + warp] = dsq;
+  }
+  __syncthreads();
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
+  if (tid == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      a += red[w];
+      b += red[8 + w];
+    }
+    partials[2 * blockIdx.x] = a;
+    partials[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (unsigned int i = lane; i < gridDim.x; i += 32) {  // fixed assignment + fixed tree = deterministic
+      a += __ldcg(partials + 2 * i);
+      b += __ldcg(partials + 2 * i + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      const double sc = static_cast<double>(p.scale);
+      const double n = static_cast<double>(p.B) * p.H * static_cast<double>(p.L) * p.S;
+      const double sum = a * sc, sumsq = b * sc * sc;
+      const double mean = sum / n;
+      double var = (n > 1.0) ? (sumsq - sum * mean) / (n - 1.0) : nan("");
+      if (var < 0.0) var = 0.0;
+      p.ws->std_unbiased = static_cast<float>(sqrt(var));
+      p.ws->mean = static_cast<float>(mean);
+      p.ws->sum = sum;
+      p.ws->sumsq = sumsq;
+      p.ws->n = n;
+      p.ws->n_partials = gridDim.x;
+      __threadfence();
+      p.ws->ticket = 0u;  // reusable without a memset
+    }
+  }
+}
+
+// =============================================================================================
+// pass 2
+// =============================================================================================
+template <typename T, int D>
+__global__ void __launch_bounds__(256, 1) xattn_forward_kernel(const XattnParams p) {
+  using TL = Tile<D>;
+  constexpr int PITCH = TL::PITCH;
+  constexpr int ND = TL::ND;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t sK = smem_u32(smem);
+  const uint32_t sV = sK + TL::KV_BYTES;
+  const uint32_t sQ = sV + TL::KV_BYTES + warp * (TL::QS_BYTES + TL::WS_BYTES);
+  const uint32_t sW = sQ + TL::QS_BYTES;
+  const float* wsm = reinterpret_cast<const float*>(smem + 2 * TL::KV_BYTES + warp * (TL::QS_BYTES + TL::WS_BYTES) +
+                                                     TL::QS_BYTES);
+  unsigned char* qsm = smem + 2 * TL::KV_BYTES + warp * (TL::QS_BYTES + TL::WS_BYTES);
+  const uint32_t bars = sK + 2 * TL::KV_BYTES + TL::WARPS * (TL::QS_BYTES + TL::WS_BYTES);
+  const uint32_t kvbar = bars;
+  const uint32_t qbar = bars + 8 + warp * 8;
+
+  // zero the pad rows (keys S..79) of K and V once: padded scores are exactly 0 (then -inf through the
+  // bias), padded P columns multiply zeros.  The row copies below never touch them.
+  for (int i = tid; i < (TL::KV_ROWS - p.S) * (PITCH / 16); i += 256) {
+    reinterpret_cast<uint4*>(smem + p.S * PITCH)[i] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(smem + TL::KV_BYTES + p.S * PITCH)[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) {
+    mbar_init(kvbar, 1);
+    for (int w = 0; w < TL::WARPS; ++w) mbar_init(bars + 8 + w * 8, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  const long long total = p.total;
+  const long long cta_begin = total * blockIdx.x / gridDim.x;
+  const long long cta_end = total * (blockIdx.x + 1) / gridDim.x;
+  const T* __restrict__ q = reinterpret_cast<const T*>(p.q);
+  const T* __restrict__ k = reinterpret_cast<const T*>(p.k);
+  const T* __restrict__ v = reinterpret_cast<const T*>(p.v);
+  T* __restrict__ out = reinterpret_cast<T*>(p.out);
+  const uint64_t pol_stream = policy_evict_first();  // Q and W are dead after this pass
+
+  // beta = sigma * std(a), folded with log2(e): softmax runs in the exp2 domain
+  const float sigma = p.sigma_dev ? __ldg(p.sigma_dev) : p.sigma_host;
+  const float beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2e;
+  const float scale_l2 = p.scale * kLog2e;
+  const int w_rep = p.B / p.Bw;
+
+  uint32_t it = 0, kvphase = 0;
+
+  for (long long idx = cta_begin; idx < cta_end;) {
+    const Seg sg = seg_of<D>(idx, cta_end, p.n_sl, p.n_hg, p.H);
+    const uint32_t row_bytes = sg.nheads * D * 2;
+    const float* Wb = p.W + static_cast<long long>(sg.b / w_rep) * p.L * p.S;
+    __syncthreads();  // every warp is done with the previous K/V
+    if (tid == 0) mbar_arrive_expect_tx(kvbar, 2 * row_bytes * p.S);
+    __syncthreads();
+    for (int r = tid; r < 2 * p.S; r += 256) {
+      const int rr = r < p.S ? r : r - p.S;
+      if (r < p.S)
+        bulk_g2s(sK + rr * PITCH, k + sg.b * p.k_sb + rr * p.k_ss + sg.hg * TL::GW, row_bytes, kvbar);
+      else
+        bulk_g2s(sV + rr * PITCH, v + sg.b * p.v_sb + rr * p.v_ss + sg.hg * TL::GW, row_bytes, kvbar);
+    }
+
+    auto issue = [&](long long sl_idx) {
+      const int l0 = static_cast<int>(sl_idx % p.n_sl) * TL::ROWS;
+      const int rows = min(TL::ROWS, p.L - l0);
+      const float* wsrc = Wb + static_cast<long long>(l0) * p.S;
+      const uint32_t wbytes = rows * p.S * 4;
+      const bool w_bulk = ((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0;
+      if (lane == 0) mbar_arrive_expect_tx(qbar, rows * row_bytes + (w_bulk ? wbytes : 0));
+      __syncwarp();
+      if (lane < rows)
+        bulk_g2s_hint(sQ + lane * PITCH, q + sg.b * p.q_sb + static_cast<long long>(l0 + lane) * p.q_sl + sg.hg * TL::GW,
+                      row_bytes, qbar, pol_stream);
+      if (w_bulk) {
+        if (lane == 16) bulk_g2s_hint(sW, wsrc, wbytes, qbar, pol_stream);
+      } else {  // odd tail / unaligned W: plain loads (visible to this warp after the __syncwarp below)
+        float* wdst = const_cast<float*>(wsm);
+        for (int i = lane; i < rows * p.S; i += 32) wdst[i] = __ldg(wsrc + i);
+      }
+      __syncwarp();
+    };
+
+    const long long first = idx + warp;
+    if (first < sg.end) issue(first);
+    bool kv_ready = false;
+    for (long long sl = first; sl < sg.end; sl += TL::WARPS) {
+      mbar_wait(qbar, it & 1);
+      ++it;
+      if (!kv_ready) {
+        mbar_wait(kvbar, kvphase);
+        kv_ready = true;
+      }
+      const int l0 = static_cast<int>(sl % p.n_sl) * TL::ROWS;
+      const int rows = min(TL::ROWS, p.L - l0);
+
+      // beta*W in the accumulator layout, shared by all heads of the group; columns >= S get -inf
+      float bw[10][4];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = 8 * j + 2 * t + (i & 1);
+          const int row = g + 8 * (i >> 1);
+          bw[j][i] = (col < p.S) ? wsm[row * p.S + col] * beta_l2 : -INFINITY;
+        }
+      }
+
+      for (int h = 0; h < sg.nheads; ++h) {
+        float acc[10][4];
+        qk_tile<T, D>(acc, sQ + h * D * 2, sK + h * D * 2, lane);
+        // logits (log2 domain), row max
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          acc[j][0] = fmaf(acc[j][0], scale_l2, bw[j][0]);
+          acc[j][1] = fmaf(acc[j][1], scale_l2, bw[j][1]);
+          acc[j][2] = fmaf(acc[j][2], scale_l2, bw[j][2]);
+          acc[j][3] = fmaf(acc[j][3], scale_l2, bw[j][3]);
+          mx0 = fmaxf(mx0, fmaxf(acc[j][0], acc[j][1]));
+          mx1 = fmaxf(mx1, fmaxf(acc[j][2], acc[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        // p = 2^(s - max), row sums, pack to the input dtype as the A operand of PV
+        float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pa[5][4];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          const float p0 = ex2_approx(acc[j][0] - mx0), p1 = ex2_approx(acc[j][1] - mx0);
+          const float p2 = ex2_approx(acc[j][2] - mx1), p3 = ex2_approx(acc[j][3] - mx1);
+          sum0 += p0 + p1;
+          sum1 += p2 + p3;
+          pa[j >> 1][(j & 1) * 2 + 0] = Mma<T>::pack(p0, p1);
+          pa[j >> 1][(j & 1) * 2 + 1] = Mma<T>::pack(p2, p3);
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+
+        __syncwarp();  // Q_h has been consumed by every lane: its columns may now be overwritten by O_h
+#pragma unroll
+        for (int c = 0; c < TL::NCH; ++c) {
+          float o[ND][4];
+          pv_tile<T, D>(o, pa, sV + (h * D + c * TL::DCH) * 2, lane);
+          unsigned char* orow0 = qsm + g * PITCH + (h * D + c * TL::DCH + 2 * t) * 2;
+          unsigned char* orow1 = orow0 + 8 * PITCH;
+#pragma unroll
+          for (int n = 0; n < ND; ++n) {
+            *reinterpret_cast<uint32_t*>(orow0 + n * 16) = Mma<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
+            *reinterpret_cast<uint32_t*>(orow1 + n * 16) = Mma<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
+          }
+        }
+      }
+
+      // O slice: shared -> global through the TMA, one row per lane
+      fence_proxy_async();
+      __syncwarp();
+      if (lane < rows) {
+        bulk_s2g(out + sg.b * p.o_sb + static_cast<long long>(l0 + lane) * p.o_sl + sg.hg * TL::GW, sQ + lane * PITCH,
+                 row_bytes);
+        bulk_commit();
+        bulk_wait_read0();  // the slice buffer may be refilled once the TMA has read it
+      }
+      __syncwarp();
+      if (sl + TL::WARPS < sg.end) issue(sl + TL::WARPS);
+    }
+    kvphase ^= 1;
+    idx = sg.end;
+  }
+  bulk_wait0();  // global writes of this thread's bulk stores are complete before the CTA retires
+}
+
+// =============================================================================================
+// host-side launchers
+// =============================================================================================
+static int grid_for(long long total) {
+  const int sms = sm_count_cached();
+  long long want = (total + 3) / 4;  // at least ~4 slices per CTA before spreading further
+  if (want < 1) want = 1;
+  return static_cast<int>(want < sms ? want : sms);
+}
+
+template <typename T, int D>
+static cudaError_t launch_stats(const XattnParams& p, cudaStream_t st) {
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_stats_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Tile<D>::STATS_SMEM);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  xattn_stats_kernel<T, D><<<grid_for(p.total), 256, Tile<D>::STATS_SMEM, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <typename T, int D>
+static cudaError_t launch_forward(const XattnParams& p, cudaStream_t st) {
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_forward_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Tile<D>::FWD_SMEM);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  xattn_forward_kernel<T, D><<<grid_for(p.total), 256, Tile<D>::FWD_SMEM, st>>>(p);
+  return cudaGetLastError();
+}
+
+int heads_per_group(int D) {
+  switch (D) {
+    case 40: return Tile<40>::G;
+    case 64: return Tile<64>::G;
+    case 80: return Tile<80>::G;
+    case 128: return Tile<128>::G;
+    case 160: return Tile<160>::G;
+    default: return 0;
+  }
+}
+
+int stats_grid(long long total) { return grid_for(total); }
+
+#define DSC_DISPATCH_D(FN, T)                         \
+  switch (D) {                                        \
+    case 40: return FN<T, 40>(p, st);                 \
+    case 64: return FN<T, 64>(p, st);                 \
+    case 80: return FN<T, 80>(p, st);                 \
+    case 128: return FN<T, 128>(p, st);               \
+    case 160: return FN<T, 160>(p, st);               \
+    default: return cudaErrorInvalidValue;            \
+  }
+
+cudaError_t run_stats(const XattnParams& p, int D, int dtype, cudaStream_t st) {
+  if (dtype == 0) {
+    DSC_DISPATCH_D(launch_stats, __half)
+  } else {
+    DSC_DISPATCH_D(launch_stats, __nv_bfloat16)
+  }
+}
+
+cudaError_t run_forward(const XattnParams& p, int D, int dtype, cudaStream_t st) {
+  if (dtype == 0) {
+    DSC_DISPATCH_D(launch_forward, __half)
+  } else {
+    DSC_DISPATCH_D(launch_forward, __nv_bfloat16)
+  }
+}
+
+}  // namespace dsc

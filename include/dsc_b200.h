@@ -1,0 +1,130 @@
+/* libdsc_b200.so -- C ABI of the B200-native region-masked cross-attention path.
+ *
+ * Drop-in boundary for the hot path of duongve13112002/DiffusionSpatialControl.  Every entry point
+ * takes plain pointers and sizes (device pointers unless marked HOST), enqueues its work on the
+ * given CUDA stream and returns immediately: 0 = ok, <0 = DSC_ERR_* (invalid argument /
+ * unsupported configuration, nothing was launched), >0 = cudaError_t from the launch.  No entry
+ * point synchronises the host, throws, or keeps global mutable state (dsc_last_error is
+ * thread-local).  `stream` is a cudaStream_t passed as void*.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   dsc_xattn_stats + dsc_xattn_forward
+ *        source/modules/attention_modify.py:74-103  scaled_dot_product_attention_regionstate
+ *        source/app.py:1004                         weight_func = w * sigma * qk.std()
+ *        (called from AttnProcessor2_0.__call__, source/modules/attention_modify.py:479-481)
+ *   dsc_region_downsample + dsc_region_accumulate
+ *        source/modules/encode_region_map_function.py:49-53 (resize / ==max / *S / -S')
+ *        source/modules/encode_region_map_function.py:57-69 (+= into the token columns)
+ *   dsc_dpmpp2m_step
+ *        k_diffusion.sampling.sample_dpmpp_2m as driven by source/modules/model_k_diffusion.py:1091-1175
+ *        with the denoiser scalings of source/modules/external_k_diffusion.py:95-98,109-114 and the
+ *        CFG combine of model_k_diffusion.py:1162-1166
+ */
+#ifndef DSC_B200_H_
+#define DSC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSC_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#define DSC_DTYPE_F16 0
+#define DSC_DTYPE_BF16 1
+
+#define DSC_OK 0
+#define DSC_ERR_INVALID_ARGUMENT (-1) /* null pointer, non-positive size, bad dtype code */
+#define DSC_ERR_UNSUPPORTED (-2)      /* valid request outside what the kernels implement */
+#define DSC_ERR_LAYOUT (-3)           /* stride / alignment contract violated */
+#define DSC_ERR_SHAPE (-4)            /* shape contract violated (e.g. B % Bw != 0), mirrors the reference raising */
+
+#define DSC_MAX_KEYS 80 /* S (text tokens) supported by the tuned kernels; SD-1.5 uses 77 */
+
+int dsc_version(void);
+
+/* Message for the last non-zero return on the calling thread ("" if none). */
+const char* dsc_last_error(void);
+
+/* Number of SMs the persistent kernels will be sized for on the current device (148 on B200). */
+int dsc_sm_count(void);
+
+/* Bytes of device workspace one attention call needs (stats + per-CTA partials + ticket).
+ * The workspace must be zero-filled ONCE after allocation; calls leave it reusable. */
+int dsc_xattn_workspace_bytes(int B, int H, int L, int D, int S, size_t* out /*HOST*/);
+
+/* Pass 1.  a = scale * Q K^T over the whole call; writes to `workspace`
+ *   {float std (unbiased, N-1), float mean, double sum, double sumsq, double n}
+ * at the offsets of dsc_xattn_stats_t below.  Deterministic (fixed-order fp64 combine).
+ *
+ * q: [B,H,L,D] addressed through q_str[4] (ELEMENT strides of B,H,L,D); k: [B,H,S,D] through k_str.
+ * Layout contract (DSC_ERR_LAYOUT otherwise): stride(D)==1, stride(H)==D, stride(L) and stride(B)
+ * multiples of 8 elements, base pointers 16-byte aligned -- i.e. the [B, L, H*D] projection output
+ * viewed as heads, which is exactly what the reference processor produces
+ * (attention_modify.py:471-474).  D in {40,64,80,128,160}; 1 <= S <= DSC_MAX_KEYS.
+ * mask_or_null: additive attention mask; only NULL is implemented (DSC_ERR_UNSUPPORTED otherwise;
+ * SD-1.5 never passes one). */
+int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4] /*HOST*/, const int64_t k_str[4] /*HOST*/,
+                    const void* mask_or_null, int B, int H, int L, int D, int S, float scale, int dtype,
+                    void* workspace, void* stream);
+
+/* Pass 2.  out = softmax(scale * Q K^T + beta * W) V with beta = sigma * std, std read from
+ * `workspace` (written by dsc_xattn_stats earlier on the same stream).
+ *
+ * W: fp32 [Bw, L, S] contiguous region-weight map; row b of the batch uses W[b / (B / Bw)]
+ *    (the batch-major repeat_interleave of attention_modify.py:96-99); requires B % Bw == 0.
+ * sigma: if sigma_dev_or_null != NULL it points to ONE fp32 on the device (no host sync),
+ *    else sigma_host is used.
+ * out: [B, L, H*D] addressed through o_str[3] (element strides of B, L, and 1 for the last dim).
+ * v: [B,H,S,D] through v_str, same layout contract as k. */
+int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t q_str[4] /*HOST*/,
+                      const int64_t k_str[4] /*HOST*/, const int64_t v_str[4] /*HOST*/, const float* W, int Bw,
+                      const float* sigma_dev_or_null, float sigma_host, const void* workspace, void* out,
+                      const int64_t o_str[3] /*HOST*/, int B, int H, int L, int D, int S, float scale, int dtype,
+                      void* stream);
+
+/* Layout of the head of the workspace (read-only for callers). */
+typedef struct dsc_xattn_stats_t {
+  uint32_t ticket; /* internal, returns to 0 */
+  uint32_t n_partials;
+  float std_unbiased;
+  float mean;
+  double sum;
+  double sumsq;
+  double n;
+} dsc_xattn_stats_t;
+
+/* Region map, step 1 (encode_region_map_function.py:49-51): for each of R region maps
+ * (uint8 [R, Hpx, Wpx], 255 = outside) compute bin = (map < 255), the OpenCV INTER_CUBIC resize of
+ * bin to (w_r, h_r) and write ds[R, h_r*w_r] uint8 in {0,1}, plus any_set[R] (uint32, 1 if any
+ * output pixel is 1 -- the `== max` rule needs it).  any_set must be zero on entry.  Bit-exact
+ * against cv2 for integer scale factors (see oracle/region_map.py). */
+int dsc_region_downsample(const uint8_t* maps, int R, int Hpx, int Wpx, int w_r, int h_r, uint8_t* ds,
+                          uint32_t* any_set, void* stream);
+
+/* Region map, step 2 (encode_region_map_function.py:51-69): W_out[L_r, n_tok] fp32 (zeroed by this
+ * call), then for each span i in order:  W[:, start_i : start_i+len_i] = fp32(fp64(W) + val) with
+ * val = (ds[region_i] == max(ds[region_i]) && weight != 0) ? weight : -mask_outsides  (fp64).
+ * span_* are int32 device arrays of length n_spans, weight/mask_outsides fp64 device arrays [R]. */
+int dsc_region_accumulate(const uint8_t* ds, const uint32_t* any_set, int R, int L_r, const double* weight,
+                          const double* mask_outsides, const int32_t* span_region, const int32_t* span_start,
+                          const int32_t* span_len, int n_spans, int n_tok, float* W_out, void* stream);
+
+/* One DPM-Solver++(2M) step in VE (k-diffusion) space, fused with the denoiser scalings and CFG:
+ *   eps   = eps_u + cfg * (eps_c - eps_u)            eps_uc = [2, n_elem] (uncond rows first), dtype
+ *   den   = x - sigma * eps
+ *   d     = first ? den : (1 + 1/(2r)) * den - 1/(2r) * den_prev
+ *   x     = (sigma_next / sigma) * x - expm1(-h) * d          (x, den_prev: fp32, updated in place)
+ *   unet_in_next[2, n_elem] = x / sqrt(sigma_next^2 + 1)       (dtype; both CFG halves; may be NULL)
+ * with h = ln(sigma/sigma_next), r = ln(sigma_prev/sigma)/h; first!=0 or sigma_next==0 selects the
+ * first-order update.  Scalars are HOST values; coefficients are formed in fp64 on the host. */
+int dsc_dpmpp2m_step(float* x, const void* eps_uc, float* den_prev, void* unet_in_next_or_null, int64_t n_elem,
+                     double sigma_prev, double sigma, double sigma_next, double cfg, int first, int dtype,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSC_B200_H_ */

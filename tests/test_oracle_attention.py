@@ -1,0 +1,87 @@
+"""The oracle restatement of the attention path is pinned (a) against the UNMODIFIED reference module
+executed in this container and (b) against the committed golden vectors (which were produced by that
+module, scripts/gen_golden.py) so the pin travels to machines without /root/reference."""
+import glob
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import attention as oa
+from oracle import ref_loader
+
+from .helpers import make_qkv, synthetic_w, weight_func
+
+needs_ref = pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not present")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "attn_*.npz"))))
+def test_oracle_matches_golden(path):
+    z = np.load(path)
+    H = int(z["heads"])
+    q, k, v = (torch.from_numpy(z[n]).float() for n in "qkv")
+    B, L, HD = q.shape
+    D = HD // H
+    view = lambda t: t.view(B, -1, H, D).transpose(1, 2)
+    out = oa.region_attention(view(q), view(k), view(v), torch.from_numpy(z["W"]).clone(), torch.tensor(float(z["sigma"])))
+    out = out.transpose(1, 2).reshape(B, L, HD)
+    assert torch.equal(out, torch.from_numpy(z["out"]))  # same ops in the same order: bit-identical
+    assert float(oa.score_std(view(q), view(k))) == pytest.approx(float(z["std"]), rel=0, abs=0)
+
+
+@needs_ref
+@pytest.mark.parametrize("B,H,L,D,S,Bw,sigma", [(2, 8, 64, 160, 77, 2, 14.6), (4, 8, 256, 40, 77, 2, 0.5), (2, 4, 40, 80, 77, 1, 3.0)])
+def test_oracle_matches_reference_function(B, H, L, D, S, Bw, sigma):
+    ref = ref_loader.attention_modify()
+    q, k, v = (t.float() for t in make_qkv(B, H, L, D, S, seed=7))
+    W = synthetic_w(Bw, L, S)
+    a = ref.scaled_dot_product_attention_regionstate(q, k, v, weight_func=weight_func, region_state=W.clone(), sigma=torch.tensor(sigma))
+    b = oa.region_attention(q, k, v, W.clone(), torch.tensor(sigma))
+    assert torch.equal(a, b)
+
+
+class _Attn(nn.Module):
+    def __init__(self, C, H, D, ctx=768):
+        super().__init__()
+        self.heads, self.scale = H, D**-0.5
+        self.to_q, self.to_k, self.to_v = nn.Linear(C, H * D, bias=False), nn.Linear(ctx, H * D, bias=False), nn.Linear(ctx, H * D, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(H * D, C), nn.Dropout(0.0)])
+        self.spatial_norm = self.group_norm = self.norm_cross = None
+        self.residual_connection, self.rescale_output_factor = False, 1.0
+
+
+@needs_ref
+def test_oracle_processor_matches_reference_processor():
+    ref = ref_loader.attention_modify()
+    torch.manual_seed(3)
+    attn = _Attn(320, 8, 40)
+    hs, ctx = torch.randn(2, 256, 320), torch.randn(2, 77, 768)
+    rp = {"region_state": {256: synthetic_w(2, 256, 77)}, "sigma": torch.tensor(5.0), "weight_func": weight_func}
+    with torch.no_grad():
+        a = ref.AttnProcessor2_0()(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)
+        b = oa.processor_forward(attn, hs, ctx, rp)
+        a_self = ref.AttnProcessor2_0()(attn_self := _Attn(320, 8, 40, ctx=320), hs, region_prompt=rp)
+        b_self = oa.processor_forward(attn_self, hs, None, rp)
+    assert torch.equal(a, b) and torch.equal(a_self, b_self)
+
+
+def test_weight_func_is_whole_tensor_unbiased_std():
+    qk = torch.randn(3, 5, 7)
+    w = torch.ones(1, 5, 7)
+    n = qk.numel()
+    want = ((qk - qk.mean()) ** 2).sum().div(n - 1).sqrt() * 2.0
+    assert torch.allclose(oa.weight_func(w, 2.0, qk), want * w)
+
+
+def test_batch_coupling_is_part_of_the_contract():
+    """std spans the batch: the same sample gives a different output when its batch neighbours change."""
+    q, k, v = (t.float() for t in make_qkv(2, 8, 64, 40, 77, seed=11))
+    W = synthetic_w(1, 64, 77)
+    full = oa.region_attention(q, k, v, W.clone(), 10.0)
+    q2 = q.clone()
+    q2[1] *= 3.0
+    other = oa.region_attention(q2, k, v, W.clone(), 10.0)
+    assert not torch.allclose(full[0], other[0])
