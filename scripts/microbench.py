@@ -1,0 +1,128 @@
+"""Masked cross-attention microbench (BASELINE configs[4]): all SD-1.5 cross-attn layer shapes x batch,
+pass 1 and pass 2 timed separately with CUDA events (L2 flushed between iterations), achieved HBM GB/s
+from the ALGORITHMIC bytes of SURVEY.md 8d, next to the reference's eager-PyTorch sequence on the same
+GPU.  Usage: python scripts/microbench.py [--out gpurun_out/microbench.jsonl] [--quick]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from diffusionspatialcontrol_b200 import attention as att  # noqa: E402
+from diffusionspatialcontrol_b200._lib import check, lib  # noqa: E402
+from oracle import attention as oa  # noqa: E402  (eager reference sequence, timed as the same-GPU bar)
+
+I64x4, I64x3 = ctypes.c_int64 * 4, ctypes.c_int64 * 3
+
+
+def alg_bytes(B, H, L, D, S, Bw, e=2):
+    return e * B * H * L * D * 3 + e * B * H * S * D * 3 + 4 * Bw * L * S
+
+
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def time_calls(fns, iters, flush):
+    """Median ms of each callable in `fns`, L2 flushed before every timed call."""
+    res = [[] for _ in fns]
+    for _ in range(iters):
+        for j, fn in enumerate(fns):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            res[j].append(a.elapsed_time(b))
+    return [sorted(r)[len(r) // 2] for r in res]
+
+
+def bench_shape(B, H, L, D, S, dtype, flush, iters=30, ref=True):
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(1234 + L)
+    q = torch.randn(B, L, H * D, device=dev, dtype=dtype, generator=g)
+    k = torch.randn(B, S, H * D, device=dev, dtype=dtype, generator=g)
+    v = torch.randn(B, S, H * D, device=dev, dtype=dtype, generator=g)
+    W = torch.zeros(B, L, S, device=dev)
+    W[:, : L // 2, 1:3] = 0.5
+    W[:, L // 3 :, 6] = 0.7
+    view = lambda t: t.view(B, -1, H, D).transpose(1, 2)
+    q4, k4, v4 = view(q), view(k), view(v)
+    out = torch.empty(B, L, H * D, device=dev, dtype=dtype)
+    ws = att.get_workspace(dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dt = 0 if dtype == torch.float16 else 1
+    qs, ks, vs, os_ = I64x4(*q4.stride()), I64x4(*k4.stride()), I64x4(*v4.stride()), I64x3(*out.stride())
+    scale = 1 / math.sqrt(D)
+
+    def k1():
+        check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), qs, ks, None, B, H, L, D, S, scale, dt, ws.data_ptr(), st))
+
+    def k2():
+        check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, None, 7.0,
+                                    ws.data_ptr(), out.data_ptr(), os_, B, H, L, D, S, scale, dt, st))
+
+    def both():
+        k1()
+        k2()
+
+    sig = torch.tensor(7.0, device=dev, dtype=dtype)
+
+    def eager():
+        oa.region_attention(q4, k4, v4, W, sig)
+
+    for _ in range(5):
+        both()
+    fns = [k1, k2, both] + ([eager] if ref else [])
+    if ref:
+        eager()
+    t = time_calls(fns, iters, flush)
+    nbytes = alg_bytes(B, H, L, D, S, B)
+    peak, how = peak_gbs()
+    rec = {
+        "B": B, "H": H, "L": L, "D": D, "S": S, "dtype": str(dtype).split(".")[-1],
+        "ms_stats": t[0], "ms_forward": t[1], "ms_both": t[2], "ms_sum": t[0] + t[1],
+        "alg_bytes": nbytes, "gbs": nbytes / (t[2] * 1e-3) / 1e9, "frac": nbytes / (t[2] * 1e-3) / 1e9 / peak,
+        "peak_gbs": peak, "peak": how,
+    }
+    if ref:
+        rec["ms_eager_fp16_reference_sequence"] = t[3]
+        rec["speedup_vs_eager"] = t[3] / t[2]
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "microbench.jsonl"))
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--batches", default="2,8,16,32")
+    ap.add_argument("--no-ref", action="store_true")
+    a = ap.parse_args()
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    shapes = [(4096, 40), (1024, 80), (256, 160), (64, 160)]
+    batches = [16] if a.quick else [int(x) for x in a.batches.split(",")]
+    with open(a.out, "w") as f:
+        for dtype in ([torch.float16] if a.quick else [torch.float16, torch.bfloat16]):
+            for B in batches:
+                for L, D in shapes:
+                    rec = bench_shape(B, 8, L, D, 77, dtype, flush, iters=15 if a.quick else 30, ref=not a.no_ref)
+                    line = json.dumps(rec)
+                    print(line, flush=True)
+                    f.write(line + "\n")
+
+
+if __name__ == "__main__":
+    main()
