@@ -90,3 +90,12 @@ def processor_forward(attn, hidden_states, encoder_hidden_states=None, region_pr
     if getattr(attn, "residual_connection", False):
         out = out + residual
     return out / getattr(attn, "rescale_output_factor", 1.0)
+
+
+class OracleAttnProcessor:
+    """The restated reference processor behind the diffusers processor protocol (same kwarg names as
+    attention_modify.py:414-424), so the CPU baseline can drive the same UNet host module."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+                 region_prompt=None, ip_adapter_masks=None):
+        return processor_forward(attn, hidden_states, encoder_hidden_states, region_prompt)
