@@ -137,7 +137,7 @@ def txt2img_latents(
 ) -> torch.Tensor:
     """The 25-step loop of model_k_diffusion.py:1027-1175 (latents only; no VAE)."""
     train = sd15_train_sigmas()
-    sigmas = get_sigmas_karras(steps, train[0].item(), train[-1].item()).to(noise.dtype)
+    sigmas = get_sigmas_karras(steps, train[0].item(), train[-1].item()).to(noise)
     x = noise * (sigmas[0] ** 2 + 1) ** 0.5
 
     def model(x_, sigma):
