@@ -2,6 +2,8 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "dsc_internal.h"
 
@@ -32,6 +34,13 @@ int sm_count_cached() {
     dev_cached = dev;
   }
   return sms;
+}
+
+// DSC_XATTN_IMPL=mma forces the legacy mma.sync kernels; default: tcgen05 where it is implemented.
+static bool use_tc5(int D) {
+  const char* e = getenv("DSC_XATTN_IMPL");
+  if (e && strcmp(e, "mma") == 0) return false;
+  return tc5_supports(D);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -107,7 +116,8 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
   p.scale = scale;
   p.ws = static_cast<Workspace*>(workspace);
   if (stats_grid(p.total) > kMaxPartials) return fail(DSC_ERR_UNSUPPORTED, "grid exceeds workspace partial slots");
-  cudaError_t e = run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
+  cudaError_t e = use_tc5(D) ? run_stats_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
+                             : run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_stats");
 }
 
@@ -146,7 +156,8 @@ int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t
   p.o_sb = o_str[0];
   p.o_sl = o_str[1];
   p.ws = const_cast<Workspace*>(static_cast<const Workspace*>(workspace));
-  cudaError_t e = run_forward(p, D, dtype, static_cast<cudaStream_t>(stream));
+  cudaError_t e = use_tc5(D) ? run_forward_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
+                             : run_forward(p, D, dtype, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_forward");
 }
 

@@ -39,6 +39,11 @@ int stats_grid(long long total);
 cudaError_t run_stats(const XattnParams& p, int D, int dtype, cudaStream_t st);
 cudaError_t run_forward(const XattnParams& p, int D, int dtype, cudaStream_t st);
 
+// tcgen05 / TMEM implementation of the same two passes (xattn_tc5.cu), D in {40, 80}
+bool tc5_supports(int D);
+cudaError_t run_stats_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st);
+cudaError_t run_forward_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st);
+
 cudaError_t run_region_downsample(const uint8_t* maps, int R, int Hpx, int Wpx, int w_r, int h_r, uint8_t* ds,
                                   uint32_t* any_set, cudaStream_t st);
 cudaError_t run_region_accumulate(const uint8_t* ds, const uint32_t* any_set, int R, int L_r, const double* weight,

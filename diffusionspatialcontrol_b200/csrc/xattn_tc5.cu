@@ -1,0 +1,514 @@
+// Region-masked cross-attention on the 5th-generation tensor cores (tcgen05.mma + TMEM), D in {40, 80}.
+//
+// Same two passes as xattn_kernels.cu (pass 1: std of scale*QK^T, pass 2: softmax(scale*QK^T + beta*W) V),
+// replacing scaled_dot_product_attention_regionstate (reference source/modules/attention_modify.py:74-103)
+// and weight_func (reference source/app.py:1004).  Why a second implementation: the legacy mma.sync path
+// is tensor-pipe / issue bound on B200 (HMMA measured at 554 TFLOP/s, about the rate the whole call needs);
+// tcgen05 is ~4x faster and takes the operand traffic off the LSU, which leaves HBM as the bound.
+//
+// Work unit = tile of 128 query rows x one head group (G*D = 160 columns: 4 heads at D=40, 2 at D=80).
+// One persistent CTA per SM owns a contiguous range of the (batch, head-group)-major tile list.
+//   warp 8        producer : TMA bulk copies (cp.async.bulk) of Q rows and the W tile into a 2/3-stage smem
+//                            ring, TMA bulk stores of finished O tiles
+//   warp 9        MMA      : one elected thread issues tcgen05.mma (M=128, N=80 for S=QK^T; N=48/80 for O=PV),
+//                            tcgen05.commit -> mbarrier
+//   warps 0-3/4-7 two consumer warpgroups, ONE THREAD PER QUERY ROW (TMEM lane = row); warpgroup g takes the
+//                 heads h = g (mod 2) of the tile, so QK^T/PV of one head overlaps the softmax of the other:
+//                   Q_h row: smem -> registers -> tcgen05.st (A operand lives in TMEM)
+//                   S row  : tcgen05.ld 80 fp32 -> + beta*W row (registers, shared by the heads) -> max / exp2 /
+//                            sum entirely in-thread (no shuffles) -> P (fp16/bf16) -> tcgen05.st over S (A of PV)
+//                   O row  : tcgen05.ld -> * 1/sum -> overwrite the Q_h columns of the row in smem
+// K_h and V_h^T of the head group stay resident in shared memory in the UMMA canonical K-major no-swizzle
+// layout (8-row x 16-byte core matrices; chunk pitch = LBO, 128 B between 8-row groups = SBO); the odd half
+// k-step of D=40 multiplies an explicit zero chunk.
+#include "dsc_device.cuh"
+#include "dsc_internal.h"
+#include "tc5_tmem.cuh"
+
+#include <type_traits>
+
+namespace dsc {
+
+constexpr float kLog2eT = 1.4426950408889634f;
+
+template <int D>
+struct TC {
+  static_assert(D == 40 || D == 80, "tcgen05 path: head dim 40 or 80");
+  static constexpr int G = 160 / D;
+  static constexpr int GW = 160;
+  static constexpr int PITCH = GW * 2 + 16;  // 336 B = 21 x 16 B: rows of a warp hit distinct 16-B bank groups
+  static constexpr int ROWS = 128;
+  static constexpr int QT_BYTES = ROWS * PITCH;
+  static constexpr int WT_BYTES = ROWS * DSC_MAX_KEYS * 4;
+  static constexpr int DCH = D / 8;                      // 16-byte chunks per head row
+  static constexpr int KSTEPS = (D + 15) / 16;           // k16 steps of QK^T
+  static constexpr int KCH = KSTEPS * 2;                 // chunks per head incl. the zero pad chunk
+  static constexpr int K_CH_BYTES = DSC_MAX_KEYS * 16;   // one chunk column: 80 keys x 16 B
+  static constexpr int K_HEAD_BYTES = KCH * K_CH_BYTES;
+  static constexpr int VT_CH_BYTES = D * 16;             // one chunk column of V^T: D rows x (8 keys) 16 B
+  static constexpr int VT_HEAD_BYTES = 10 * VT_CH_BYTES;
+  static constexpr int N_PV = (D == 40) ? 48 : D;        // UMMA N must be a multiple of 16
+  static constexpr int K_BYTES = G * K_HEAD_BYTES;
+  static constexpr int VT_BYTES = G * VT_HEAD_BYTES + 128;  // + slack: N=48 reads 8 rows past a 40-row chunk
+  // TMEM columns of one warpgroup
+  static constexpr int S_COL = 0;
+  static constexpr int O_COL = 80;
+  static constexpr int QA_COL = 80 + N_PV;
+  static constexpr int QA_COLS = KCH * 4;
+  static constexpr int WG_COLS = 256;
+  static_assert(QA_COL + QA_COLS <= WG_COLS, "TMEM budget");
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int FWD_STAGES = 2;
+  static constexpr int STATS_STAGES = 3;
+  static constexpr int FWD_SMEM = K_BYTES + VT_BYTES + FWD_STAGES * (QT_BYTES + WT_BYTES) + BAR_BYTES;
+  static constexpr int STATS_SMEM = K_BYTES + STATS_STAGES * QT_BYTES + BAR_BYTES;
+};
+
+constexpr int kConsumerThreads = 256;
+constexpr int kThreads = 320;
+
+// ---------------------------------------------------------------- tcgen05 plumbing
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]^T   (kind::f16: fp16 or bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle: 8x16B core matrices, LBO between the two K chunks
+// of a k16 step, SBO between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) |
+         (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46);
+}
+template <typename T>
+__host__ __device__ constexpr uint32_t idesc_f16(int n) {
+  const uint32_t fmt = std::is_same<T, __half>::value ? 0u : 1u;  // 0 = F16, 1 = BF16
+  // [4,6) D format = F32 | [7,10) A format | [10,13) B format | bits 15/16 = 0: A, B K-major | [17,23) N>>3 | [24,29) M>>4
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+struct Item {
+  int b, hg, nheads, l0, rows;
+  long long seg;
+};
+template <int D>
+__device__ __forceinline__ Item decode(long long idx, const XattnParams& p) {
+  Item it;
+  it.seg = idx / p.n_sl;
+  const int tile = static_cast<int>(idx % p.n_sl);
+  it.b = static_cast<int>(it.seg / p.n_hg);
+  it.hg = static_cast<int>(it.seg % p.n_hg);
+  it.nheads = min(TC<D>::G, p.H - it.hg * TC<D>::G);
+  it.l0 = tile * TC<D>::ROWS;
+  it.rows = min(TC<D>::ROWS, p.L - it.l0);
+  return it;
+}
+
+// K_h -> canonical [chunk][key][16 B]; V_h -> V^T canonical [key chunk][d][8 keys]; by the 256 consumer threads
+template <typename T, int D, bool STATS>
+__device__ __forceinline__ void stage_kv(unsigned char* smem, const XattnParams& p, const Item& it, int ctid) {
+  using C = TC<D>;
+  const T* __restrict__ k = reinterpret_cast<const T*>(p.k);
+  const int per_head = p.S * C::DCH;
+  for (int e = ctid; e < it.nheads * per_head; e += kConsumerThreads) {
+    const int h = e / per_head, rem = e - h * per_head;
+    const int key = rem / C::DCH, c = rem - key * C::DCH;
+    const uint4 v = *reinterpret_cast<const uint4*>(k + it.b * p.k_sb + static_cast<long long>(key) * p.k_ss +
+                                                    (it.hg * C::G + h) * D + c * 8);
+    *reinterpret_cast<uint4*>(smem + h * C::K_HEAD_BYTES + c * C::K_CH_BYTES + key * 16) = v;
+  }
+  if constexpr (!STATS) {
+    const T* __restrict__ vv = reinterpret_cast<const T*>(p.v);
+    unsigned char* sVt = smem + C::K_BYTES;
+    for (int e = ctid; e < it.nheads * per_head; e += kConsumerThreads) {
+      const int h = e / per_head, rem = e - h * per_head;
+      const int key = rem / C::DCH, c = rem - key * C::DCH;
+      const uint4 v = *reinterpret_cast<const uint4*>(vv + it.b * p.v_sb + static_cast<long long>(key) * p.v_ss +
+                                                      (it.hg * C::G + h) * D + c * 8);
+      const uint16_t* e16 = reinterpret_cast<const uint16_t*>(&v);
+      unsigned char* dst = sVt + h * C::VT_HEAD_BYTES + (key >> 3) * C::VT_CH_BYTES + (c * 8) * 16 + (key & 7) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint16_t*>(dst + j * 16) = e16[j];
+    }
+  }
+  fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+}
+
+template <typename T, int D, bool STATS>
+__global__ void __launch_bounds__(kThreads, 1) xattn_tc5_kernel(const XattnParams p) {
+  using C = TC<D>;
+  constexpr int NST = STATS ? C::STATS_STAGES : C::FWD_STAGES;
+  constexpr int STAGE_BYTES = STATS ? C::QT_BYTES : (C::QT_BYTES + C::WT_BYTES);
+  constexpr int KV_BYTES = STATS ? C::K_BYTES : (C::K_BYTES + C::VT_BYTES);
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t sStage = s0 + KV_BYTES;
+  const uint32_t bars = sStage + NST * STAGE_BYTES;
+  // barrier map (8 B each): full[NST] | odone[NST] | qrdy[2] | srdy[2] | prdy[2] | ordy[2] ; tmem ptr after
+  const uint32_t b_full = bars, b_odone = bars + 8 * NST, b_qrdy = bars + 16 * NST, b_srdy = b_qrdy + 16,
+                 b_prdy = b_qrdy + 32, b_ordy = b_qrdy + 48;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV_BYTES + NST * STAGE_BYTES + 192);
+
+  // one-time init: zero K / V^T (pad keys, pad chunk), barriers, TMEM allocation
+  for (int i = tid; i < KV_BYTES / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_odone + 8 * s, kConsumerThreads);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(b_qrdy + 8 * g, 128);
+      mbar_init(b_srdy + 8 * g, 1);
+      mbar_init(b_prdy + 8 * g, 128);
+      mbar_init(b_ordy + 8 * g, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const long long total = p.total;
+  const long long begin = total * blockIdx.x / gridDim.x;
+  const long long end = total * (blockIdx.x + 1) / gridDim.x;
+  const int n_items = static_cast<int>(end - begin);
+
+  if (warp == 8) {
+    // ============================== producer: TMA loads and stores =================================
+    const T* __restrict__ q = reinterpret_cast<const T*>(p.q);
+    T* __restrict__ out = reinterpret_cast<T*>(p.out);
+    const uint64_t pol = STATS ? policy_evict_last() : policy_evict_first();
+    auto store_tile = [&](int i) {  // O tile of item i leaves through the TMA (pass 2 only)
+      if constexpr (!STATS) {
+        const Item it = decode<D>(begin + i, p);
+        const uint32_t sQ = sStage + (i % NST) * STAGE_BYTES;
+        const uint32_t row_bytes = it.nheads * D * 2;
+        for (int r = lane; r < it.rows; r += 32)
+          bulk_s2g(out + it.b * p.o_sb + static_cast<long long>(it.l0 + r) * p.o_sl + it.hg * C::GW, sQ + r * C::PITCH,
+                   row_bytes);
+        bulk_commit();
+        bulk_wait_read0();
+        __syncwarp();
+      }
+    };
+    for (int i = 0; i < n_items; ++i) {
+      const int s = i % NST;
+      if (i >= NST) {
+        mbar_wait(b_odone + 8 * s, ((i / NST) - 1) & 1);
+        store_tile(i - NST);
+      }
+      const Item it = decode<D>(begin + i, p);
+      const uint32_t sQ = sStage + s * STAGE_BYTES;
+      const uint32_t row_bytes = it.nheads * D * 2;
+      uint32_t tx = it.rows * row_bytes;
+      const float* wsrc = nullptr;
+      uint32_t wbytes = 0;
+      if constexpr (!STATS) {
+        wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.S;
+        wbytes = it.rows * p.S * 4;
+        if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
+      }
+      if (lane == 0) mbar_arrive_expect_tx(b_full + 8 * s, tx);
+      __syncwarp();
+      for (int r = lane; r < it.rows; r += 32)
+        bulk_g2s_hint(sQ + r * C::PITCH, q + it.b * p.q_sb + static_cast<long long>(it.l0 + r) * p.q_sl + it.hg * C::GW,
+                      row_bytes, b_full + 8 * s, pol);
+      if (wbytes != 0 && lane == 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
+    }
+    for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) {
+      mbar_wait(b_odone + 8 * (i % NST), (i / NST) & 1);
+      store_tile(i);
+    }
+    bulk_wait0();
+  } else if (warp == 9) {
+    // ============================== MMA issuer (one thread) =========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = idesc_f16<T>(80);
+      constexpr uint32_t idesc_pv = idesc_f16<T>(C::N_PV);
+      uint32_t nq[2] = {0, 0}, np[2] = {0, 0};
+      for (int i = 0; i < n_items; ++i) {
+        const Item it = decode<D>(begin + i, p);
+        for (int h0 = 0; h0 < it.nheads; h0 += 2) {
+          for (int g = 0; g < 2; ++g) {  // S = Q_h K_h^T for both warpgroups
+            const int h = h0 + g;
+            if (h >= it.nheads) break;
+            mbar_wait(b_qrdy + 8 * g, nq[g] & 1);
+            ++nq[g];
+            tc_fence_after();
+            const uint32_t tw = tmem_base + g * C::WG_COLS;
+#pragma unroll
+            for (int ks = 0; ks < C::KSTEPS; ++ks)
+              umma_ts(tw + C::S_COL, tw + C::QA_COL + ks * 8,
+                      smem_desc(s0 + h * C::K_HEAD_BYTES + ks * 2 * C::K_CH_BYTES, C::K_CH_BYTES, 128), idesc_qk, ks);
+            tc_commit(b_srdy + 8 * g);
+          }
+          if constexpr (!STATS) {
+            for (int g = 0; g < 2; ++g) {  // O = P V_h
+              const int h = h0 + g;
+              if (h >= it.nheads) break;
+              mbar_wait(b_prdy + 8 * g, np[g] & 1);
+              ++np[g];
+              tc_fence_after();
+              const uint32_t tw = tmem_base + g * C::WG_COLS;
+#pragma unroll
+              for (int kk = 0; kk < 5; ++kk)
+                umma_ts(tw + C::O_COL, tw + C::S_COL + kk * 8,
+                        smem_desc(s0 + C::K_BYTES + h * C::VT_HEAD_BYTES + kk * 2 * C::VT_CH_BYTES, C::VT_CH_BYTES, 128),
+                        idesc_pv, kk);
+              tc_commit(b_ordy + 8 * g);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== consumers: one thread per query row =============================
+    const int g = warp >> 2;                       // warpgroup
+    const int row = (warp & 3) * 32 + lane;        // tile row == TMEM lane
+    const int ctid = tid;                          // 0..255
+    const uint32_t tw = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * C::WG_COLS;
+    const float sigma = STATS ? 0.f : (p.sigma_dev ? __ldg(p.sigma_dev) : p.sigma_host);
+    const float beta_l2 = STATS ? 0.f : sigma * __ldcg(&p.ws->std_unbiased) * kLog2eT;
+    const float scale_l2 = p.scale * kLog2eT;
+    if constexpr (D % 16 == 8) {  // zero the K-padding columns of the A operand once
+      uint32_t z[4] = {0, 0, 0, 0};
+      tmem_st_x4(tw + C::QA_COL + D / 2, z);
+      tc_wait_st();
+    }
+    double dsum = 0.0, dsq = 0.0;
+    uint32_t n_s = 0, n_o = 0;
+    long long cur_seg = -1;
+    for (int i = 0; i < n_items; ++i) {
+      const Item it = decode<D>(begin + i, p);
+      const int s = i % NST;
+      if (it.seg != cur_seg) {  // new (batch, head group): restage K / V^T (all MMAs on the old ones have retired)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        stage_kv<T, D, STATS>(smem, p, it, ctid);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        cur_seg = it.seg;
+      }
+      mbar_wait(b_full + 8 * s, (i / NST) & 1);
+      unsigned char* qrow = smem + KV_BYTES + s * STAGE_BYTES + row * C::PITCH;
+      float bw[STATS ? 1 : 80];
+      if constexpr (!STATS) {  // beta*W row (log2 domain), shared by this row's heads; keys >= S get -inf
+        const float* wt = reinterpret_cast<const float*>(smem + KV_BYTES + s * STAGE_BYTES + C::QT_BYTES) + row * p.S;
+        const float* wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.S;
+        const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(it.rows * p.S * 4)) & 15) == 0;
+        const float* wr = bulk ? wt : (wsrc + static_cast<long long>(row < it.rows ? row : 0) * p.S);
+#pragma unroll
+        for (int j = 0; j < 80; ++j) bw[j] = (j < p.S) ? wr[j] * beta_l2 : -INFINITY;
+      }
+      for (int h = g; h < it.nheads; h += 2) {
+        // ---- Q_h row -> TMEM (A operand of S = Q K^T)
+        {
+          uint32_t qw[D / 2];
+          const uint4* src = reinterpret_cast<const uint4*>(qrow + h * D * 2);
+#pragma unroll
+          for (int c = 0; c < C::DCH; ++c) {
+            const uint4 v = src[c];
+            qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
+          }
+          if constexpr (D == 40) {
+            tmem_st_x16(tw + C::QA_COL, qw);
+            tmem_st_x4(tw + C::QA_COL + 16, qw + 16);
+          } else {
+            tmem_st_x32(tw + C::QA_COL, qw);
+            tmem_st_x8(tw + C::QA_COL + 32, qw + 32);
+          }
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(b_qrdy + 8 * g);
+        }
+        // ---- S row
+        mbar_wait(b_srdy + 8 * g, n_s & 1);
+        ++n_s;
+        tc_fence_after();
+        float sc[80];
+        tmem_ld_x64(tw + C::S_COL, reinterpret_cast<uint32_t*>(sc));
+        tmem_ld_x16(tw + C::S_COL + 64, reinterpret_cast<uint32_t*>(sc) + 64);
+        tc_wait_ld();
+        if constexpr (STATS) {
+          float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 80; ++j) {
+            fs[j & 3] += sc[j];
+            fq[j & 3] = fmaf(sc[j], sc[j], fq[j & 3]);
+          }
+          if (row < it.rows) {  // pad keys contribute exact zeros; pad rows hold stale data
+            dsum += static_cast<double>((fs[0] + fs[1]) + (fs[2] + fs[3]));
+            dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
+          }
+        } else {
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int j = 0; j < 80; ++j) {
+            sc[j] = fmaf(sc[j], scale_l2, bw[j]);
+            mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+          }
+          const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          float sm[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t pw[40];
+#pragma unroll
+          for (int j = 0; j < 40; ++j) {
+            const float p0 = ex2_approx(sc[2 * j] - m), p1 = ex2_approx(sc[2 * j + 1] - m);
+            sm[j & 3] += p0 + p1;
+            pw[j] = Mma<T>::pack(p0, p1);
+          }
+          const float inv = 1.f / ((sm[0] + sm[1]) + (sm[2] + sm[3]));
+          tmem_st_x32(tw + C::S_COL, pw);  // P aliases S (all of S is in registers by now)
+          tmem_st_x8(tw + C::S_COL + 32, pw + 32);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(b_prdy + 8 * g);
+          // ---- O row
+          mbar_wait(b_ordy + 8 * g, n_o & 1);
+          ++n_o;
+          tc_fence_after();
+          float o[D];
+          if constexpr (D == 40) {
+            tmem_ld_x32(tw + C::O_COL, reinterpret_cast<uint32_t*>(o));
+            tmem_ld_x8(tw + C::O_COL + 32, reinterpret_cast<uint32_t*>(o) + 32);
+          } else {
+            tmem_ld_x64(tw + C::O_COL, reinterpret_cast<uint32_t*>(o));
+            tmem_ld_x16(tw + C::O_COL + 64, reinterpret_cast<uint32_t*>(o) + 64);
+          }
+          tc_wait_ld();
+          uint4* dst = reinterpret_cast<uint4*>(qrow + h * D * 2);  // O_h overwrites Q_h of this row
+#pragma unroll
+          for (int c = 0; c < C::DCH; ++c) {
+            uint4 v;
+            v.x = Mma<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
+            v.y = Mma<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+            v.z = Mma<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+            v.w = Mma<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+            dst[c] = v;
+          }
+        }
+      }
+      if constexpr (!STATS) fence_proxy_async();  // O rows -> visible to the TMA store
+      tc_fence_before();
+      mbar_arrive(b_odone + 8 * s);
+    }
+    if constexpr (STATS) {
+      // CTA partial in a fixed order (warp shuffle tree, then warps 0..7 serially) -> workspace
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        dsq += __shfl_xor_sync(0xffffffffu, dsq, o);
+      }
+      double* red = reinterpret_cast<double*>(smem);  // K region is dead: every MMA has been consumed
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (lane == 0) {
+        red[warp] = dsum;
+        red[8 + warp] = dsq;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) {
+          a += red[w];
+          b += red[8 + w];
+        }
+        double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
+        partials[2 * blockIdx.x] = a;
+        partials[2 * blockIdx.x + 1] = b;
+        __threadfence();
+        const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
+        if (t == gridDim.x - 1) {  // last CTA: fold all partials in index order (deterministic)
+          __threadfence();
+          double sa = 0.0, sb = 0.0;
+          for (unsigned int c = 0; c < gridDim.x; ++c) {
+            sa += __ldcg(partials + 2 * c);
+            sb += __ldcg(partials + 2 * c + 1);
+          }
+          const double scl = static_cast<double>(p.scale);
+          const double n = static_cast<double>(p.B) * p.H * static_cast<double>(p.L) * p.S;
+          const double sum = sa * scl, sumsq = sb * scl * scl, mean = sum / n;
+          double var = (n > 1.0) ? (sumsq - sum * mean) / (n - 1.0) : nan("");
+          if (var < 0.0) var = 0.0;
+          p.ws->std_unbiased = static_cast<float>(sqrt(var));
+          p.ws->mean = static_cast<float>(mean);
+          p.ws->sum = sum;
+          p.ws->sumsq = sumsq;
+          p.ws->n = n;
+          p.ws->n_partials = gridDim.x;
+          __threadfence();
+          p.ws->ticket = 0u;
+        }
+      }
+    }
+  }
+
+  // teardown: everyone is done with TMEM before it is released
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 9) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// =============================================================================================
+template <typename T, int D, bool STATS>
+static cudaError_t launch_tc5(XattnParams p, cudaStream_t st) {
+  using C = TC<D>;
+  constexpr int smem = STATS ? C::STATS_SMEM : C::FWD_SMEM;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_tc5_kernel<T, D, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  // re-partition for 128-row tiles and 160-column head groups
+  p.n_hg = (p.H + C::G - 1) / C::G;
+  p.n_sl = (p.L + C::ROWS - 1) / C::ROWS;
+  p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
+  const int sms = sm_count_cached();
+  const int grid = static_cast<int>(p.total < sms ? p.total : sms);
+  xattn_tc5_kernel<T, D, STATS><<<grid, kThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+bool tc5_supports(int D) { return D == 40 || D == 80; }
+
+cudaError_t run_stats_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st) {
+  if (dtype == DSC_DTYPE_F16)
+    return D == 40 ? launch_tc5<__half, 40, true>(p, st) : launch_tc5<__half, 80, true>(p, st);
+  return D == 40 ? launch_tc5<__nv_bfloat16, 40, true>(p, st) : launch_tc5<__nv_bfloat16, 80, true>(p, st);
+}
+
+cudaError_t run_forward_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st) {
+  if (dtype == DSC_DTYPE_F16)
+    return D == 40 ? launch_tc5<__half, 40, false>(p, st) : launch_tc5<__half, 80, false>(p, st);
+  return D == 40 ? launch_tc5<__nv_bfloat16, 40, false>(p, st) : launch_tc5<__nv_bfloat16, 80, false>(p, st);
+}
+
+}  // namespace dsc

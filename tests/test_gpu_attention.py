@@ -18,6 +18,16 @@ from oracle import attention as oa
 from .helpers import make_qkv, rel_l2, synthetic_w, weight_func
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["tc5", "mma"])
+def impl(request, monkeypatch):
+    """Every test runs against both kernel families: tcgen05/TMEM (default where implemented: D=40, 80)
+    and the legacy mma.sync path (all head dims; also the cross-check of the first)."""
+    monkeypatch.setenv("DSC_XATTN_IMPL", request.param)
+    return request.param
+
+
 TOL = 2e-3
 STD_TOL = 1e-5
 
