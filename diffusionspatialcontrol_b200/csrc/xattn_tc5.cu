@@ -8,8 +8,11 @@
 //
 // Work unit = tile of 128 query rows x one head group (G*D = 160 columns: 4 heads at D=40, 2 at D=80).
 // One persistent CTA per SM owns a contiguous range of the (batch, head-group)-major tile list.
-//   warp 8        producer : TMA bulk copies (cp.async.bulk) of Q rows and the W tile into a 2/3-stage smem
-//                            ring, TMA bulk stores of finished O tiles
+//   warp 8        producer : TMA tensor-map loads (cp.async.bulk.tensor, 64B-swizzled 32-column boxes) of the Q
+//                            tile + one bulk copy of the W tile into a 2/3-stage smem ring, tensor-map stores of
+//                            finished O tiles.  (Measured, profiles/r1_tma_copy_rate.jsonl: a 1-D bulk copy costs
+//                            ~30 ns of TMA issue per SM whatever its size, so per-row copies cap at 1.6-3 TB/s;
+//                            one box instruction per 8 KB streams at > 5.5 TB/s.)
 //   warp 9        MMA      : one elected thread issues tcgen05.mma (M=128, N=80 for S=QK^T; N=48/80 for O=PV),
 //                            tcgen05.commit -> mbarrier
 //   warps 0-3/4-7 two consumer warpgroups, ONE THREAD PER QUERY ROW (TMEM lane = row); warpgroup g takes the
@@ -21,6 +24,8 @@
 // K_h and V_h^T of the head group stay resident in shared memory in the UMMA canonical K-major no-swizzle
 // layout (8-row x 16-byte core matrices; chunk pitch = LBO, 128 B between 8-row groups = SBO); the odd half
 // k-step of D=40 multiplies an explicit zero chunk.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "dsc_device.cuh"
 #include "dsc_internal.h"
 #include "tc5_tmem.cuh"
@@ -36,9 +41,14 @@ struct TC {
   static_assert(D == 40 || D == 80, "tcgen05 path: head dim 40 or 80");
   static constexpr int G = 160 / D;
   static constexpr int GW = 160;
-  static constexpr int PITCH = GW * 2 + 16;  // 336 B = 21 x 16 B: rows of a warp hit distinct 16-B bank groups
   static constexpr int ROWS = 128;
-  static constexpr int QT_BYTES = ROWS * PITCH;
+  // Q/O tile in smem = 5 TMA boxes of [128 rows x 32 columns (64 B)], SWIZZLE_64B: the 16-byte chunk c of
+  // row r of a box sits at r*64 + ((c ^ ((r>>1)&3)) << 4), so 8 consecutive rows (one quarter-warp of
+  // row-per-thread accesses) always hit 8 distinct 16-byte bank groups.  Dense: no padding bytes.
+  static constexpr int BOX_COLS = 32;
+  static constexpr int NBOX = GW / BOX_COLS;
+  static constexpr int BOX_BYTES = ROWS * BOX_COLS * 2;
+  static constexpr int QT_BYTES = NBOX * BOX_BYTES;
   static constexpr int WT_BYTES = ROWS * DSC_MAX_KEYS * 4;
   static constexpr int DCH = D / 8;                      // 16-byte chunks per head row
   static constexpr int KSTEPS = (D + 15) / 16;           // k16 steps of QK^T
@@ -49,7 +59,10 @@ struct TC {
   static constexpr int VT_HEAD_BYTES = 10 * VT_CH_BYTES;
   static constexpr int N_PV = (D == 40) ? 48 : D;        // UMMA N must be a multiple of 16
   static constexpr int K_BYTES = G * K_HEAD_BYTES;
-  static constexpr int VT_BYTES = G * VT_HEAD_BYTES + 128;  // + slack: N=48 reads 8 rows past a 40-row chunk
+  static constexpr int VT_BYTES_RAW = G * VT_HEAD_BYTES + 128;  // + slack: N=48 reads 8 rows past a 40-row chunk
+  // round K + V^T up so that the stage ring (swizzled boxes) starts 1024-byte aligned
+  static constexpr int VT_BYTES = ((K_BYTES + VT_BYTES_RAW + 1023) / 1024) * 1024 - K_BYTES;
+  static constexpr int K_BYTES_PAD = ((K_BYTES + 1023) / 1024) * 1024;  // stats pass: K only
   // TMEM columns of one warpgroup
   static constexpr int S_COL = 0;
   static constexpr int O_COL = 80;
@@ -61,7 +74,7 @@ struct TC {
   static constexpr int FWD_STAGES = 2;
   static constexpr int STATS_STAGES = 3;
   static constexpr int FWD_SMEM = K_BYTES + VT_BYTES + FWD_STAGES * (QT_BYTES + WT_BYTES) + BAR_BYTES;
-  static constexpr int STATS_SMEM = K_BYTES + STATS_STAGES * QT_BYTES + BAR_BYTES;
+  static constexpr int STATS_SMEM = K_BYTES_PAD + STATS_STAGES * QT_BYTES + BAR_BYTES;
 };
 
 constexpr int kConsumerThreads = 256;
@@ -78,6 +91,26 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// TMA tensor-map (3-D: columns, rows, batch) box load / store
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, "
+      "%5}], [%2], %6;" ::"r"(dst),
+      "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, int c0, int c1, int c2, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// byte offset of the 16-byte chunk `cg` (0 .. GW/8-1) of tile row `r` inside the swizzled Q/O tile
+template <int D>
+__device__ __forceinline__ uint32_t tile_chunk_off(int r, int cg) {
+  return (cg >> 2) * TC<D>::BOX_BYTES + r * 64 + (((cg & 3) ^ ((r >> 1) & 3)) << 4);
+}
+
 // D[tmem] (+)= A[tmem] * B[smem desc]^T   (kind::f16: fp16 or bf16 inputs, fp32 accumulate)
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
@@ -151,12 +184,14 @@ __device__ __forceinline__ void stage_kv(unsigned char* smem, const XattnParams&
 }
 
 template <typename T, int D, bool STATS>
-__global__ void __launch_bounds__(kThreads, 1) xattn_tc5_kernel(const XattnParams p) {
+__global__ void __launch_bounds__(kThreads, 1)
+xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_o) {
   using C = TC<D>;
   constexpr int NST = STATS ? C::STATS_STAGES : C::FWD_STAGES;
   constexpr int STAGE_BYTES = STATS ? C::QT_BYTES : (C::QT_BYTES + C::WT_BYTES);
-  constexpr int KV_BYTES = STATS ? C::K_BYTES : (C::K_BYTES + C::VT_BYTES);
-  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int KV_BYTES = STATS ? C::K_BYTES_PAD : (C::K_BYTES + C::VT_BYTES);
+  static_assert(KV_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0, "swizzled boxes need aligned bases");
+  extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sStage = s0 + KV_BYTES;
@@ -200,51 +235,53 @@ __global__ void __launch_bounds__(kThreads, 1) xattn_tc5_kernel(const XattnParam
 
   if (warp == 8) {
     // ============================== producer: TMA loads and stores =================================
-    const T* __restrict__ q = reinterpret_cast<const T*>(p.q);
-    T* __restrict__ out = reinterpret_cast<T*>(p.out);
     const uint64_t pol = STATS ? policy_evict_last() : policy_evict_first();
     auto store_tile = [&](int i) {  // O tile of item i leaves through the TMA (pass 2 only)
       if constexpr (!STATS) {
-        const Item it = decode<D>(begin + i, p);
-        const uint32_t sQ = sStage + (i % NST) * STAGE_BYTES;
-        const uint32_t row_bytes = it.nheads * D * 2;
-        for (int r = lane; r < it.rows; r += 32)
-          bulk_s2g(out + it.b * p.o_sb + static_cast<long long>(it.l0 + r) * p.o_sl + it.hg * C::GW, sQ + r * C::PITCH,
-                   row_bytes);
-        bulk_commit();
-        bulk_wait_read0();
+        if (lane == 0) {
+          const Item it = decode<D>(begin + i, p);
+          const uint32_t sQ = sStage + (i % NST) * STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < C::NBOX; ++j)  // rows >= L and columns >= H*D are clipped by the TMA
+            tma_store_3d(&tm_o, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, sQ + j * C::BOX_BYTES);
+          bulk_commit();
+          bulk_wait_read0();
+        }
         __syncwarp();
       }
     };
     for (int i = 0; i < n_items; ++i) {
       const int s = i % NST;
       if (i >= NST) {
-        mbar_wait(b_odone + 8 * s, ((i / NST) - 1) & 1);
+        if (lane == 0) mbar_wait(b_odone + 8 * s, ((i / NST) - 1) & 1);
+        __syncwarp();
         store_tile(i - NST);
       }
-      const Item it = decode<D>(begin + i, p);
-      const uint32_t sQ = sStage + s * STAGE_BYTES;
-      const uint32_t row_bytes = it.nheads * D * 2;
-      uint32_t tx = it.rows * row_bytes;
-      const float* wsrc = nullptr;
-      uint32_t wbytes = 0;
-      if constexpr (!STATS) {
-        wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.S;
-        wbytes = it.rows * p.S * 4;
-        if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
+      if (lane == 0) {
+        const Item it = decode<D>(begin + i, p);
+        const uint32_t sQ = sStage + s * STAGE_BYTES;
+        uint32_t tx = C::QT_BYTES;  // out-of-bounds parts of a box are zero-filled and still counted
+        const float* wsrc = nullptr;
+        uint32_t wbytes = 0;
+        if constexpr (!STATS) {
+          wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.S;
+          wbytes = it.rows * p.S * 4;
+          if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
+        }
+        mbar_arrive_expect_tx(b_full + 8 * s, tx);
+#pragma unroll
+        for (int j = 0; j < C::NBOX; ++j)
+          tma_load_3d(sQ + j * C::BOX_BYTES, &tm_q, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, b_full + 8 * s, pol);
+        if (wbytes != 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
       }
-      if (lane == 0) mbar_arrive_expect_tx(b_full + 8 * s, tx);
       __syncwarp();
-      for (int r = lane; r < it.rows; r += 32)
-        bulk_g2s_hint(sQ + r * C::PITCH, q + it.b * p.q_sb + static_cast<long long>(it.l0 + r) * p.q_sl + it.hg * C::GW,
-                      row_bytes, b_full + 8 * s, pol);
-      if (wbytes != 0 && lane == 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
     }
     for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) {
-      mbar_wait(b_odone + 8 * (i % NST), (i / NST) & 1);
+      if (lane == 0) mbar_wait(b_odone + 8 * (i % NST), (i / NST) & 1);
+      __syncwarp();
       store_tile(i);
     }
-    bulk_wait0();
+    if (lane == 0) bulk_wait0();
   } else if (warp == 9) {
     // ============================== MMA issuer (one thread) =========================================
     if (lane == 0) {
@@ -314,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) xattn_tc5_kernel(const XattnParam
         cur_seg = it.seg;
       }
       mbar_wait(b_full + 8 * s, (i / NST) & 1);
-      unsigned char* qrow = smem + KV_BYTES + s * STAGE_BYTES + row * C::PITCH;
+      unsigned char* qtile = smem + KV_BYTES + s * STAGE_BYTES;
       float bw[STATS ? 1 : 80];
       if constexpr (!STATS) {  // beta*W row (log2 domain), shared by this row's heads; keys >= S get -inf
         const float* wt = reinterpret_cast<const float*>(smem + KV_BYTES + s * STAGE_BYTES + C::QT_BYTES) + row * p.S;
@@ -328,10 +365,9 @@ __global__ void __launch_bounds__(kThreads, 1) xattn_tc5_kernel(const XattnParam
         // ---- Q_h row -> TMEM (A operand of S = Q K^T)
         {
           uint32_t qw[D / 2];
-          const uint4* src = reinterpret_cast<const uint4*>(qrow + h * D * 2);
 #pragma unroll
           for (int c = 0; c < C::DCH; ++c) {
-            const uint4 v = src[c];
+            const uint4 v = *reinterpret_cast<const uint4*>(qtile + tile_chunk_off<D>(row, h * C::DCH + c));
             qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
           }
           if constexpr (D == 40) {
@@ -399,15 +435,14 @@ __global__ void __launch_bounds__(kThreads, 1) xattn_tc5_kernel(const XattnParam
             tmem_ld_x16(tw + C::O_COL + 64, reinterpret_cast<uint32_t*>(o) + 64);
           }
           tc_wait_ld();
-          uint4* dst = reinterpret_cast<uint4*>(qrow + h * D * 2);  // O_h overwrites Q_h of this row
 #pragma unroll
-          for (int c = 0; c < C::DCH; ++c) {
+          for (int c = 0; c < C::DCH; ++c) {  // O_h overwrites Q_h of this row (same swizzled chunks)
             uint4 v;
             v.x = Mma<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
             v.y = Mma<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
             v.z = Mma<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
             v.w = Mma<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
-            dst[c] = v;
+            *reinterpret_cast<uint4*>(qtile + tile_chunk_off<D>(row, h * C::DCH + c)) = v;
           }
         }
       }
@@ -475,6 +510,32 @@ __global__ void __launch_bounds__(kThreads, 1) xattn_tc5_kernel(const XattnParam
 }
 
 // =============================================================================================
+// ---- host: tensor maps -------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// [B, L, cols] 16-bit tensor with element strides (sb, sl, 1) -> boxes of 32 columns x 128 rows, 64B swizzle
+static bool make_map(CUtensorMap* m, const void* base, int cols, int L, int B, long long sl, long long sb) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(sl) * 2, static_cast<cuuint64_t>(B > 1 ? sb : sl * L) * 2};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename T, int D, bool STATS>
 static cudaError_t launch_tc5(XattnParams p, cudaStream_t st) {
   using C = TC<D>;
@@ -487,13 +548,17 @@ static cudaError_t launch_tc5(XattnParams p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured_dev = dev;
   }
+  CUtensorMap tm_q, tm_o;
+  if (!make_map(&tm_q, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb)) return cudaErrorInvalidValue;
+  if (STATS) tm_o = tm_q;
+  else if (!make_map(&tm_o, p.out, p.H * D, p.L, p.B, p.o_sl, p.o_sb)) return cudaErrorInvalidValue;
   // re-partition for 128-row tiles and 160-column head groups
   p.n_hg = (p.H + C::G - 1) / C::G;
   p.n_sl = (p.L + C::ROWS - 1) / C::ROWS;
   p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
   const int sms = sm_count_cached();
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
-  xattn_tc5_kernel<T, D, STATS><<<grid, kThreads, smem, st>>>(p);
+  xattn_tc5_kernel<T, D, STATS><<<grid, kThreads, smem, st>>>(p, tm_q, tm_o);
   return cudaGetLastError();
 }
 
