@@ -42,7 +42,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source for sm_100a into libdsc_b200.so; returns its path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(CSRC / s) for s in SOURCES]]
+    extra = os.environ.get("DSC_NVCC_EXTRA", "").split()  # e.g. -DDSC_WATCHDOG for a debug build
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", str(LIB_PATH), *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

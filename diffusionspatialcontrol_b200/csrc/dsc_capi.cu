@@ -36,11 +36,14 @@ int sm_count_cached() {
   return sms;
 }
 
-// DSC_XATTN_IMPL=mma forces the legacy mma.sync kernels; default: tcgen05 where it is implemented.
+// Kernel family per call.  DSC_XATTN_IMPL=mma forces the legacy mma.sync kernels, =tc5 forces tcgen05/TMEM
+// wherever it is implemented (D = 40, 80); default "auto" = whichever measured faster on B200 for the head dim
+// (profiles/): tcgen05 at D = 40, mma.sync elsewhere.
 static bool use_tc5(int D) {
   const char* e = getenv("DSC_XATTN_IMPL");
   if (e && strcmp(e, "mma") == 0) return false;
-  return tc5_supports(D);
+  if (e && strcmp(e, "tc5") == 0) return tc5_supports(D);
+  return D == 40;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -55,18 +55,21 @@ struct TC {
   static constexpr int KCH = KSTEPS * 2;                 // chunks per head incl. the zero pad chunk
   static constexpr int K_CH_BYTES = DSC_MAX_KEYS * 16;   // one chunk column: 80 keys x 16 B
   static constexpr int K_HEAD_BYTES = KCH * K_CH_BYTES;
-  static constexpr int VT_CH_BYTES = D * 16;             // one chunk column of V^T: D rows x (8 keys) 16 B
+  // O = P [V | 1]: row D of V^T is all ones, so column D of O is the softmax row sum (of the rounded P that the
+  // tensor core actually multiplies); UMMA N must be a multiple of 16 -> 48 / 96 rows
+  static constexpr int N_PV = (D == 40) ? 48 : 96;
+  static constexpr int VT_CH_BYTES = N_PV * 16;          // one chunk column of V^T: N_PV rows x (8 keys) 16 B
   static constexpr int VT_HEAD_BYTES = 10 * VT_CH_BYTES;
-  static constexpr int N_PV = (D == 40) ? 48 : D;        // UMMA N must be a multiple of 16
   static constexpr int K_BYTES = G * K_HEAD_BYTES;
-  static constexpr int VT_BYTES_RAW = G * VT_HEAD_BYTES + 128;  // + slack: N=48 reads 8 rows past a 40-row chunk
+  static constexpr int VT_BYTES_RAW = G * VT_HEAD_BYTES;
   // round K + V^T up so that the stage ring (swizzled boxes) starts 1024-byte aligned
   static constexpr int VT_BYTES = ((K_BYTES + VT_BYTES_RAW + 1023) / 1024) * 1024 - K_BYTES;
   static constexpr int K_BYTES_PAD = ((K_BYTES + 1023) / 1024) * 1024;  // stats pass: K only
   // TMEM columns of one warpgroup
-  static constexpr int S_COL = 0;
-  static constexpr int O_COL = 80;
-  static constexpr int QA_COL = 80 + N_PV;
+  static constexpr int S_COL = 0;    // S = Q K^T (fp32, 80 columns)
+  static constexpr int P_COL = 80;   // P (16-bit pairs, 40 columns): separate from S so QK^T of the next head can start early
+  static constexpr int O_COL = 120;  // O (fp32, N_PV columns)
+  static constexpr int QA_COL = 120 + N_PV;
   static constexpr int QA_COLS = KCH * 4;
   static constexpr int WG_COLS = 256;
   static_assert(QA_COL + QA_COLS <= WG_COLS, "TMEM budget");
@@ -77,8 +80,72 @@ struct TC {
   static constexpr int STATS_SMEM = K_BYTES_PAD + STATS_STAGES * QT_BYTES + BAR_BYTES;
 };
 
+#ifdef DSC_WATCHDOG
+// Debug build only: a barrier wait that gives up after ~1 s, records who was waiting on what in the
+// workspace debug words (offset 48: {tag | block << 8 | warp << 24, parity}) and lets the kernel drain.
+__device__ unsigned int g_wd_abort = 0;
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, uint32_t tag, Workspace* ws) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (*reinterpret_cast<volatile unsigned int*>(&g_wd_abort)) return;
+    if (clock64() - t0 > (1ll << 31)) {
+      if (atomicCAS(&g_wd_abort, 0u, 1u) == 0u) {
+        unsigned int* d = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(ws) + 48);
+        d[0] = tag | (blockIdx.x << 8) | ((threadIdx.x >> 5) << 24);
+        d[1] = parity | 0x100u;
+      }
+      return;
+    }
+  }
+}
+#define MBAR_WAIT(bar, parity, tag) mbar_wait_wd(bar, parity, tag, p.ws)
+#else
+#define MBAR_WAIT(bar, parity, tag) mbar_wait(bar, parity)
+#endif
+// Service warps (producer, MMA issuers) poll with a short sleep between probes: a hot spin loop would
+// compete with the two consumer warps of the same sub-partition for issue slots and the barrier unit.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  while (true) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    __nanosleep(64);
+  }
+}
+
+#ifdef DSC_TRACE
+// Debug build only: clock64 timeline of block 0 (lane 0 of warps 0, 4, 9, 10) -> g_trace[warp][slot] = {tag, clock}.
+// The slot counter lives in a register (tr_n) so that a trace point costs one clock read and one store.
+__device__ long long g_trace[4][512][2];
+__device__ int g_trace_n[4];
+#define TRACE_DECL                                                                                        \
+  int tr_n = 0;                                                                                           \
+  const int tr_k = (blockIdx.x == 0 && (threadIdx.x & 31) == 0)                                           \
+                       ? ((threadIdx.x >> 5) == 0 ? 0 : (threadIdx.x >> 5) == 4 ? 1 : (threadIdx.x >> 5) == 9 ? 2 \
+                          : (threadIdx.x >> 5) == 10 ? 3 : -1)                                            \
+                       : -1;
+#define TRACE(tag)                                  \
+  do {                                              \
+    if (tr_k >= 0 && tr_n < 512) {                  \
+      g_trace[tr_k][tr_n][0] = (tag);               \
+      g_trace[tr_k][tr_n][1] = clock64();           \
+      g_trace_n[tr_k] = ++tr_n;                     \
+    }                                               \
+  } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(tag) do {} while (0)
+#endif
+
 constexpr int kConsumerThreads = 256;
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;       // warps 0-7 consumers | 8 producer | 9, 10 MMA issuers | 11 idle (fills the warpgroup)
+constexpr int kConsumerRegs = 224;  // setmaxnreg: 8 x 32 x 224 + 4 x 32 x 56 = 64512 <= 65536
+constexpr int kServiceRegs = 56;
 
 // ---------------------------------------------------------------- tcgen05 plumbing
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -137,47 +204,79 @@ __host__ __device__ constexpr uint32_t idesc_f16(int n) {
 }
 
 struct Item {
-  int b, hg, nheads, l0, rows;
-  long long seg;
+  int b, hg, nheads, l0, rows, tile;
 };
+// item index (32-bit: the launcher guarantees total < 2^31) -> (batch, head group, 128-row tile)
 template <int D>
-__device__ __forceinline__ Item decode(long long idx, const XattnParams& p) {
+__device__ __forceinline__ Item decode(int idx, const XattnParams& p) {
   Item it;
-  it.seg = idx / p.n_sl;
-  const int tile = static_cast<int>(idx % p.n_sl);
-  it.b = static_cast<int>(it.seg / p.n_hg);
-  it.hg = static_cast<int>(it.seg % p.n_hg);
+  const int seg = idx / p.n_sl;
+  it.tile = idx - seg * p.n_sl;
+  it.b = seg / p.n_hg;
+  it.hg = seg - it.b * p.n_hg;
   it.nheads = min(TC<D>::G, p.H - it.hg * TC<D>::G);
-  it.l0 = tile * TC<D>::ROWS;
+  it.l0 = it.tile * TC<D>::ROWS;
   it.rows = min(TC<D>::ROWS, p.L - it.l0);
   return it;
 }
 
-// K_h -> canonical [chunk][key][16 B]; V_h -> V^T canonical [key chunk][d][8 keys]; by the 256 consumer threads
+// K_h -> canonical [chunk][key][16 B]; V_h -> V^T canonical [key chunk][d][8 keys] (+ the ones row); by the 256
+// consumer threads.  Every thread owns up to MAXE 16-byte pieces; all of its loads are issued before the first
+// use (clamped addresses instead of predicated loads keep the values in registers), so the DRAM latency is paid
+// once per tensor, not once per piece.
 template <typename T, int D, bool STATS>
 __device__ __forceinline__ void stage_kv(unsigned char* smem, const XattnParams& p, const Item& it, int ctid) {
   using C = TC<D>;
-  const T* __restrict__ k = reinterpret_cast<const T*>(p.k);
+  constexpr int MAXE = (C::G * DSC_MAX_KEYS * C::DCH + kConsumerThreads - 1) / kConsumerThreads;  // 7
   const int per_head = p.S * C::DCH;
-  for (int e = ctid; e < it.nheads * per_head; e += kConsumerThreads) {
+  const int n_e = it.nheads * per_head;
+  int soff[MAXE];  // smem offset of the piece inside K (bytes); V^T offsets are derived from (h, key, c)
+  int hkc[MAXE];   // h << 16 | key << 8 | c
+  long long goff[MAXE];
+#pragma unroll
+  for (int u = 0; u < MAXE; ++u) {
+    const int e = min(ctid + u * kConsumerThreads, n_e - 1);
     const int h = e / per_head, rem = e - h * per_head;
     const int key = rem / C::DCH, c = rem - key * C::DCH;
-    const uint4 v = *reinterpret_cast<const uint4*>(k + it.b * p.k_sb + static_cast<long long>(key) * p.k_ss +
-                                                    (it.hg * C::G + h) * D + c * 8);
-    *reinterpret_cast<uint4*>(smem + h * C::K_HEAD_BYTES + c * C::K_CH_BYTES + key * 16) = v;
+    hkc[u] = (h << 16) | (key << 8) | c;
+    soff[u] = h * C::K_HEAD_BYTES + c * C::K_CH_BYTES + key * 16;
+    goff[u] = static_cast<long long>(key) * p.k_ss + (it.hg * C::G + h) * D + c * 8;
   }
-  if constexpr (!STATS) {
-    const T* __restrict__ vv = reinterpret_cast<const T*>(p.v);
-    unsigned char* sVt = smem + C::K_BYTES;
-    for (int e = ctid; e < it.nheads * per_head; e += kConsumerThreads) {
-      const int h = e / per_head, rem = e - h * per_head;
-      const int key = rem / C::DCH, c = rem - key * C::DCH;
-      const uint4 v = *reinterpret_cast<const uint4*>(vv + it.b * p.v_sb + static_cast<long long>(key) * p.v_ss +
-                                                      (it.hg * C::G + h) * D + c * 8);
-      const uint16_t* e16 = reinterpret_cast<const uint16_t*>(&v);
-      unsigned char* dst = sVt + h * C::VT_HEAD_BYTES + (key >> 3) * C::VT_CH_BYTES + (c * 8) * 16 + (key & 7) * 2;
+  const T* __restrict__ k = reinterpret_cast<const T*>(p.k) + it.b * p.k_sb;
+  uint4 kv[MAXE], vv4[STATS ? 1 : MAXE];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint16_t*>(dst + j * 16) = e16[j];
+  for (int u = 0; u < MAXE; ++u) kv[u] = __ldg(reinterpret_cast<const uint4*>(k + goff[u]));
+  if constexpr (!STATS) {  // V pieces are requested before the first K piece is consumed: one DRAM round trip
+    const T* __restrict__ vv = reinterpret_cast<const T*>(p.v) + it.b * p.v_sb;
+#pragma unroll
+    for (int u = 0; u < MAXE; ++u) {
+      const int key = (hkc[u] >> 8) & 0xff, h = hkc[u] >> 16, c = hkc[u] & 0xff;
+      vv4[u] = __ldg(reinterpret_cast<const uint4*>(vv + static_cast<long long>(key) * p.v_ss + (it.hg * C::G + h) * D + c * 8));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < MAXE; ++u)
+    if (ctid + u * kConsumerThreads < n_e) *reinterpret_cast<uint4*>(smem + soff[u]) = kv[u];
+  if constexpr (!STATS) {
+    unsigned char* sVt = smem + C::K_BYTES;
+#pragma unroll
+    for (int u = 0; u < MAXE; ++u) {
+      if (ctid + u * kConsumerThreads < n_e) {
+        const int key = (hkc[u] >> 8) & 0xff, h = hkc[u] >> 16, c = hkc[u] & 0xff;
+        unsigned char* dst = sVt + h * C::VT_HEAD_BYTES + (key >> 3) * C::VT_CH_BYTES + (c * 8) * 16 + (key & 7) * 2;
+        const uint32_t w[4] = {vv4[u].x, vv4[u].y, vv4[u].z, vv4[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<uint16_t*>(dst + (2 * j) * 16) = static_cast<uint16_t>(w[j] & 0xffffu);
+          *reinterpret_cast<uint16_t*>(dst + (2 * j + 1) * 16) = static_cast<uint16_t>(w[j] >> 16);
+        }
+      }
+    }
+    // ones row (d = D) for the valid keys: O[:, D] = sum_k P[:, k]
+    const uint16_t one = std::is_same<T, __half>::value ? 0x3C00 : 0x3F80;
+    for (int e = ctid; e < it.nheads * p.S; e += kConsumerThreads) {
+      const int h = e / p.S, key = e - h * p.S;
+      *reinterpret_cast<uint16_t*>(sVt + h * C::VT_HEAD_BYTES + (key >> 3) * C::VT_CH_BYTES + D * 16 + (key & 7) * 2) = one;
     }
   }
   fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -193,6 +292,7 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
   static_assert(KV_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0, "swizzled boxes need aligned bases");
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  TRACE_DECL
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sStage = s0 + KV_BYTES;
   const uint32_t bars = sStage + NST * STAGE_BYTES;
@@ -201,6 +301,7 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
                  b_prdy = b_qrdy + 32, b_ordy = b_qrdy + 48;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV_BYTES + NST * STAGE_BYTES + 192);
 
+  TRACE(1);
   // one-time init: zero K / V^T (pad keys, pad chunk), barriers, TMEM allocation
   for (int i = tid; i < KV_BYTES / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
@@ -216,7 +317,7 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
     }
     fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
                      smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)))
                  : "memory");
@@ -227,108 +328,123 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  TRACE(2);
 
-  const long long total = p.total;
-  const long long begin = total * blockIdx.x / gridDim.x;
-  const long long end = total * (blockIdx.x + 1) / gridDim.x;
-  const int n_items = static_cast<int>(end - begin);
+  const int begin = static_cast<int>(p.total * blockIdx.x / gridDim.x);
+  const int n_items = static_cast<int>(p.total * (blockIdx.x + 1) / gridDim.x) - begin;
 
-  if (warp == 8) {
-    // ============================== producer: TMA loads and stores =================================
-    const uint64_t pol = STATS ? policy_evict_last() : policy_evict_first();
-    auto store_tile = [&](int i) {  // O tile of item i leaves through the TMA (pass 2 only)
-      if constexpr (!STATS) {
+  if (warp >= 8) {
+    // registers go to the consumer warpgroups: the service warps need very few
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs));
+    if (warp == 8) {
+      // ============================== producer: TMA loads and stores ===============================
+      const uint64_t pol = STATS ? policy_evict_last() : policy_evict_first();
+      auto store_tile = [&](int i) {  // O tile of item i leaves through the TMA (pass 2 only)
+        if constexpr (!STATS) {
+          if (lane == 0) {
+            const Item it = decode<D>(begin + i, p);
+            const uint32_t sQ = sStage + (i % NST) * STAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < C::NBOX; ++j)  // rows >= L and columns >= H*D are clipped by the TMA
+              tma_store_3d(&tm_o, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, sQ + j * C::BOX_BYTES);
+            bulk_commit();
+            bulk_wait_read0();
+          }
+          __syncwarp();
+        }
+      };
+      for (int i = 0; i < n_items; ++i) {
+        const int s = i % NST;
+        if (i >= NST) {
+          if (lane == 0) mbar_wait_relaxed(b_odone + 8 * s, ((i / NST) - 1) & 1);
+          __syncwarp();
+          store_tile(i - NST);
+        }
         if (lane == 0) {
           const Item it = decode<D>(begin + i, p);
-          const uint32_t sQ = sStage + (i % NST) * STAGE_BYTES;
-#pragma unroll
-          for (int j = 0; j < C::NBOX; ++j)  // rows >= L and columns >= H*D are clipped by the TMA
-            tma_store_3d(&tm_o, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, sQ + j * C::BOX_BYTES);
-          bulk_commit();
-          bulk_wait_read0();
-        }
-        __syncwarp();
-      }
-    };
-    for (int i = 0; i < n_items; ++i) {
-      const int s = i % NST;
-      if (i >= NST) {
-        if (lane == 0) mbar_wait(b_odone + 8 * s, ((i / NST) - 1) & 1);
-        __syncwarp();
-        store_tile(i - NST);
-      }
-      if (lane == 0) {
-        const Item it = decode<D>(begin + i, p);
-        const uint32_t sQ = sStage + s * STAGE_BYTES;
-        uint32_t tx = C::QT_BYTES;  // out-of-bounds parts of a box are zero-filled and still counted
-        const float* wsrc = nullptr;
-        uint32_t wbytes = 0;
-        if constexpr (!STATS) {
-          wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.S;
-          wbytes = it.rows * p.S * 4;
-          if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
-        }
-        mbar_arrive_expect_tx(b_full + 8 * s, tx);
-#pragma unroll
-        for (int j = 0; j < C::NBOX; ++j)
-          tma_load_3d(sQ + j * C::BOX_BYTES, &tm_q, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, b_full + 8 * s, pol);
-        if (wbytes != 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
-      }
-      __syncwarp();
-    }
-    for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) {
-      if (lane == 0) mbar_wait(b_odone + 8 * (i % NST), (i / NST) & 1);
-      __syncwarp();
-      store_tile(i);
-    }
-    if (lane == 0) bulk_wait0();
-  } else if (warp == 9) {
-    // ============================== MMA issuer (one thread) =========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = idesc_f16<T>(80);
-      constexpr uint32_t idesc_pv = idesc_f16<T>(C::N_PV);
-      uint32_t nq[2] = {0, 0}, np[2] = {0, 0};
-      for (int i = 0; i < n_items; ++i) {
-        const Item it = decode<D>(begin + i, p);
-        for (int h0 = 0; h0 < it.nheads; h0 += 2) {
-          for (int g = 0; g < 2; ++g) {  // S = Q_h K_h^T for both warpgroups
-            const int h = h0 + g;
-            if (h >= it.nheads) break;
-            mbar_wait(b_qrdy + 8 * g, nq[g] & 1);
-            ++nq[g];
-            tc_fence_after();
-            const uint32_t tw = tmem_base + g * C::WG_COLS;
-#pragma unroll
-            for (int ks = 0; ks < C::KSTEPS; ++ks)
-              umma_ts(tw + C::S_COL, tw + C::QA_COL + ks * 8,
-                      smem_desc(s0 + h * C::K_HEAD_BYTES + ks * 2 * C::K_CH_BYTES, C::K_CH_BYTES, 128), idesc_qk, ks);
-            tc_commit(b_srdy + 8 * g);
-          }
+          const uint32_t sQ = sStage + s * STAGE_BYTES;
+          uint32_t tx = C::QT_BYTES;  // out-of-bounds parts of a box are zero-filled and still counted
+          const float* wsrc = nullptr;
+          uint32_t wbytes = 0;
           if constexpr (!STATS) {
-            for (int g = 0; g < 2; ++g) {  // O = P V_h
-              const int h = h0 + g;
-              if (h >= it.nheads) break;
-              mbar_wait(b_prdy + 8 * g, np[g] & 1);
-              ++np[g];
+            wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.S;
+            wbytes = it.rows * p.S * 4;
+            if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
+          }
+          mbar_arrive_expect_tx(b_full + 8 * s, tx);
+#pragma unroll
+          for (int j = 0; j < C::NBOX; ++j)
+            tma_load_3d(sQ + j * C::BOX_BYTES, &tm_q, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, b_full + 8 * s, pol);
+          if (wbytes != 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
+        }
+        __syncwarp();
+      }
+      for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) {
+        if (lane == 0) mbar_wait_relaxed(b_odone + 8 * (i % NST), (i / NST) & 1);
+        __syncwarp();
+        store_tile(i);
+      }
+      if (lane == 0) bulk_wait0();
+    } else if (warp <= 10) {
+      // ============================== MMA issuer of warpgroup g (one thread) =======================
+      // Mirrors the consumer pipeline: S(n+1) = Q K^T is issued while the consumers work on head n.
+      const int g = warp - 9;
+      if (lane == 0) {
+        constexpr uint32_t idesc_qk = idesc_f16<T>(80);
+        constexpr uint32_t idesc_pv = idesc_f16<T>(C::N_PV);
+        const uint32_t tw = tmem_base + g * C::WG_COLS;
+        uint32_t nq = 0, np = 0;
+        auto issue_qk = [&](int h) {
+          TRACE(20);
+          mbar_wait_relaxed(b_qrdy + 8 * g, nq & 1);
+          TRACE(21);
+          ++nq;
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < C::KSTEPS; ++ks)
+            umma_ts(tw + C::S_COL, tw + C::QA_COL + ks * 8,
+                    smem_desc(s0 + h * C::K_HEAD_BYTES + ks * 2 * C::K_CH_BYTES, C::K_CH_BYTES, 128), idesc_qk, ks);
+          tc_commit(b_srdy + 8 * g);
+          TRACE(22);
+        };
+        for (int r0 = 0; r0 < n_items;) {  // runs of consecutive tiles that share one (batch, head group)
+          const Item it0 = decode<D>(begin + r0, p);
+          const int r1 = min(n_items, r0 + p.n_sl - it0.tile);
+          const int hpw = it0.nheads > g ? (it0.nheads - g + 1) >> 1 : 0;  // heads of this warpgroup per tile: 0, 1 or 2
+          const int n_pairs = (r1 - r0) * hpw;
+          if (n_pairs > 0) issue_qk(g);
+          for (int n = 0; n < n_pairs; ++n) {
+            if (n + 1 < n_pairs) issue_qk(hpw == 2 ? g + 2 * ((n + 1) & 1) : g);
+            if constexpr (!STATS) {
+              const int h = hpw == 2 ? g + 2 * (n & 1) : g;
+              TRACE(23);
+              mbar_wait_relaxed(b_prdy + 8 * g, np & 1);
+              TRACE(24);
+              ++np;
               tc_fence_after();
-              const uint32_t tw = tmem_base + g * C::WG_COLS;
 #pragma unroll
               for (int kk = 0; kk < 5; ++kk)
-                umma_ts(tw + C::O_COL, tw + C::S_COL + kk * 8,
+                umma_ts(tw + C::O_COL, tw + C::P_COL + kk * 8,
                         smem_desc(s0 + C::K_BYTES + h * C::VT_HEAD_BYTES + kk * 2 * C::VT_CH_BYTES, C::VT_CH_BYTES, 128),
                         idesc_pv, kk);
               tc_commit(b_ordy + 8 * g);
+              TRACE(25);
             }
           }
+          r0 = r1;
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ============================== consumers: one thread per query row =============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
     const int g = warp >> 2;                       // warpgroup
     const int row = (warp & 3) * 32 + lane;        // tile row == TMEM lane
-    const int ctid = tid;                          // 0..255
+    const uint32_t row_off = row * 64, row_sw = (row >> 1) & 3;  // swizzled position of this row's chunks
+    auto chunk_off = [&](int cg) -> uint32_t {
+      return (cg >> 2) * C::BOX_BYTES + row_off + ((static_cast<uint32_t>(cg & 3) ^ row_sw) << 4);
+    };
     const uint32_t tw = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * C::WG_COLS;
     const float sigma = STATS ? 0.f : (p.sigma_dev ? __ldg(p.sigma_dev) : p.sigma_host);
     const float beta_l2 = STATS ? 0.f : sigma * __ldcg(&p.ws->std_unbiased) * kLog2eT;
@@ -340,115 +456,189 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
     }
     double dsum = 0.0, dsq = 0.0;
     uint32_t n_s = 0, n_o = 0;
-    long long cur_seg = -1;
-    for (int i = 0; i < n_items; ++i) {
-      const Item it = decode<D>(begin + i, p);
-      const int s = i % NST;
-      if (it.seg != cur_seg) {  // new (batch, head group): restage K / V^T (all MMAs on the old ones have retired)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        stage_kv<T, D, STATS>(smem, p, it, ctid);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        cur_seg = it.seg;
+
+    // Q_h row of (item i, head h): swizzled smem -> registers -> TMEM (A operand of S = Q K^T); signals the MMA warp
+    auto stage_q = [&](int i, int h) {
+      const unsigned char* qtile = smem + KV_BYTES + (i % NST) * STAGE_BYTES;
+      uint32_t qw[D / 2];
+#pragma unroll
+      for (int c = 0; c < C::DCH; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(qtile + chunk_off(h * C::DCH + c));
+        qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
       }
-      mbar_wait(b_full + 8 * s, (i / NST) & 1);
-      unsigned char* qtile = smem + KV_BYTES + s * STAGE_BYTES;
-      float bw[STATS ? 1 : 80];
-      if constexpr (!STATS) {  // beta*W row (log2 domain), shared by this row's heads; keys >= S get -inf
-        const float* wt = reinterpret_cast<const float*>(smem + KV_BYTES + s * STAGE_BYTES + C::QT_BYTES) + row * p.S;
-        const float* wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.S;
-        const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(it.rows * p.S * 4)) & 15) == 0;
-        const float* wr = bulk ? wt : (wsrc + static_cast<long long>(row < it.rows ? row : 0) * p.S);
-#pragma unroll
-        for (int j = 0; j < 80; ++j) bw[j] = (j < p.S) ? wr[j] * beta_l2 : -INFINITY;
+      if constexpr (D == 40) {
+        tmem_st_x16(tw + C::QA_COL, qw);
+        tmem_st_x4(tw + C::QA_COL + 16, qw + 16);
+      } else {
+        tmem_st_x32(tw + C::QA_COL, qw);
+        tmem_st_x8(tw + C::QA_COL + 32, qw + 32);
       }
-      for (int h = g; h < it.nheads; h += 2) {
-        // ---- Q_h row -> TMEM (A operand of S = Q K^T)
-        {
-          uint32_t qw[D / 2];
-#pragma unroll
-          for (int c = 0; c < C::DCH; ++c) {
-            const uint4 v = *reinterpret_cast<const uint4*>(qtile + tile_chunk_off<D>(row, h * C::DCH + c));
-            qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
-          }
-          if constexpr (D == 40) {
-            tmem_st_x16(tw + C::QA_COL, qw);
-            tmem_st_x4(tw + C::QA_COL + 16, qw + 16);
-          } else {
-            tmem_st_x32(tw + C::QA_COL, qw);
-            tmem_st_x8(tw + C::QA_COL + 32, qw + 32);
-          }
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(b_qrdy + 8 * g);
-        }
-        // ---- S row
-        mbar_wait(b_srdy + 8 * g, n_s & 1);
-        ++n_s;
-        tc_fence_after();
-        float sc[80];
-        tmem_ld_x64(tw + C::S_COL, reinterpret_cast<uint32_t*>(sc));
-        tmem_ld_x16(tw + C::S_COL + 64, reinterpret_cast<uint32_t*>(sc) + 64);
-        tc_wait_ld();
-        if constexpr (STATS) {
-          float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int j = 0; j < 80; ++j) {
-            fs[j & 3] += sc[j];
-            fq[j & 3] = fmaf(sc[j], sc[j], fq[j & 3]);
-          }
-          if (row < it.rows) {  // pad keys contribute exact zeros; pad rows hold stale data
-            dsum += static_cast<double>((fs[0] + fs[1]) + (fs[2] + fs[3]));
-            dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
-          }
-        } else {
-          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int j = 0; j < 80; ++j) {
-            sc[j] = fmaf(sc[j], scale_l2, bw[j]);
-            mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
-          }
-          const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-          float sm[4] = {0.f, 0.f, 0.f, 0.f};
-          uint32_t pw[40];
-#pragma unroll
-          for (int j = 0; j < 40; ++j) {
-            const float p0 = ex2_approx(sc[2 * j] - m), p1 = ex2_approx(sc[2 * j + 1] - m);
-            sm[j & 3] += p0 + p1;
-            pw[j] = Mma<T>::pack(p0, p1);
-          }
-          const float inv = 1.f / ((sm[0] + sm[1]) + (sm[2] + sm[3]));
-          tmem_st_x32(tw + C::S_COL, pw);  // P aliases S (all of S is in registers by now)
-          tmem_st_x8(tw + C::S_COL + 32, pw + 32);
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(b_prdy + 8 * g);
-          // ---- O row
-          mbar_wait(b_ordy + 8 * g, n_o & 1);
-          ++n_o;
-          tc_fence_after();
-          float o[D];
-          if constexpr (D == 40) {
-            tmem_ld_x32(tw + C::O_COL, reinterpret_cast<uint32_t*>(o));
-            tmem_ld_x8(tw + C::O_COL + 32, reinterpret_cast<uint32_t*>(o) + 32);
-          } else {
-            tmem_ld_x64(tw + C::O_COL, reinterpret_cast<uint32_t*>(o));
-            tmem_ld_x16(tw + C::O_COL + 64, reinterpret_cast<uint32_t*>(o) + 64);
-          }
-          tc_wait_ld();
-#pragma unroll
-          for (int c = 0; c < C::DCH; ++c) {  // O_h overwrites Q_h of this row (same swizzled chunks)
-            uint4 v;
-            v.x = Mma<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
-            v.y = Mma<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
-            v.z = Mma<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
-            v.w = Mma<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
-            *reinterpret_cast<uint4*>(qtile + tile_chunk_off<D>(row, h * C::DCH + c)) = v;
-          }
-        }
-      }
-      if constexpr (!STATS) fence_proxy_async();  // O rows -> visible to the TMA store
+      tc_wait_st();
       tc_fence_before();
-      mbar_arrive(b_odone + 8 * s);
+      mbar_arrive(b_qrdy + 8 * g);
+    };
+    // O row of the previous head: TMEM -> * 1/rowsum (the ones-row of V^T put the sum in column D) -> smem tile
+    auto drain_o = [&](int i, int h) {
+      if constexpr (!STATS) {
+        MBAR_WAIT(b_ordy + 8 * g, n_o & 1, 5);
+        ++n_o;
+        tc_fence_after();
+        float o[D + 8];
+        if constexpr (D == 40) {
+          tmem_ld_x32(tw + C::O_COL, reinterpret_cast<uint32_t*>(o));
+          tmem_ld_x16(tw + C::O_COL + 32, reinterpret_cast<uint32_t*>(o) + 32);
+        } else {
+          tmem_ld_x64(tw + C::O_COL, reinterpret_cast<uint32_t*>(o));
+          tmem_ld_x16(tw + C::O_COL + 64, reinterpret_cast<uint32_t*>(o) + 64);
+          tmem_ld_x8(tw + C::O_COL + 80, reinterpret_cast<uint32_t*>(o) + 80);
+        }
+        tc_wait_ld();
+        const float inv = 1.f / o[D];
+        unsigned char* qtile = smem + KV_BYTES + (i % NST) * STAGE_BYTES;
+#pragma unroll
+        for (int c = 0; c < C::DCH; ++c) {  // O_h overwrites Q_h of this row (same swizzled chunks)
+          uint4 v;
+          v.x = Mma<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
+          v.y = Mma<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+          v.z = Mma<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+          v.w = Mma<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+          *reinterpret_cast<uint4*>(qtile + chunk_off(h * C::DCH + c)) = v;
+        }
+      }
+    };
+    auto release_item = [&](int i) {  // this thread is done with the tile of item i
+      if constexpr (!STATS) fence_proxy_async();  // O rows -> visible to the TMA store
+      mbar_arrive(b_odone + 8 * (i % NST));
+    };
+
+    for (int r0 = 0; r0 < n_items;) {  // runs of consecutive tiles that share one (batch, head group)
+      const Item it0 = decode<D>(begin + r0, p);
+      const int r1 = min(n_items, r0 + p.n_sl - it0.tile);
+      // new (batch, head group): restage K / V^T (every MMA on the old ones has been consumed)
+      TRACE(3);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      stage_kv<T, D, STATS>(smem, p, it0, tid);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      TRACE(4);
+      const int hpw = it0.nheads > g ? (it0.nheads - g + 1) >> 1 : 0;  // heads of this warpgroup per tile: 0, 1 or 2
+      if (hpw == 0) {  // this warpgroup has no head in these tiles: just hand them back
+        for (int i = r0; i < r1; ++i) {
+          MBAR_WAIT(b_full + 8 * (i % NST), (i / NST) & 1, 6);
+          release_item(i);
+        }
+        r0 = r1;
+        continue;
+      }
+      const float* wbase = STATS ? nullptr : p.W + (static_cast<long long>(it0.b / (p.B / p.Bw)) * p.L) * p.S;
+      MBAR_WAIT(b_full + 8 * (r0 % NST), (r0 / NST) & 1, 7);
+      TRACE(5);
+      stage_q(r0, g);
+      TRACE(6);
+      if (STATS && hpw == 1) release_item(r0);
+      float bw[STATS ? 1 : 80];
+      for (int i = r0; i < r1; ++i) {
+        const int l0 = (it0.tile + (i - r0)) * C::ROWS;
+        const int rows = min(C::ROWS, p.L - l0);
+        for (int hi = 0; hi < hpw; ++hi) {
+          const int h = g + 2 * hi;
+          const bool first = (i == r0) && (hi == 0);
+          // ---- S row of this head
+          TRACE(10);
+          MBAR_WAIT(b_srdy + 8 * g, n_s & 1, 8);
+          TRACE(11);
+          ++n_s;
+          tc_fence_after();
+          float sc[80];
+          tmem_ld_x64(tw + C::S_COL, reinterpret_cast<uint32_t*>(sc));
+          tmem_ld_x16(tw + C::S_COL + 64, reinterpret_cast<uint32_t*>(sc) + 64);
+          tc_wait_ld();
+          TRACE(12);
+          // The previous head's O normally leaves TMEM after this head's softmax (its PV has long finished by
+          // then).  If that head was the last one of the PREVIOUS tile, its stage must be handed back before
+          // we wait for the tile after this one (2-stage ring), so it is drained first.
+          bool o_pending = !STATS && !first;
+          if (o_pending && hi == 0) {
+            drain_o(i - 1, g + 2 * (hpw - 1));
+            release_item(i - 1);
+            o_pending = false;
+          }
+          // ---- look ahead: Q of the next head goes to TMEM now, its QK^T runs under this head's softmax
+          if (hi + 1 < hpw) {
+            stage_q(i, h + 2);
+            if (STATS) release_item(i);  // pass 1 only reads Q; h + 2 is the last head of this warpgroup
+          } else if (i + 1 < r1) {
+            MBAR_WAIT(b_full + 8 * ((i + 1) % NST), ((i + 1) / NST) & 1, 9);
+            stage_q(i + 1, g);
+            if (STATS && hpw == 1) release_item(i + 1);
+          }
+          TRACE(13);
+          if constexpr (STATS) {
+            float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 80; ++j) {
+              fs[j & 3] += sc[j];
+              fq[j & 3] = fmaf(sc[j], sc[j], fq[j & 3]);
+            }
+            if (row < rows) {  // pad keys contribute exact zeros; rows beyond L were zero-filled by the TMA
+              dsum += static_cast<double>((fs[0] + fs[1]) + (fs[2] + fs[3]));
+              dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
+            }
+          } else {
+            if (hi == 0) {  // beta*W row (log2 domain), shared by this row's heads; keys >= S get -inf
+              const float* wsrc = wbase + static_cast<long long>(l0) * p.S;
+              const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.S * 4)) & 15) == 0;
+              if (bulk) {  // all loads first (independent, conflict-free: row pitch = S words), then the scaling
+                const float* wt = reinterpret_cast<const float*>(smem + KV_BYTES + (i % NST) * STAGE_BYTES + C::QT_BYTES) + row * p.S;
+                if (p.S == 77) {
+#pragma unroll
+                  for (int j = 0; j < 77; ++j) bw[j] = wt[j];
+                  bw[77] = bw[78] = bw[79] = -INFINITY;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 80; ++j) bw[j] = (j < p.S) ? wt[j] : -INFINITY;
+                }
+              } else {
+                const float* wr = wsrc + static_cast<long long>(row < rows ? row : 0) * p.S;
+#pragma unroll
+                for (int j = 0; j < 80; ++j) bw[j] = (j < p.S) ? __ldg(wr + j) : -INFINITY;
+              }
+#pragma unroll
+              for (int j = 0; j < 80; ++j) bw[j] *= beta_l2;  // -inf stays -inf (beta >= 0); beta = 0 handled below
+              if (beta_l2 == 0.f) {
+#pragma unroll
+                for (int j = 0; j < 80; ++j) bw[j] = (j < p.S) ? 0.f : -INFINITY;
+              }
+            }
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int j = 0; j < 80; ++j) {
+              sc[j] = fmaf(sc[j], scale_l2, bw[j]);
+              mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+            }
+            const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            uint32_t pw[40];
+#pragma unroll
+            for (int j = 0; j < 40; ++j) pw[j] = Mma<T>::pack(ex2_approx(sc[2 * j] - m), ex2_approx(sc[2 * j + 1] - m));
+            TRACE(14);
+            // ---- O of the previous head (same tile) must leave TMEM before P lets the next PV overwrite it
+            if (o_pending) drain_o(i, h - 2);
+            TRACE(15);
+            tmem_st_x32(tw + C::P_COL, pw);
+            tmem_st_x8(tw + C::P_COL + 32, pw + 32);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(b_prdy + 8 * g);
+            TRACE(16);
+          }
+        }
+      }
+      TRACE(7);
+      if constexpr (!STATS) {
+        drain_o(r1 - 1, g + 2 * (hpw - 1));
+        release_item(r1 - 1);
+      }
+      TRACE(8);
+      r0 = r1;
     }
     if constexpr (STATS) {
       // CTA partial in a fixed order (warp shuffle tree, then warps 0..7 serially) -> workspace
@@ -501,15 +691,16 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
   }
 
   // teardown: everyone is done with TMEM before it is released
+  TRACE(9);
   tc_fence_before();
   __syncthreads();
+  TRACE(30);
   tc_fence_after();
-  if (warp == 9) {
+  if (warp == 8) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
-// =============================================================================================
 // ---- host: tensor maps -------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -556,11 +747,23 @@ static cudaError_t launch_tc5(XattnParams p, cudaStream_t st) {
   p.n_hg = (p.H + C::G - 1) / C::G;
   p.n_sl = (p.L + C::ROWS - 1) / C::ROWS;
   p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
+  if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
   const int sms = sm_count_cached();
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
   xattn_tc5_kernel<T, D, STATS><<<grid, kThreads, smem, st>>>(p, tm_q, tm_o);
   return cudaGetLastError();
 }
+
+#ifdef DSC_TRACE
+extern "C" int dsc_debug_trace(long long* out /*HOST 4*512*2*/, int* counts /*HOST 4*/) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 4 * 512 * 2);
+  cudaMemcpyFromSymbol(counts, g_trace_n, sizeof(int) * 4);
+  int z[4] = {0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_trace_n, z, sizeof(z));
+  return 0;
+}
+#endif
 
 bool tc5_supports(int D) { return D == 40 || D == 80; }
 

@@ -16,6 +16,12 @@ v = torch.randn(B, S, H * D).to(dt).cuda()
 view = lambda t: t.view(B, -1, H, D).transpose(1, 2)
 q4, k4, v4 = view(q), view(k), view(v)
 a = (q4.double() @ k4.double().transpose(-2, -1)) / math.sqrt(D)
+def wd():
+    ws = att.get_workspace(torch.device("cuda"))
+    w = ws[48:56].cpu().numpy().view("uint32")
+    if w[1]:
+        print("WATCHDOG: tag", int(w[0]) & 0xff, "block", (int(w[0]) >> 8) & 0xffff, "warp", int(w[0]) >> 24, "parity", int(w[1]) & 1)
+import atexit; atexit.register(wd)
 print("impl", os.environ.get("DSC_XATTN_IMPL", "tc5(default)"), "shape", B, H, L, D, S, flush=True)
 if mode == "stats":
     ws = att.score_stats(q4, k4)
