@@ -31,6 +31,7 @@ struct XattnParams {
   int n_sl;         // 16-row slices per (batch, head-group)
   long long total;  // B * n_hg * n_sl
   Workspace* ws;
+  unsigned stagger_ns;  // experiment knob of the 4-warpgroup tcgen05 kernel (0 = off)
 };
 
 int sm_count_cached();

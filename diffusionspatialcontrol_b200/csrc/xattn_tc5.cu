@@ -30,6 +30,9 @@
 #include "dsc_internal.h"
 #include "tc5_tmem.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <type_traits>
 
 namespace dsc {
@@ -84,6 +87,7 @@ struct TC {
 // Debug build only: a barrier wait that gives up after ~1 s, records who was waiting on what in the
 // workspace debug words (offset 48: {tag | block << 8 | warp << 24, parity}) and lets the kernel drain.
 __device__ unsigned int g_wd_abort = 0;
+__device__ unsigned int g_wd_info[2] = {0, 0};
 __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, uint32_t tag, Workspace* ws) {
   const long long t0 = clock64();
   while (true) {
@@ -109,11 +113,24 @@ __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, uint
 // Service warps (producer, MMA issuers) poll with a short sleep between probes: a hot spin loop would
 // compete with the two consumer warps of the same sub-partition for issue slots and the barrier unit.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+#ifdef DSC_WATCHDOG
+  const long long t0 = clock64();
+#endif
   while (true) {
     uint32_t ok;
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return;
+#ifdef DSC_WATCHDOG
+    if (*reinterpret_cast<volatile unsigned int*>(&g_wd_abort)) return;
+    if (clock64() - t0 > (1ll << 31)) {
+      if (atomicCAS(&g_wd_abort, 0u, 1u) == 0u) {
+        g_wd_info[0] = 100u | (blockIdx.x << 8) | ((threadIdx.x >> 5) << 24);
+        g_wd_info[1] = (bar & 0xffffu) | (parity << 16) | ((threadIdx.x & 31) << 20);
+      }
+      return;
+    }
+#endif
     __nanosleep(64);
   }
 }
@@ -137,8 +154,14 @@ __device__ int g_trace_n[4];
       g_trace_n[tr_k] = ++tr_n;                     \
     }                                               \
   } while (0)
+#define TRACE_DECL_X4                                                                                     \
+  int tr_n = 0;                                                                                           \
+  const int tr_k = blockIdx.x != 0 ? -1                                                                  \
+                   : threadIdx.x == 0 ? 0 : threadIdx.x == 128 ? 1 : threadIdx.x == 512 ? 2                \
+                   : threadIdx.x == 19 * 32 + 16 ? 3 : -1;
 #else
 #define TRACE_DECL
+#define TRACE_DECL_X4
 #define TRACE(tag) do {} while (0)
 #endif
 
@@ -220,66 +243,103 @@ __device__ __forceinline__ Item decode(int idx, const XattnParams& p) {
   return it;
 }
 
-// K_h -> canonical [chunk][key][16 B]; V_h -> V^T canonical [key chunk][d][8 keys] (+ the ones row); by the 256
-// consumer threads.  Every thread owns up to MAXE 16-byte pieces; all of its loads are issued before the first
-// use (clamped addresses instead of predicated loads keep the values in registers), so the DRAM latency is paid
-// once per tensor, not once per piece.
-template <typename T, int D, bool STATS>
+// Pull the K / V head group of (batch, head group) `it` towards L2 (one 128-byte line per request): issued at kernel
+// start for the first run and right after each restage for the following one, so the staging loads hit L2.
+template <typename T, int D, bool STATS, int NTHR>
+__device__ __forceinline__ void prefetch_kv(const XattnParams& p, const Item& it, int ctid) {
+  using C = TC<D>;
+  const int row_bytes = it.nheads * D * 2;
+  const int lines_per_row = (row_bytes + 127) / 128;
+  const int n_lines = p.S * lines_per_row;
+  const char* kb = reinterpret_cast<const char*>(reinterpret_cast<const T*>(p.k) + it.b * p.k_sb + it.hg * C::GW);
+  const char* vb = reinterpret_cast<const char*>(reinterpret_cast<const T*>(p.v) + it.b * p.v_sb + it.hg * C::GW);
+  for (int e = ctid; e < n_lines; e += NTHR) {
+    const int key = e / lines_per_row, l = e - key * lines_per_row;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + static_cast<long long>(key) * p.k_ss * 2 + l * 128));
+    if constexpr (!STATS) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + static_cast<long long>(key) * p.v_ss * 2 + l * 128));
+  }
+}
+
+// K_h -> canonical [chunk][key][16 B]; V_h -> V^T canonical [key chunk][d][8 keys] (+ the ones row), by NTHR
+// consumer threads.  All loads of a thread are issued before their first use (clamped addresses, no predicated
+// loads), and the thread->piece maps are chosen so that every shared-memory store is bank-conflict free:
+//   K  : piece = (head, chunk, key), key fastest  -> consecutive lanes store 16 B apart
+//   V^T: item  = (head, key chunk, d), d fastest  -> a thread gathers the 8 keys of one d (8 two-byte loads, lanes
+//        coalesce along d) and stores one 16-byte row; consecutive lanes store 16 B apart.  (Scattering two-byte
+//        elements of a row-major piece instead costs 8-way conflicts: measured 7.4k cycles per restage.)
+#ifdef DSC_TRACE
+__device__ long long g_kv_trace[8];
+#define KV_TRACE(tag) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_kv_trace[(tag) - 31] = clock64(); } while (0)
+#else
+#define KV_TRACE(tag) do {} while (0)
+#endif
+template <typename T, int D, bool STATS, int NTHR = 256>
 __device__ __forceinline__ void stage_kv(unsigned char* smem, const XattnParams& p, const Item& it, int ctid) {
   using C = TC<D>;
-  constexpr int MAXE = (C::G * DSC_MAX_KEYS * C::DCH + kConsumerThreads - 1) / kConsumerThreads;  // 7
-  const int per_head = p.S * C::DCH;
-  const int n_e = it.nheads * per_head;
-  int soff[MAXE];  // smem offset of the piece inside K (bytes); V^T offsets are derived from (h, key, c)
-  int hkc[MAXE];   // h << 16 | key << 8 | c
-  long long goff[MAXE];
+  constexpr int MAXK = (C::G * DSC_MAX_KEYS * C::DCH + NTHR - 1) / NTHR;
+  constexpr int NPAIR = D / 2 + 1;  // column pairs of V incl. the (ones, zero) pair that forms row D
+  constexpr int MAXV = (C::G * 10 * NPAIR + NTHR - 1) / NTHR;
+  KV_TRACE(31);
+  // 32-bit element offsets from the (batch, head group) base: the index math must stay cheap, this runs on every
+  // thread for every piece (64-bit multiplies here cost more issue slots than the loads themselves)
+  const T* __restrict__ kg = reinterpret_cast<const T*>(p.k) + it.b * p.k_sb + it.hg * C::GW;
+  const int kss = static_cast<int>(p.k_ss), vss = static_cast<int>(p.v_ss);
+  const int n_k = it.nheads * C::DCH * p.S;
+  uint4 kv[MAXK];
+  int ksoff[MAXK];
 #pragma unroll
-  for (int u = 0; u < MAXE; ++u) {
-    const int e = min(ctid + u * kConsumerThreads, n_e - 1);
-    const int h = e / per_head, rem = e - h * per_head;
-    const int key = rem / C::DCH, c = rem - key * C::DCH;
-    hkc[u] = (h << 16) | (key << 8) | c;
-    soff[u] = h * C::K_HEAD_BYTES + c * C::K_CH_BYTES + key * 16;
-    goff[u] = static_cast<long long>(key) * p.k_ss + (it.hg * C::G + h) * D + c * 8;
+  for (int u = 0; u < MAXK; ++u) {
+    const int e = min(ctid + u * NTHR, n_k - 1);
+    const int hc = e / p.S, key = e - hc * p.S;       // one runtime division per piece
+    const int h = hc / C::DCH, c = hc - h * C::DCH;   // constant divisor
+    ksoff[u] = h * C::K_HEAD_BYTES + c * C::K_CH_BYTES + key * 16;
+    kv[u] = __ldg(reinterpret_cast<const uint4*>(kg + (key * kss + h * D + c * 8)));
   }
-  const T* __restrict__ k = reinterpret_cast<const T*>(p.k) + it.b * p.k_sb;
-  uint4 kv[MAXE], vv4[STATS ? 1 : MAXE];
-#pragma unroll
-  for (int u = 0; u < MAXE; ++u) kv[u] = __ldg(reinterpret_cast<const uint4*>(k + goff[u]));
-  if constexpr (!STATS) {  // V pieces are requested before the first K piece is consumed: one DRAM round trip
-    const T* __restrict__ vv = reinterpret_cast<const T*>(p.v) + it.b * p.v_sb;
-#pragma unroll
-    for (int u = 0; u < MAXE; ++u) {
-      const int key = (hkc[u] >> 8) & 0xff, h = hkc[u] >> 16, c = hkc[u] & 0xff;
-      vv4[u] = __ldg(reinterpret_cast<const uint4*>(vv + static_cast<long long>(key) * p.v_ss + (it.hg * C::G + h) * D + c * 8));
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < MAXE; ++u)
-    if (ctid + u * kConsumerThreads < n_e) *reinterpret_cast<uint4*>(smem + soff[u]) = kv[u];
+  uint32_t ve[STATS ? 1 : MAXV][8];  // ve[u][j] = V[key 8*kc+j][d, d+1] (two 16-bit values)
+  int vsoff[STATS ? 1 : MAXV];
   if constexpr (!STATS) {
-    unsigned char* sVt = smem + C::K_BYTES;
+    const T* __restrict__ vg = reinterpret_cast<const T*>(p.v) + it.b * p.v_sb + it.hg * C::GW;
+    const int n_v = it.nheads * 10 * NPAIR;
+    const uint32_t one = std::is_same<T, __half>::value ? 0x3C00u : 0x3F80u;
 #pragma unroll
-    for (int u = 0; u < MAXE; ++u) {
-      if (ctid + u * kConsumerThreads < n_e) {
-        const int key = (hkc[u] >> 8) & 0xff, h = hkc[u] >> 16, c = hkc[u] & 0xff;
-        unsigned char* dst = sVt + h * C::VT_HEAD_BYTES + (key >> 3) * C::VT_CH_BYTES + (c * 8) * 16 + (key & 7) * 2;
-        const uint32_t w[4] = {vv4[u].x, vv4[u].y, vv4[u].z, vv4[u].w};
+    for (int u = 0; u < MAXV; ++u) {
+      const int e = min(ctid + u * NTHR, n_v - 1);
+      const int hk = e / NPAIR, dp = e - hk * NPAIR;  // constant divisors
+      const int h = hk / 10, kc = hk - h * 10;
+      vsoff[u] = h * C::VT_HEAD_BYTES + kc * C::VT_CH_BYTES + dp * 32;
+      const int col = h * D + min(dp, D / 2 - 1) * 2;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          *reinterpret_cast<uint16_t*>(dst + (2 * j) * 16) = static_cast<uint16_t>(w[j] & 0xffffu);
-          *reinterpret_cast<uint16_t*>(dst + (2 * j + 1) * 16) = static_cast<uint16_t>(w[j] >> 16);
-        }
+      for (int j = 0; j < 8; ++j) {
+        const int key = kc * 8 + j;
+        const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(vg + (min(key, p.S - 1) * vss + col)));
+        ve[u][j] = key >= p.S ? 0u : (dp == D / 2 ? one : x);  // pad keys multiply nothing; pair D/2 = (1, 0)
       }
     }
-    // ones row (d = D) for the valid keys: O[:, D] = sum_k P[:, k]
-    const uint16_t one = std::is_same<T, __half>::value ? 0x3C00 : 0x3F80;
-    for (int e = ctid; e < it.nheads * p.S; e += kConsumerThreads) {
-      const int h = e / p.S, key = e - h * p.S;
-      *reinterpret_cast<uint16_t*>(sVt + h * C::VT_HEAD_BYTES + (key >> 3) * C::VT_CH_BYTES + D * 16 + (key & 7) * 2) = one;
+  }
+  KV_TRACE(32);
+#pragma unroll
+  for (int u = 0; u < MAXK; ++u)
+    if (ctid + u * NTHR < n_k) *reinterpret_cast<uint4*>(smem + ksoff[u]) = kv[u];
+  KV_TRACE(33);
+  if constexpr (!STATS) {
+    const int n_v = it.nheads * 10 * NPAIR;
+#pragma unroll
+    for (int u = 0; u < MAXV; ++u) {
+      if (ctid + u * NTHR < n_v) {
+        uint4 lo, hi;  // row d (low halves) and row d+1 (high halves), 8 keys each
+        lo.x = __byte_perm(ve[u][0], ve[u][1], 0x5410); hi.x = __byte_perm(ve[u][0], ve[u][1], 0x7632);
+        lo.y = __byte_perm(ve[u][2], ve[u][3], 0x5410); hi.y = __byte_perm(ve[u][2], ve[u][3], 0x7632);
+        lo.z = __byte_perm(ve[u][4], ve[u][5], 0x5410); hi.z = __byte_perm(ve[u][4], ve[u][5], 0x7632);
+        lo.w = __byte_perm(ve[u][6], ve[u][7], 0x5410); hi.w = __byte_perm(ve[u][6], ve[u][7], 0x7632);
+        unsigned char* dst = smem + C::K_BYTES + vsoff[u];
+        *reinterpret_cast<uint4*>(dst) = lo;
+        *reinterpret_cast<uint4*>(dst + 16) = hi;
+      }
     }
   }
+  KV_TRACE(34);
   fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+  KV_TRACE(35);
 }
 
 template <typename T, int D, bool STATS>
@@ -293,6 +353,10 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TRACE_DECL
+  {  // first thing: start pulling this CTA's first K / V head group into L2
+    const int begin0 = static_cast<int>(p.total * blockIdx.x / gridDim.x);
+    if (tid < kConsumerThreads && begin0 < p.total) prefetch_kv<T, D, STATS, kConsumerThreads>(p, decode<D>(begin0, p), tid);
+  }
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sStage = s0 + KV_BYTES;
   const uint32_t bars = sStage + NST * STAGE_BYTES;
@@ -520,6 +584,7 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
       stage_kv<T, D, STATS>(smem, p, it0, tid);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       TRACE(4);
+      if (r1 < n_items) prefetch_kv<T, D, STATS, kConsumerThreads>(p, decode<D>(begin + r1, p), tid);
       const int hpw = it0.nheads > g ? (it0.nheads - g + 1) >> 1 : 0;  // heads of this warpgroup per tile: 0, 1 or 2
       if (hpw == 0) {  // this warpgroup has no head in these tiles: just hand them back
         for (int i = r0; i < r1; ++i) {
@@ -701,6 +766,361 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
   }
 }
 
+// =============================================================================================
+// Four consumer warpgroups, one head each (D = 40: the 4 heads of a 160-column tile are processed concurrently).
+//
+// Same producer / TMA ring / resident K, V^T / TMEM-operand scheme as xattn_tc5_kernel, but 16 consumer warps
+// (4 per SM sub-partition instead of 2) hide the TMEM and mbarrier round trips of the per-head chain
+//   Q row -> TMEM | S = Q K^T | S row -> softmax -> P -> TMEM | O = P [V|1] | O row -> smem
+// behind each other.  TMEM: 128 columns per warpgroup: S (80 fp32; P overwrites its first 40 columns once the row is
+// in registers) and O (48 fp32; the Q operand occupies its first 24 columns until S is done).  The beta*W row is
+// streamed from the shared W tile (registers are 112 per consumer thread here).  One MMA warp: lane g issues for
+// warpgroup g.
+constexpr int kX4Consumers = 512;
+constexpr int kX4Threads = 640;   // warps 0-15 consumers | 16 producer | 17 MMA issuers (lanes 0-3) | 18, 19 idle
+// 640 threads -> 96 registers per thread from __launch_bounds__; the consumer path fits without spills, so no
+// setmaxnreg here (a CTA's register pool is what it was launched with: 640 x 96 leaves nothing to hand over).
+
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(kX4Threads, 1)
+xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_o) {
+  constexpr int D = 40;
+  using C = TC<D>;
+  constexpr int NST = STATS ? C::STATS_STAGES : C::FWD_STAGES;
+  constexpr int STAGE_BYTES = STATS ? C::QT_BYTES : (C::QT_BYTES + C::WT_BYTES);
+  constexpr int KV_BYTES = STATS ? C::K_BYTES_PAD : (C::K_BYTES + C::VT_BYTES);
+  constexpr int S_COL = 0, O_COL = 80, WG_COLS = 128;  // P aliases S, the Q operand aliases O
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  TRACE_DECL_X4
+  TRACE(1);
+  {  // first thing: start pulling this CTA's first K / V head group into L2
+    const int begin0 = static_cast<int>(p.total * blockIdx.x / gridDim.x);
+    if (tid < kX4Consumers && begin0 < p.total) prefetch_kv<T, 40, STATS, kX4Consumers>(p, decode<40>(begin0, p), tid);
+  }
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t sStage = s0 + KV_BYTES;
+  const uint32_t bars = sStage + NST * STAGE_BYTES;
+  // barrier map (8 B each): full[NST] | odone[NST] | qrdy[4] | srdy[4] | prdy[4] | ordy[4] ; tmem ptr after
+  const uint32_t b_full = bars, b_odone = bars + 8 * NST, b_qrdy = bars + 16 * NST, b_srdy = b_qrdy + 32,
+                 b_prdy = b_qrdy + 64, b_ordy = b_qrdy + 96;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV_BYTES + NST * STAGE_BYTES + 240);
+
+  for (int i = tid; i < KV_BYTES / 16; i += kX4Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_odone + 8 * s, kX4Consumers);
+    }
+    for (int g = 0; g < 4; ++g) {
+      mbar_init(b_qrdy + 8 * g, 128);
+      mbar_init(b_srdy + 8 * g, 1);
+      mbar_init(b_prdy + 8 * g, 128);
+      mbar_init(b_ordy + 8 * g, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  TRACE(2);
+
+  const int begin = static_cast<int>(p.total * blockIdx.x / gridDim.x);
+  const int n_items = static_cast<int>(p.total * (blockIdx.x + 1) / gridDim.x) - begin;
+
+  if (warp >= 16) {
+    // Service warps 16..19: lane 0 of warp 16+g issues the tensor-core work of warpgroup g; lane 16 of warp 19 is
+    // the TMA producer.  (Two lanes of one warp in different loops simply interleave.)
+    const int wsvc = __shfl_sync(0xffffffffu, warp, 0) - 16;  // warp-uniform
+    if (wsvc == 3 && lane == 16) {
+      // ============================== producer: TMA loads and stores ===============================
+      const uint64_t pol = STATS ? policy_evict_last() : policy_evict_first();
+      auto store_tile = [&](int i) {
+        if constexpr (!STATS) {
+          const Item it = decode<D>(begin + i, p);
+          const uint32_t sQ = sStage + (i % NST) * STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < C::NBOX; ++j)
+            tma_store_3d(&tm_o, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, sQ + j * C::BOX_BYTES);
+          bulk_commit();
+          bulk_wait_read0();
+        }
+      };
+      for (int i = 0; i < n_items; ++i) {
+        const int s = i % NST;
+        if (i >= NST) {
+          mbar_wait_relaxed(b_odone + 8 * s, ((i / NST) - 1) & 1);
+          TRACE(41);
+          store_tile(i - NST);
+          TRACE(42);
+        }
+        const Item it = decode<D>(begin + i, p);
+        const uint32_t sQ = sStage + s * STAGE_BYTES;
+        uint32_t tx = C::QT_BYTES;
+        const float* wsrc = nullptr;
+        uint32_t wbytes = 0;
+        if constexpr (!STATS) {
+          wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.S;
+          wbytes = it.rows * p.S * 4;
+          if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
+        }
+        mbar_arrive_expect_tx(b_full + 8 * s, tx);
+#pragma unroll
+        for (int j = 0; j < C::NBOX; ++j)
+          tma_load_3d(sQ + j * C::BOX_BYTES, &tm_q, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, b_full + 8 * s, pol);
+        if (wbytes != 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
+        TRACE(40);
+      }
+      for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) {
+        mbar_wait_relaxed(b_odone + 8 * (i % NST), (i / NST) & 1);
+        store_tile(i);
+      }
+      bulk_wait0();
+    } else if (lane == 0) {
+      // ============================== MMA issuer of warpgroup g ====================================
+      const int g = wsvc;
+      constexpr uint32_t idesc_qk = idesc_f16<T>(80);
+      constexpr uint32_t idesc_pv = idesc_f16<T>(C::N_PV);
+      const uint32_t tw = tmem_base + g * WG_COLS;
+      const uint64_t kdesc = smem_desc(s0 + g * C::K_HEAD_BYTES, C::K_CH_BYTES, 128);
+      const uint64_t vdesc = smem_desc(s0 + C::K_BYTES + g * C::VT_HEAD_BYTES, C::VT_CH_BYTES, 128);
+      uint32_t n = 0;
+      for (int i = 0; i < n_items; ++i) {
+        const Item it = decode<D>(begin + i, p);
+        if (g >= it.nheads) continue;
+        mbar_wait_relaxed(b_qrdy + 8 * g, n & 1);
+        TRACE(21);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < C::KSTEPS; ++ks)  // descriptor start address advances by 2 chunks per k-step
+          umma_ts(tw + S_COL, tw + O_COL + ks * 8, kdesc + static_cast<uint64_t>((ks * 2 * C::K_CH_BYTES) >> 4), idesc_qk, ks);
+        tc_commit(b_srdy + 8 * g);
+        TRACE(22);
+        if constexpr (!STATS) {
+          mbar_wait_relaxed(b_prdy + 8 * g, n & 1);
+          TRACE(24);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 5; ++kk)
+            umma_ts(tw + O_COL, tw + S_COL + kk * 8, vdesc + static_cast<uint64_t>((kk * 2 * C::VT_CH_BYTES) >> 4), idesc_pv, kk);
+          tc_commit(b_ordy + 8 * g);
+          TRACE(25);
+        }
+        ++n;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== consumers: warpgroup g = head g, one thread per query row ======
+    const int g = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t row_off = row * 64, row_sw = (row >> 1) & 3;
+    auto chunk_off = [&](int cg) -> uint32_t {
+      return (cg >> 2) * C::BOX_BYTES + row_off + ((static_cast<uint32_t>(cg & 3) ^ row_sw) << 4);
+    };
+    const uint32_t tw = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * WG_COLS;
+    const float sigma = STATS ? 0.f : (p.sigma_dev ? __ldg(p.sigma_dev) : p.sigma_host);
+    const float beta_l2 = STATS ? 0.f : sigma * __ldcg(&p.ws->std_unbiased) * kLog2eT;
+    const float scale_l2 = p.scale * kLog2eT;
+    double dsum = 0.0, dsq = 0.0;
+    uint32_t n = 0;
+    const unsigned stagger_ns = p.stagger_ns;
+    for (int r0 = 0; r0 < n_items;) {
+      const Item it0 = decode<D>(begin + r0, p);
+      const int r1 = min(n_items, r0 + p.n_sl - it0.tile);
+      TRACE(3);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      stage_kv<T, D, STATS, kX4Consumers>(smem, p, it0, tid);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      TRACE(4);
+      if (r1 < n_items) prefetch_kv<T, D, STATS, kX4Consumers>(p, decode<D>(begin + r1, p), tid);
+      const bool active = g < it0.nheads;
+      if (stagger_ns) __nanosleep(stagger_ns * g);  // de-phase the warpgroups (experiment)
+      for (int i = r0; i < r1; ++i) {
+        const int s = i % NST;
+        const int l0 = (it0.tile + (i - r0)) * C::ROWS;
+        const int rows = min(C::ROWS, p.L - l0);
+        unsigned char* qtile = smem + KV_BYTES + s * STAGE_BYTES;
+        TRACE(10);
+        MBAR_WAIT(b_full + 8 * s, (i / NST) & 1, 6);
+        TRACE(5);
+        if (active) {
+          // ---- Q row of head g -> TMEM (first 24 columns of the O region; columns 20..23 = zero K padding)
+          {
+            uint32_t qw[24];
+#pragma unroll
+            for (int c = 0; c < C::DCH; ++c) {
+              const uint4 v = *reinterpret_cast<const uint4*>(qtile + chunk_off(g * C::DCH + c));
+              qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
+            }
+            qw[20] = qw[21] = qw[22] = qw[23] = 0u;
+            tmem_st_x16(tw + O_COL, qw);
+            tmem_st_x8(tw + O_COL + 16, qw + 16);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(b_qrdy + 8 * g);
+          }
+          TRACE(6);
+          if constexpr (STATS) mbar_arrive(b_odone + 8 * s);  // pass 1 only reads Q
+          // ---- S row
+          MBAR_WAIT(b_srdy + 8 * g, n & 1, 8);
+          TRACE(11);
+          tc_fence_after();
+          float sc[80];
+          tmem_ld_x64(tw + S_COL, reinterpret_cast<uint32_t*>(sc));
+          tmem_ld_x16(tw + S_COL + 64, reinterpret_cast<uint32_t*>(sc) + 64);
+          tc_wait_ld();
+          TRACE(12);
+          if constexpr (STATS) {
+            float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 80; ++j) {
+              fs[j & 3] += sc[j];
+              fq[j & 3] = fmaf(sc[j], sc[j], fq[j & 3]);
+            }
+            if (row < rows) {
+              dsum += static_cast<double>((fs[0] + fs[1]) + (fs[2] + fs[3]));
+              dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
+            }
+          } else {
+            // logits in the log2 domain: s*scale*log2e + beta*log2e*W, W streamed from the shared tile
+            const float* wsrc = p.W + ((static_cast<long long>(it0.b / (p.B / p.Bw)) * p.L + l0) * p.S);
+            const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.S * 4)) & 15) == 0;
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (bulk) {
+              const float* wt = reinterpret_cast<const float*>(qtile + C::QT_BYTES) + row * p.S;
+              if (p.S == 77) {
+#pragma unroll
+                for (int j = 0; j < 77; ++j) {
+                  sc[j] = fmaf(sc[j], scale_l2, wt[j] * beta_l2);
+                  mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+                }
+                sc[77] = sc[78] = sc[79] = -INFINITY;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 80; ++j) {
+                  sc[j] = (j < p.S) ? fmaf(sc[j], scale_l2, wt[j] * beta_l2) : -INFINITY;
+                  mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+                }
+              }
+            } else {
+              const float* wr = wsrc + static_cast<long long>(row < rows ? row : 0) * p.S;
+#pragma unroll
+              for (int j = 0; j < 80; ++j) {
+                sc[j] = (j < p.S) ? fmaf(sc[j], scale_l2, __ldg(wr + j) * beta_l2) : -INFINITY;
+                mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+              }
+            }
+            const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            uint32_t pw[40];
+#pragma unroll
+            for (int j = 0; j < 40; ++j) pw[j] = Mma<T>::pack(ex2_approx(sc[2 * j] - m), ex2_approx(sc[2 * j + 1] - m));
+            TRACE(14);
+            tmem_st_x32(tw + S_COL, pw);  // P over the first 40 columns of S (the whole S row is in registers)
+            tmem_st_x8(tw + S_COL + 32, pw + 32);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(b_prdy + 8 * g);
+            TRACE(16);
+            // ---- O row
+            MBAR_WAIT(b_ordy + 8 * g, n & 1, 5);
+            TRACE(17);
+            tc_fence_after();
+            float o[48];
+            tmem_ld_x32(tw + O_COL, reinterpret_cast<uint32_t*>(o));
+            tmem_ld_x16(tw + O_COL + 32, reinterpret_cast<uint32_t*>(o) + 32);
+            tc_wait_ld();
+            const float inv = 1.f / o[D];
+#pragma unroll
+            for (int c = 0; c < C::DCH; ++c) {
+              uint4 v;
+              v.x = Mma<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
+              v.y = Mma<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+              v.z = Mma<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+              v.w = Mma<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+              *reinterpret_cast<uint4*>(qtile + chunk_off(g * C::DCH + c)) = v;
+            }
+            TRACE(18);
+            tc_fence_before();  // the next Q operand overwrites the O columns: order the TMEM reads before it
+          }
+          ++n;
+        } else if constexpr (STATS) {
+          mbar_arrive(b_odone + 8 * s);
+        }
+        if constexpr (!STATS) {
+          fence_proxy_async();
+          mbar_arrive(b_odone + 8 * s);
+        }
+      }
+      r0 = r1;
+    }
+    if constexpr (STATS) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        dsq += __shfl_xor_sync(0xffffffffu, dsq, o);
+      }
+      double* red = reinterpret_cast<double*>(smem);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (lane == 0) {
+        red[warp] = dsum;
+        red[16 + warp] = dsq;
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 16; ++w) {
+          a += red[w];
+          b += red[16 + w];
+        }
+        double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
+        partials[2 * blockIdx.x] = a;
+        partials[2 * blockIdx.x + 1] = b;
+        __threadfence();
+        const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
+        if (t == gridDim.x - 1) {
+          __threadfence();
+          double sa = 0.0, sb = 0.0;
+          for (unsigned int c = 0; c < gridDim.x; ++c) {
+            sa += __ldcg(partials + 2 * c);
+            sb += __ldcg(partials + 2 * c + 1);
+          }
+          const double scl = static_cast<double>(p.scale);
+          const double nn = static_cast<double>(p.B) * p.H * static_cast<double>(p.L) * p.S;
+          const double sum = sa * scl, sumsq = sb * scl * scl, mean = sum / nn;
+          double var = (nn > 1.0) ? (sumsq - sum * mean) / (nn - 1.0) : nan("");
+          if (var < 0.0) var = 0.0;
+          p.ws->std_unbiased = static_cast<float>(sqrt(var));
+          p.ws->mean = static_cast<float>(mean);
+          p.ws->sum = sum;
+          p.ws->sumsq = sumsq;
+          p.ws->n = nn;
+          p.ws->n_partials = gridDim.x;
+          __threadfence();
+          p.ws->ticket = 0u;
+        }
+      }
+    }
+  }
+
+  TRACE(9);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  TRACE(30);
+  if (warp == 16) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
 // ---- host: tensor maps -------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -754,26 +1174,75 @@ static cudaError_t launch_tc5(XattnParams p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+#ifdef DSC_WATCHDOG
+extern "C" int dsc_debug_watchdog(unsigned int* out /*HOST 3*/) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_wd_info, 8);
+  cudaMemcpyFromSymbol(out + 2, g_wd_abort, 4);
+  return 0;
+}
+#endif
+
 #ifdef DSC_TRACE
 extern "C" int dsc_debug_trace(long long* out /*HOST 4*512*2*/, int* counts /*HOST 4*/) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 4 * 512 * 2);
   cudaMemcpyFromSymbol(counts, g_trace_n, sizeof(int) * 4);
+  { long long kv[8]; cudaMemcpyFromSymbol(kv, g_kv_trace, sizeof(kv));
+    printf("kv staging (block 0, thread 0, last call): enter->loads_issued %lld, ->k_stored %lld, ->v_stored %lld, ->fenced %lld cycles\n",
+           kv[1] - kv[0], kv[2] - kv[0], kv[3] - kv[0], kv[4] - kv[0]); }
   int z[4] = {0, 0, 0, 0};
   cudaMemcpyToSymbol(g_trace_n, z, sizeof(z));
   return 0;
 }
 #endif
 
+template <typename T, bool STATS>
+static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
+  using C = TC<40>;
+  constexpr int smem = STATS ? C::STATS_SMEM : C::FWD_SMEM;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_tc5x4_kernel<T, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  CUtensorMap tm_q, tm_o;
+  if (!make_map(&tm_q, p.q, p.H * 40, p.L, p.B, p.q_sl, p.q_sb)) return cudaErrorInvalidValue;
+  if (STATS) tm_o = tm_q;
+  else if (!make_map(&tm_o, p.out, p.H * 40, p.L, p.B, p.o_sl, p.o_sb)) return cudaErrorInvalidValue;
+  p.n_hg = (p.H + C::G - 1) / C::G;
+  p.n_sl = (p.L + C::ROWS - 1) / C::ROWS;
+  p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
+  if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
+  const int sms = sm_count_cached();
+  const int grid = static_cast<int>(p.total < sms ? p.total : sms);
+  { const char* e = getenv("DSC_X4_STAGGER_NS"); p.stagger_ns = e ? static_cast<unsigned>(atoi(e)) : 0u; }
+  xattn_tc5x4_kernel<T, STATS><<<grid, kX4Threads, smem, st>>>(p, tm_q, tm_o);
+  return cudaGetLastError();
+}
+
+// D = 40 has two tcgen05 variants: "x4" (4 consumer warpgroups, one head each; default) and "x2" (2 warpgroups,
+// software-pipelined heads).  DSC_TC5_VARIANT=x2 selects the latter for A/B runs.
+static bool use_x4(int D) {
+  if (D != 40) return false;
+  const char* e = getenv("DSC_TC5_VARIANT");
+  return !(e && e[0] == 'x' && e[1] == '2');
+}
+
 bool tc5_supports(int D) { return D == 40 || D == 80; }
 
 cudaError_t run_stats_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st) {
+  if (use_x4(D)) return dtype == DSC_DTYPE_F16 ? launch_tc5x4<__half, true>(p, st) : launch_tc5x4<__nv_bfloat16, true>(p, st);
   if (dtype == DSC_DTYPE_F16)
     return D == 40 ? launch_tc5<__half, 40, true>(p, st) : launch_tc5<__half, 80, true>(p, st);
   return D == 40 ? launch_tc5<__nv_bfloat16, 40, true>(p, st) : launch_tc5<__nv_bfloat16, 80, true>(p, st);
 }
 
 cudaError_t run_forward_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st) {
+  if (use_x4(D)) return dtype == DSC_DTYPE_F16 ? launch_tc5x4<__half, false>(p, st) : launch_tc5x4<__nv_bfloat16, false>(p, st);
   if (dtype == DSC_DTYPE_F16)
     return D == 40 ? launch_tc5<__half, 40, false>(p, st) : launch_tc5<__half, 80, false>(p, st);
   return D == 40 ? launch_tc5<__nv_bfloat16, 40, false>(p, st) : launch_tc5<__nv_bfloat16, 80, false>(p, st);

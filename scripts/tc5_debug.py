@@ -21,7 +21,15 @@ def wd():
     w = ws[48:56].cpu().numpy().view("uint32")
     if w[1]:
         print("WATCHDOG: tag", int(w[0]) & 0xff, "block", (int(w[0]) >> 8) & 0xffff, "warp", int(w[0]) >> 24, "parity", int(w[1]) & 1)
-import atexit; atexit.register(wd)
+def wd2():
+    import ctypes
+    from diffusionspatialcontrol_b200 import _lib
+    raw = ctypes.CDLL(str(_lib.LIB_PATH))
+    if hasattr(raw, "dsc_debug_watchdog"):
+        o = (ctypes.c_uint * 3)(); raw.dsc_debug_watchdog(o)
+        if o[2]:
+            print("WATCHDOG2: abort; tag", o[0] & 0xff, "block", (o[0] >> 8) & 0xffff, "warp", o[0] >> 24, "bar_off", hex(o[1] & 0xffff), "parity", (o[1] >> 16) & 1, "lane", o[1] >> 20)
+import atexit; atexit.register(wd); atexit.register(wd2)
 print("impl", os.environ.get("DSC_XATTN_IMPL", "tc5(default)"), "shape", B, H, L, D, S, flush=True)
 if mode == "stats":
     ws = att.score_stats(q4, k4)
