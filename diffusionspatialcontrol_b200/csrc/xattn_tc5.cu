@@ -219,6 +219,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
   return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) |
          (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46);
 }
+// kind::f16 instruction descriptor with independent A / B formats (0 = F16, 1 = BF16)
+__host__ __device__ constexpr uint32_t idesc_ab(uint32_t afmt, uint32_t bfmt, int n) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
 template <typename T>
 __host__ __device__ constexpr uint32_t idesc_f16(int n) {
   const uint32_t fmt = std::is_same<T, __half>::value ? 0u : 1u;  // 0 = F16, 1 = BF16
@@ -241,6 +245,37 @@ __device__ __forceinline__ Item decode(int idx, const XattnParams& p) {
   it.l0 = it.tile * TC<D>::ROWS;
   it.rows = min(TC<D>::ROWS, p.L - it.l0);
   return it;
+}
+
+// Last step of pass 1, executed by ONE WARP of the last-arriving CTA: fold the per-CTA fp64 partials in a fixed
+// order (lane-strided loads, then a fixed shuffle tree: deterministic, and ~5 loads deep instead of a 148-long
+// serial chain of L2 round trips) and publish std / mean.
+__device__ __forceinline__ void finalize_stats(const XattnParams& p, const double* partials, int lane) {
+  double sa = 0.0, sb = 0.0;
+  for (unsigned int c = lane; c < gridDim.x; c += 32) {
+    sa += __ldcg(partials + 2 * c);
+    sb += __ldcg(partials + 2 * c + 1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  if (lane == 0) {
+    const double scl = static_cast<double>(p.scale);
+    const double n = static_cast<double>(p.B) * p.H * static_cast<double>(p.L) * p.S;
+    const double sum = sa * scl, sumsq = sb * scl * scl, mean = sum / n;
+    double var = (n > 1.0) ? (sumsq - sum * mean) / (n - 1.0) : nan("");
+    if (var < 0.0) var = 0.0;
+    p.ws->std_unbiased = static_cast<float>(sqrt(var));
+    p.ws->mean = static_cast<float>(mean);
+    p.ws->sum = sum;
+    p.ws->sumsq = sumsq;
+    p.ws->n = n;
+    p.ws->n_partials = gridDim.x;
+    __threadfence();
+    p.ws->ticket = 0u;  // reusable without a memset
+  }
 }
 
 // Pull the K / V head group of (batch, head group) `it` towards L2 (one 128-byte line per request): issued at kernel
@@ -269,8 +304,12 @@ __device__ __forceinline__ void prefetch_kv(const XattnParams& p, const Item& it
 //        elements of a row-major piece instead costs 8-way conflicts: measured 7.4k cycles per restage.)
 #ifdef DSC_TRACE
 __device__ long long g_kv_trace[8];
+__device__ unsigned long long g_cta_times[160][2];  // globaltimer (ns) at CTA start / end
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define CTA_TIME(k) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_cta_times[blockIdx.x][k] = gtimer(); } while (0)
 #define KV_TRACE(tag) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_kv_trace[(tag) - 31] = clock64(); } while (0)
 #else
+#define CTA_TIME(k) do {} while (0)
 #define KV_TRACE(tag) do {} while (0)
 #endif
 template <typename T, int D, bool STATS, int NTHR = 256>
@@ -719,37 +758,24 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
         red[8 + warp] = dsq;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < 8; ++w) {
-          a += red[w];
-          b += red[8 + w];
-        }
-        double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
-        partials[2 * blockIdx.x] = a;
-        partials[2 * blockIdx.x + 1] = b;
-        __threadfence();
-        const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
-        if (t == gridDim.x - 1) {  // last CTA: fold all partials in index order (deterministic)
-          __threadfence();
-          double sa = 0.0, sb = 0.0;
-          for (unsigned int c = 0; c < gridDim.x; ++c) {
-            sa += __ldcg(partials + 2 * c);
-            sb += __ldcg(partials + 2 * c + 1);
+      double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
+      if (warp == 0) {
+        unsigned int last = 0;
+        if (lane == 0) {
+          double a = 0.0, b = 0.0;
+          for (int w = 0; w < 8; ++w) {
+            a += red[w];
+            b += red[8 + w];
           }
-          const double scl = static_cast<double>(p.scale);
-          const double n = static_cast<double>(p.B) * p.H * static_cast<double>(p.L) * p.S;
-          const double sum = sa * scl, sumsq = sb * scl * scl, mean = sum / n;
-          double var = (n > 1.0) ? (sumsq - sum * mean) / (n - 1.0) : nan("");
-          if (var < 0.0) var = 0.0;
-          p.ws->std_unbiased = static_cast<float>(sqrt(var));
-          p.ws->mean = static_cast<float>(mean);
-          p.ws->sum = sum;
-          p.ws->sumsq = sumsq;
-          p.ws->n = n;
-          p.ws->n_partials = gridDim.x;
+          partials[2 * blockIdx.x] = a;
+          partials[2 * blockIdx.x + 1] = b;
           __threadfence();
-          p.ws->ticket = 0u;
+          last = atomicAdd(&p.ws->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {  // last CTA: fold all partials (deterministic order)
+          __threadfence();
+          finalize_stats(p, partials, lane);
         }
       }
     }
@@ -794,6 +820,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TRACE_DECL_X4
   TRACE(1);
+  CTA_TIME(0);
   {  // first thing: start pulling this CTA's first K / V head group into L2
     const int begin0 = static_cast<int>(p.total * blockIdx.x / gridDim.x);
     if (tid < kX4Consumers && begin0 < p.total) prefetch_kv<T, 40, STATS, kX4Consumers>(p, decode<40>(begin0, p), tid);
@@ -881,14 +908,13 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
       }
       for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) {
         mbar_wait_relaxed(b_odone + 8 * (i % NST), (i / NST) & 1);
-        store_tile(i);
+        store_tile(i);  // waits until the TMA has read the tile; the writes themselves complete before the grid does
       }
-      bulk_wait0();
     } else if (lane == 0) {
       // ============================== MMA issuer of warpgroup g ====================================
       const int g = wsvc;
       constexpr uint32_t idesc_qk = idesc_f16<T>(80);
-      constexpr uint32_t idesc_pv = idesc_f16<T>(C::N_PV);
+      constexpr uint32_t idesc_pv = idesc_f16<T>(C::N_PV);  // A (= P) and B (= V^T) share the input dtype
       const uint32_t tw = tmem_base + g * WG_COLS;
       const uint64_t kdesc = smem_desc(s0 + g * C::K_HEAD_BYTES, C::K_CH_BYTES, 128);
       const uint64_t vdesc = smem_desc(s0 + C::K_BYTES + g * C::VT_HEAD_BYTES, C::VT_CH_BYTES, 128);
@@ -943,122 +969,137 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
       TRACE(4);
       if (r1 < n_items) prefetch_kv<T, D, STATS, kX4Consumers>(p, decode<D>(begin + r1, p), tid);
       const bool active = g < it0.nheads;
-      if (stagger_ns) __nanosleep(stagger_ns * g);  // de-phase the warpgroups (experiment)
+      if (stagger_ns) __nanosleep(stagger_ns * (g >> 1));  // de-phase the warpgroup pairs {0,1} / {2,3} (experiment)
+      // Q row of head g of tile i -> TMEM (first 24 columns of the O region; columns 20..23 = zero K padding)
+      auto stage_q = [&](int i) {
+        const int s = i % NST;
+        const unsigned char* qtile = smem + KV_BYTES + s * STAGE_BYTES;
+        MBAR_WAIT(b_full + 8 * s, (i / NST) & 1, 6);
+        TRACE(5);
+        uint32_t qw[24];
+#pragma unroll
+        for (int c = 0; c < C::DCH; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(qtile + chunk_off(g * C::DCH + c));
+          qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
+        }
+        qw[20] = qw[21] = qw[22] = qw[23] = 0u;
+        tmem_st_x16(tw + O_COL, qw);
+        tmem_st_x8(tw + O_COL + 16, qw + 16);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(b_qrdy + 8 * g);
+        TRACE(6);
+        if constexpr (STATS) mbar_arrive(b_odone + 8 * s);  // pass 1 only reads Q
+      };
+      if (!active) {  // no head for this warpgroup in these tiles: just hand them back
+        for (int i = r0; i < r1; ++i) {
+          MBAR_WAIT(b_full + 8 * (i % NST), (i / NST) & 1, 6);
+          if constexpr (!STATS) fence_proxy_async();
+          mbar_arrive(b_odone + 8 * (i % NST));
+        }
+        r0 = r1;
+        continue;
+      }
+      stage_q(r0);
       for (int i = r0; i < r1; ++i) {
         const int s = i % NST;
         const int l0 = (it0.tile + (i - r0)) * C::ROWS;
         const int rows = min(C::ROWS, p.L - l0);
         unsigned char* qtile = smem + KV_BYTES + s * STAGE_BYTES;
+        // ---- S row
         TRACE(10);
-        MBAR_WAIT(b_full + 8 * s, (i / NST) & 1, 6);
-        TRACE(5);
-        if (active) {
-          // ---- Q row of head g -> TMEM (first 24 columns of the O region; columns 20..23 = zero K padding)
-          {
-            uint32_t qw[24];
-#pragma unroll
-            for (int c = 0; c < C::DCH; ++c) {
-              const uint4 v = *reinterpret_cast<const uint4*>(qtile + chunk_off(g * C::DCH + c));
-              qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
-            }
-            qw[20] = qw[21] = qw[22] = qw[23] = 0u;
-            tmem_st_x16(tw + O_COL, qw);
-            tmem_st_x8(tw + O_COL + 16, qw + 16);
-            tc_wait_st();
+        MBAR_WAIT(b_srdy + 8 * g, n & 1, 8);
+        TRACE(11);
+        tc_fence_after();
+        float sc[80];
+        tmem_ld_x64(tw + S_COL, reinterpret_cast<uint32_t*>(sc));
+        tmem_ld_x16(tw + S_COL + 64, reinterpret_cast<uint32_t*>(sc) + 64);
+        tc_wait_ld();
+        TRACE(12);
+        if constexpr (STATS) {
+          if (i + 1 < r1) {  // S is in registers: the next tile's Q K^T may run under this tile's accumulation
             tc_fence_before();
-            mbar_arrive(b_qrdy + 8 * g);
+            stage_q(i + 1);
           }
-          TRACE(6);
-          if constexpr (STATS) mbar_arrive(b_odone + 8 * s);  // pass 1 only reads Q
-          // ---- S row
-          MBAR_WAIT(b_srdy + 8 * g, n & 1, 8);
-          TRACE(11);
-          tc_fence_after();
-          float sc[80];
-          tmem_ld_x64(tw + S_COL, reinterpret_cast<uint32_t*>(sc));
-          tmem_ld_x16(tw + S_COL + 64, reinterpret_cast<uint32_t*>(sc) + 64);
-          tc_wait_ld();
-          TRACE(12);
-          if constexpr (STATS) {
-            float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+          float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 80; ++j) {
-              fs[j & 3] += sc[j];
-              fq[j & 3] = fmaf(sc[j], sc[j], fq[j & 3]);
-            }
-            if (row < rows) {
-              dsum += static_cast<double>((fs[0] + fs[1]) + (fs[2] + fs[3]));
-              dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
-            }
-          } else {
-            // logits in the log2 domain: s*scale*log2e + beta*log2e*W, W streamed from the shared tile
-            const float* wsrc = p.W + ((static_cast<long long>(it0.b / (p.B / p.Bw)) * p.L + l0) * p.S);
-            const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.S * 4)) & 15) == 0;
-            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            if (bulk) {
-              const float* wt = reinterpret_cast<const float*>(qtile + C::QT_BYTES) + row * p.S;
-              if (p.S == 77) {
+          for (int j = 0; j < 80; ++j) {
+            fs[j & 3] += sc[j];
+            fq[j & 3] = fmaf(sc[j], sc[j], fq[j & 3]);
+          }
+          if (row < rows) {
+            dsum += static_cast<double>((fs[0] + fs[1]) + (fs[2] + fs[3]));
+            dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
+          }
+        } else {
+          // logits in the log2 domain: s*scale*log2e + beta*log2e*W, W streamed from the shared tile
+          const float* wsrc = p.W + ((static_cast<long long>(it0.b / (p.B / p.Bw)) * p.L + l0) * p.S);
+          const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.S * 4)) & 15) == 0;
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if (bulk) {
+            const float* wt = reinterpret_cast<const float*>(qtile + C::QT_BYTES) + row * p.S;
+            if (p.S == 77) {
 #pragma unroll
-                for (int j = 0; j < 77; ++j) {
-                  sc[j] = fmaf(sc[j], scale_l2, wt[j] * beta_l2);
-                  mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
-                }
-                sc[77] = sc[78] = sc[79] = -INFINITY;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 80; ++j) {
-                  sc[j] = (j < p.S) ? fmaf(sc[j], scale_l2, wt[j] * beta_l2) : -INFINITY;
-                  mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
-                }
+              for (int j = 0; j < 77; ++j) {
+                sc[j] = fmaf(sc[j], scale_l2, wt[j] * beta_l2);
+                mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
               }
+              sc[77] = sc[78] = sc[79] = -INFINITY;
             } else {
-              const float* wr = wsrc + static_cast<long long>(row < rows ? row : 0) * p.S;
 #pragma unroll
               for (int j = 0; j < 80; ++j) {
-                sc[j] = (j < p.S) ? fmaf(sc[j], scale_l2, __ldg(wr + j) * beta_l2) : -INFINITY;
+                sc[j] = (j < p.S) ? fmaf(sc[j], scale_l2, wt[j] * beta_l2) : -INFINITY;
                 mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
               }
             }
-            const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-            uint32_t pw[40];
+          } else {
+            const float* wr = wsrc + static_cast<long long>(row < rows ? row : 0) * p.S;
 #pragma unroll
-            for (int j = 0; j < 40; ++j) pw[j] = Mma<T>::pack(ex2_approx(sc[2 * j] - m), ex2_approx(sc[2 * j + 1] - m));
-            TRACE(14);
-            tmem_st_x32(tw + S_COL, pw);  // P over the first 40 columns of S (the whole S row is in registers)
-            tmem_st_x8(tw + S_COL + 32, pw + 32);
-            tc_wait_st();
-            tc_fence_before();
-            mbar_arrive(b_prdy + 8 * g);
-            TRACE(16);
-            // ---- O row
-            MBAR_WAIT(b_ordy + 8 * g, n & 1, 5);
-            TRACE(17);
-            tc_fence_after();
-            float o[48];
-            tmem_ld_x32(tw + O_COL, reinterpret_cast<uint32_t*>(o));
-            tmem_ld_x16(tw + O_COL + 32, reinterpret_cast<uint32_t*>(o) + 32);
-            tc_wait_ld();
-            const float inv = 1.f / o[D];
-#pragma unroll
-            for (int c = 0; c < C::DCH; ++c) {
-              uint4 v;
-              v.x = Mma<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
-              v.y = Mma<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
-              v.z = Mma<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
-              v.w = Mma<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
-              *reinterpret_cast<uint4*>(qtile + chunk_off(g * C::DCH + c)) = v;
+            for (int j = 0; j < 80; ++j) {
+              sc[j] = (j < p.S) ? fmaf(sc[j], scale_l2, __ldg(wr + j) * beta_l2) : -INFINITY;
+              mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
             }
-            TRACE(18);
-            tc_fence_before();  // the next Q operand overwrites the O columns: order the TMEM reads before it
           }
-          ++n;
-        } else if constexpr (STATS) {
-          mbar_arrive(b_odone + 8 * s);
-        }
-        if constexpr (!STATS) {
+          const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          uint32_t pw[40];
+#pragma unroll
+          for (int j = 0; j < 40; ++j) pw[j] = Mma<T>::pack(ex2_approx(sc[2 * j] - m), ex2_approx(sc[2 * j + 1] - m));
+          // (ex2.approx.f16x2 was tried to halve the MUFU work: on sm_100a it lowers to two MUFU.EX2.F16 plus
+          //  repacking, i.e. more issue slots for the same MUFU count -- measured slower)
+          TRACE(14);
+          tmem_st_x32(tw + S_COL, pw);  // P over the first 40 columns of S (the whole S row is in registers)
+          tmem_st_x8(tw + S_COL + 32, pw + 32);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(b_prdy + 8 * g);
+          TRACE(16);
+          // ---- O row
+          MBAR_WAIT(b_ordy + 8 * g, n & 1, 5);
+          TRACE(17);
+          tc_fence_after();
+          float o[48];
+          tmem_ld_x32(tw + O_COL, reinterpret_cast<uint32_t*>(o));
+          tmem_ld_x16(tw + O_COL + 32, reinterpret_cast<uint32_t*>(o) + 32);
+          tc_wait_ld();
+          if (i + 1 < r1) {  // the O columns are free again: next tile's Q -> TMEM now, its Q K^T runs under the O store
+            tc_fence_before();
+            stage_q(i + 1);
+          }
+          const float inv = 1.f / o[D];
+#pragma unroll
+          for (int c = 0; c < C::DCH; ++c) {
+            uint4 v;
+            v.x = Mma<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
+            v.y = Mma<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+            v.z = Mma<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+            v.w = Mma<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+            *reinterpret_cast<uint4*>(qtile + chunk_off(g * C::DCH + c)) = v;
+          }
+          TRACE(18);
           fence_proxy_async();
           mbar_arrive(b_odone + 8 * s);
         }
+        ++n;
       }
       r0 = r1;
     }
@@ -1075,37 +1116,24 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         red[16 + warp] = dsq;
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (tid == 0) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < 16; ++w) {
-          a += red[w];
-          b += red[16 + w];
-        }
-        double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
-        partials[2 * blockIdx.x] = a;
-        partials[2 * blockIdx.x + 1] = b;
-        __threadfence();
-        const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
-        if (t == gridDim.x - 1) {
-          __threadfence();
-          double sa = 0.0, sb = 0.0;
-          for (unsigned int c = 0; c < gridDim.x; ++c) {
-            sa += __ldcg(partials + 2 * c);
-            sb += __ldcg(partials + 2 * c + 1);
+      double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
+      if (warp == 0) {
+        unsigned int last = 0;
+        if (lane == 0) {
+          double a = 0.0, b = 0.0;
+          for (int w = 0; w < 16; ++w) {
+            a += red[w];
+            b += red[16 + w];
           }
-          const double scl = static_cast<double>(p.scale);
-          const double nn = static_cast<double>(p.B) * p.H * static_cast<double>(p.L) * p.S;
-          const double sum = sa * scl, sumsq = sb * scl * scl, mean = sum / nn;
-          double var = (nn > 1.0) ? (sumsq - sum * mean) / (nn - 1.0) : nan("");
-          if (var < 0.0) var = 0.0;
-          p.ws->std_unbiased = static_cast<float>(sqrt(var));
-          p.ws->mean = static_cast<float>(mean);
-          p.ws->sum = sum;
-          p.ws->sumsq = sumsq;
-          p.ws->n = nn;
-          p.ws->n_partials = gridDim.x;
+          partials[2 * blockIdx.x] = a;
+          partials[2 * blockIdx.x + 1] = b;
           __threadfence();
-          p.ws->ticket = 0u;
+          last = atomicAdd(&p.ws->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {  // last CTA: fold all partials (deterministic order)
+          __threadfence();
+          finalize_stats(p, partials, lane);
         }
       }
     }
@@ -1116,6 +1144,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   __syncthreads();
   tc_fence_after();
   TRACE(30);
+  CTA_TIME(1);
   if (warp == 16) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
@@ -1188,6 +1217,13 @@ extern "C" int dsc_debug_trace(long long* out /*HOST 4*512*2*/, int* counts /*HO
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 4 * 512 * 2);
   cudaMemcpyFromSymbol(counts, g_trace_n, sizeof(int) * 4);
+  { static unsigned long long ct[160][2]; cudaMemcpyFromSymbol(ct, g_cta_times, sizeof(ct));
+    unsigned long long t0 = ~0ull, t1 = 0; for (int i = 0; i < 148; ++i) { if (ct[i][0] && ct[i][0] < t0) t0 = ct[i][0]; if (ct[i][1] > t1) t1 = ct[i][1]; }
+    printf("cta times (ns, last kernel): span %llu;", t1 - t0);
+    unsigned long long smin = ~0ull, smax = 0, dmin = ~0ull, dmax = 0;
+    for (int i = 0; i < 148; ++i) { unsigned long long st = ct[i][0] - t0, d = ct[i][1] - ct[i][0]; if (st < smin) smin = st; if (st > smax) smax = st; if (d < dmin) dmin = d; if (d > dmax) dmax = d; }
+    printf(" start offsets %llu..%llu; durations %llu..%llu\n", smin, smax, dmin, dmax);
+    printf("cta durations ns:"); for (int i = 0; i < 148; ++i) printf(" %llu", ct[i][1] - ct[i][0]); printf("\n"); }
   { long long kv[8]; cudaMemcpyFromSymbol(kv, g_kv_trace, sizeof(kv));
     printf("kv staging (block 0, thread 0, last call): enter->loads_issued %lld, ->k_stored %lld, ->v_stored %lld, ->fenced %lld cycles\n",
            kv[1] - kv[0], kv[2] - kv[0], kv[3] - kv[0], kv[4] - kv[0]); }
