@@ -18,6 +18,8 @@
 //   the 77-key score rows live in registers (10 n-tiles x 4), softmax row reductions are quad shuffles,
 //   the W tile is read once per slice and reused by all heads of the group,
 //   O overwrites the warp's Q slice in shared memory and leaves through TMA bulk stores.
+#include <stdlib.h>
+
 #include "dsc_device.cuh"
 #include "dsc_internal.h"
 
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(256, 1) xattn_stats_kernel(const XattnParams p
   constexpr int PITCH = TL::PITCH;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: pass 2 may start its prologue early
   const uint32_t sK = smem_u32(smem);
   const uint32_t sQ = sK + TL::KV_BYTES + warp * 2 * TL::QS_BYTES;  // two stages per warp
   const uint32_t bars = sK + TL::KV_BYTES + TL::WARPS * 2 * TL::QS_BYTES;
@@ -345,9 +348,10 @@ __global__ void __launch_bounds__(256, 1) xattn_forward_kernel(const XattnParams
   T* __restrict__ out = reinterpret_cast<T*>(p.out);
   const uint64_t pol_stream = policy_evict_first();  // Q and W are dead after this pass
 
-  // beta = sigma * std(a), folded with log2(e): softmax runs in the exp2 domain
-  const float sigma = p.sigma_dev ? __ldg(p.sigma_dev) : p.sigma_host;
-  const float beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2e;
+  // beta = sigma * std(a), folded with log2(e): softmax runs in the exp2 domain.  Read lazily: with programmatic
+  // dependent launch this kernel starts (barrier init, K/V and first Q/W copies) while pass 1 is still finishing.
+  float beta_l2 = 0.f;
+  bool have_beta = false;
   const float scale_l2 = p.scale * kLog2e;
   const int w_rep = p.B / p.Bw;
 
@@ -401,6 +405,12 @@ __global__ void __launch_bounds__(256, 1) xattn_forward_kernel(const XattnParams
       const int l0 = static_cast<int>(sl % p.n_sl) * TL::ROWS;
       const int rows = min(TL::ROWS, p.L - l0);
 
+      if (!have_beta) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // pass 1 has published the std
+        const float sigma = p.sigma_dev ? __ldcg(p.sigma_dev) : p.sigma_host;
+        beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2e;
+        have_beta = true;
+      }
       // beta*W in the accumulator layout, shared by all heads of the group; columns >= S get -inf
       float bw[10][4];
 #pragma unroll
@@ -518,8 +528,18 @@ static cudaError_t launch_forward(const XattnParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured_dev = dev;
   }
-  xattn_forward_kernel<T, D><<<grid_for(p.total), 256, Tile<D>::FWD_SMEM, st>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid_for(p.total));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = Tile<D>::FWD_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const char* nopdl = getenv("DSC_NO_PDL");
+  cfg.attrs = attr;
+  cfg.numAttrs = (nopdl && nopdl[0] == '1') ? 0 : 1;  // may overlap the tail of pass 1 (griddepcontrol.wait before beta)
+  return cudaLaunchKernelEx(&cfg, xattn_forward_kernel<T, D>, p);
 }
 
 int heads_per_group(int D) {

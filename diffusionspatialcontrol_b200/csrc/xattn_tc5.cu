@@ -171,6 +171,10 @@ constexpr int kConsumerRegs = 224;  // setmaxnreg: 8 x 32 x 224 + 4 x 32 x 56 = 
 constexpr int kServiceRegs = 56;
 
 // ---------------------------------------------------------------- tcgen05 plumbing
+// programmatic dependent launch (PDL): pass 2 is launched while pass 1 still runs; it may do everything that does
+// not need the std (barrier init, TMEM alloc, K/V staging, first Q tiles, first QK^T) and blocks here before beta.
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -392,6 +396,7 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TRACE_DECL
+  if constexpr (STATS) pdl_launch_dependents();
   {  // first thing: start pulling this CTA's first K / V head group into L2
     const int begin0 = static_cast<int>(p.total * blockIdx.x / gridDim.x);
     if (tid < kConsumerThreads && begin0 < p.total) prefetch_kv<T, D, STATS, kConsumerThreads>(p, decode<D>(begin0, p), tid);
@@ -549,8 +554,8 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
       return (cg >> 2) * C::BOX_BYTES + row_off + ((static_cast<uint32_t>(cg & 3) ^ row_sw) << 4);
     };
     const uint32_t tw = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * C::WG_COLS;
-    const float sigma = STATS ? 0.f : (p.sigma_dev ? __ldg(p.sigma_dev) : p.sigma_host);
-    const float beta_l2 = STATS ? 0.f : sigma * __ldcg(&p.ws->std_unbiased) * kLog2eT;
+    float beta_l2 = 0.f;  // read after pass 1 has completed (PDL), right before first use
+    bool have_beta = STATS;
     const float scale_l2 = p.scale * kLog2eT;
     if constexpr (D % 16 == 8) {  // zero the K-padding columns of the A operand once
       uint32_t z[4] = {0, 0, 0, 0};
@@ -688,6 +693,12 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
               dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
             }
           } else {
+            if (!have_beta) {
+              pdl_wait_prior_grid();
+              const float sigma = p.sigma_dev ? __ldcg(p.sigma_dev) : p.sigma_host;
+              beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2eT;
+              have_beta = true;
+            }
             if (hi == 0) {  // beta*W row (log2 domain), shared by this row's heads; keys >= S get -inf
               const float* wsrc = wbase + static_cast<long long>(l0) * p.S;
               const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.S * 4)) & 15) == 0;
@@ -821,6 +832,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   TRACE_DECL_X4
   TRACE(1);
   CTA_TIME(0);
+  if constexpr (STATS) pdl_launch_dependents();  // let pass 2 start its prologue on SMs as they free up
   {  // first thing: start pulling this CTA's first K / V head group into L2
     const int begin0 = static_cast<int>(p.total * blockIdx.x / gridDim.x);
     if (tid < kX4Consumers && begin0 < p.total) prefetch_kv<T, 40, STATS, kX4Consumers>(p, decode<40>(begin0, p), tid);
@@ -953,8 +965,8 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
       return (cg >> 2) * C::BOX_BYTES + row_off + ((static_cast<uint32_t>(cg & 3) ^ row_sw) << 4);
     };
     const uint32_t tw = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * WG_COLS;
-    const float sigma = STATS ? 0.f : (p.sigma_dev ? __ldg(p.sigma_dev) : p.sigma_host);
-    const float beta_l2 = STATS ? 0.f : sigma * __ldcg(&p.ws->std_unbiased) * kLog2eT;
+    float beta_l2 = 0.f;     // sigma * std * log2(e); read after pass 1 has completed (PDL), right before first use
+    bool have_beta = STATS;
     const float scale_l2 = p.scale * kLog2eT;
     double dsum = 0.0, dsq = 0.0;
     uint32_t n = 0;
@@ -1032,6 +1044,12 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
             dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
           }
         } else {
+          if (!have_beta) {
+            pdl_wait_prior_grid();  // pass 1 (same stream, launched just before) has published the std
+            const float sigma = p.sigma_dev ? __ldcg(p.sigma_dev) : p.sigma_host;
+            beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2eT;
+            have_beta = true;
+          }
           // logits in the log2 domain: s*scale*log2e + beta*log2e*W, W streamed from the shared tile
           const float* wsrc = p.W + ((static_cast<long long>(it0.b / (p.B / p.Bw)) * p.L + l0) * p.S);
           const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.S * 4)) & 15) == 0;
@@ -1199,8 +1217,18 @@ static cudaError_t launch_tc5(XattnParams p, cudaStream_t st) {
   if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
   const int sms = sm_count_cached();
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
-  xattn_tc5_kernel<T, D, STATS><<<grid, kThreads, smem, st>>>(p, tm_q, tm_o);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const char* nopdl = getenv("DSC_NO_PDL");
+  cfg.attrs = attr;
+  cfg.numAttrs = (!STATS && !(nopdl && nopdl[0] == '1')) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, xattn_tc5_kernel<T, D, STATS>, p, tm_q, tm_o);
 }
 
 #ifdef DSC_WATCHDOG
@@ -1256,8 +1284,18 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   const int sms = sm_count_cached();
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
   { const char* e = getenv("DSC_X4_STAGGER_NS"); p.stagger_ns = e ? static_cast<unsigned>(atoi(e)) : 0u; }
-  xattn_tc5x4_kernel<T, STATS><<<grid, kX4Threads, smem, st>>>(p, tm_q, tm_o);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kX4Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const char* nopdl = getenv("DSC_NO_PDL");
+  cfg.attrs = attr;
+  cfg.numAttrs = (!STATS && !(nopdl && nopdl[0] == '1')) ? 1 : 0;  // pass 2 may overlap the tail of pass 1
+  return cudaLaunchKernelEx(&cfg, xattn_tc5x4_kernel<T, STATS>, p, tm_q, tm_o);
 }
 
 // D = 40 has two tcgen05 variants: "x4" (4 consumer warpgroups, one head each; default) and "x2" (2 warpgroups,
