@@ -120,8 +120,11 @@ def build_pipeline(device):
     from diffusionspatialcontrol_b200.unet_sd15 import UNetSD15
 
     torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True  # PyTorch-side conv autotuning for the UNet host (not our kernels)
     unet = UNetSD15().to(device=device, dtype=torch.float16).eval()
-    return RegionTxt2ImgPipeline(unet, SyntheticTokenizer(VOCAB))
+    if not os.environ.get("DSC_BENCH_NO_CHANNELS_LAST"):
+        unet = unet.to(memory_format=torch.channels_last)
+    return RegionTxt2ImgPipeline(unet, SyntheticTokenizer(VOCAB), use_cuda_graph=not os.environ.get("DSC_BENCH_NO_GRAPH"))
 
 
 def attention_roofline(device):
@@ -156,32 +159,38 @@ def attention_roofline(device):
             check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, None, 7.0,
                                         ws.data_ptr(), out.data_ptr(), os_, B, H, L, D, S, sc, 0, st))
 
-        for _ in range(3):
+        def call():  # one attention call = pass 1 + pass 2 back to back (pass 2 is a programmatic dependent launch)
             k1(); k2()
-        t1, t2 = [], []
+
+        for _ in range(3):
+            call()
+        t1, t2, tc = [], [], []
         for _ in range(20):
-            for fn, acc in ((k1, t1), (k2, t2)):
-                flush.zero_()
+            for fn, acc in ((k1, t1), (k2, t2), (call, tc)):
+                flush.zero_()                                  # evict our inputs (512 MiB write) ...
+                flush[: flush.numel() // 2].view(torch.int64).sum()  # ... and leave clean lines behind
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); fn(); b.record(); b.synchronize()
                 acc.append(a.elapsed_time(b))
         n = len(t1)
         nbytes = 2 * B * H * L * D * 3 + 2 * B * H * S * D * 3 + 4 * B * L * S
-        per_shape[(L, D)] = {"ms_stats": sum(t1) / n, "ms_forward": sum(t2) / n, "bytes": nbytes}
+        per_shape[(L, D)] = {"ms_stats": sum(t1) / n, "ms_forward": sum(t2) / n, "ms_call": sum(tc) / n, "bytes": nbytes}
     (L0, D0) = max(per_shape, key=lambda s: per_shape[s]["bytes"])
     d = per_shape[(L0, D0)]
-    ach = d["bytes"] / ((d["ms_stats"] + d["ms_forward"]) * 1e-3) / 1e9
+    ach = d["bytes"] / (d["ms_call"] * 1e-3) / 1e9
     tot_b = sum(per_shape[s]["bytes"] for s in cross_attention_shapes(HEIGHT, WIDTH))
-    tot_t = sum(per_shape[s]["ms_stats"] + per_shape[s]["ms_forward"] for s in cross_attention_shapes(HEIGHT, WIDTH))
+    tot_t = sum(per_shape[s]["ms_call"] for s in cross_attention_shapes(HEIGHT, WIDTH))
     return {
         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
         "peak_source": how,
-        "kernel": "dsc_xattn_stats + dsc_xattn_forward (both passes of one attention call)",
+        "kernel": "one attention call = dsc_xattn_stats + dsc_xattn_forward, timed as a pair (one CUDA-event pair around the "
+                  "two launches; pass 2 is a programmatic dependent launch of pass 1, as in the pipeline)",
         "shape": {"B": B, "H": H, "L": L0, "D": D0, "S": S, "dtype": "f16"},
-        "algorithmic_bytes_per_call": d["bytes"], "avg_ms_stats": d["ms_stats"], "avg_ms_forward": d["ms_forward"],
+        "algorithmic_bytes_per_call": d["bytes"], "avg_ms_call": d["ms_call"],
+        "avg_ms_stats_alone": d["ms_stats"], "avg_ms_forward_alone": d["ms_forward"],
         "all_16_layers": {"bytes_per_unet_step": tot_b, "ms_per_unet_step": tot_t,
                           "achieved": tot_b / (tot_t * 1e-3) / 1e9, "frac": tot_b / (tot_t * 1e-3) / 1e9 / peak},
-        "l2": "flushed (512 MiB memset) before every timed launch",
+        "l2": "flushed before every timed call (512 MiB write, then a 256 MiB read so that L2 holds clean lines)",
     }
 
 

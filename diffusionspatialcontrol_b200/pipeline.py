@@ -40,11 +40,14 @@ class RegionTxt2ImgPipeline:
     vae_scale_factor = 8
     do_classifier_free_guidance = True
 
-    def __init__(self, unet, tokenizer, processor: Optional[RegionAttnProcessor] = None):
+    def __init__(self, unet, tokenizer, processor: Optional[RegionAttnProcessor] = None, use_cuda_graph: bool = False):
         self.unet = unet
         self.tokenizer = tokenizer
-        self.processor = processor if processor is not None else RegionAttnProcessor(cache_kv=True)
+        # inside a captured graph the K/V projections are replayed as captured, so the Python-side cache is moot there
+        self.processor = processor if processor is not None else RegionAttnProcessor(cache_kv=not use_cuda_graph)
         self.unet.set_attn_processor(self.processor)  # same hook as reference app.py:479-481
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs: Dict[tuple, dict] = {}
 
     @property
     def device(self):
@@ -53,6 +56,46 @@ class RegionTxt2ImgPipeline:
     @property
     def dtype(self):
         return next(self.unet.parameters()).dtype
+
+    # ---- one UNet evaluation, optionally as a captured CUDA graph -------------------------------------------
+    def _graph_state(self, n: int, height: int, width: int, region_state, weight_func) -> dict:
+        """Static buffers + captured graph of ONE denoising-step UNet call (all 32 attention layers, our two passes
+        per cross-attention layer included) for a given batch shape.  Launch-bound glue (hundreds of small PyTorch
+        kernels per step) is replayed with one graph launch; our kernels are capture-safe (no host sync, workspace
+        pre-allocated, tensor maps passed by value)."""
+        key = (n, height, width, self.dtype, tuple(sorted(region_state.keys())))
+        st = self._graphs.get(key)
+        if st is not None:
+            return st
+        dev, dt = self.device, self.dtype
+        st = {
+            "x": torch.zeros((2 * n, self.unet.in_channels, height // 8, width // 8), device=dev, dtype=dt),
+            "t": torch.zeros((), device=dev, dtype=torch.float32),
+            "sigma": torch.zeros((), device=dev, dtype=torch.float32),
+            "ctx": torch.zeros((2 * n, 77, self.unet_ctx_dim()), device=dev, dtype=dt),
+            "rs": {L: torch.zeros_like(w, device=dev, dtype=torch.float32) for L, w in region_state.items()},
+        }
+        rp = {"region_state": st["rs"], "sigma": st["sigma"], "weight_func": weight_func}
+        kw = {"region_prompt": rp}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up on a side stream (allocations, autotuning, workspace)
+            for _ in range(2):
+                self.unet(st["x"], st["t"], st["ctx"], cross_attention_kwargs=kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            # (a channels_last UNet returns a channels_last eps: the sampler kernel wants plain NCHW order)
+            st["eps"] = self.unet(st["x"], st["t"], st["ctx"], cross_attention_kwargs=kw).contiguous()
+        st["graph"] = g
+        self._graphs[key] = st
+        return st
+
+    def unet_ctx_dim(self) -> int:
+        for m in self.unet.modules():
+            if getattr(m, "is_cross_attention", False):
+                return m.to_k.in_features
+        return 768
 
     @torch.no_grad()
     def txt2img(self, prompt_embeds: torch.Tensor, negative_prompt_embeds: torch.Tensor, text_ids,
@@ -73,6 +116,22 @@ class RegionTxt2ImgPipeline:
         x = noise.to(dev, torch.float32) * (sig[0] ** 2 + 1) ** 0.5  # model_k_diffusion.py:1043
         x = x.contiguous()
         den_prev = torch.zeros_like(x)
+        if self.use_cuda_graph:
+            st = self._graph_state(n, height, width, region_state, weight_func)
+            st["ctx"].copy_(ctx)
+            for L, w in region_state.items():
+                st["rs"][L].copy_(w)
+            unet_in = st["x"]
+            unet_in.copy_(torch.cat([x, x]).mul_(sched.c_in(0)))
+            for i in range(num_inference_steps):
+                st["t"].copy_(t_dev[i])
+                st["sigma"].copy_(sig_dev[i])
+                st["graph"].replay()
+                last = i == num_inference_steps - 1
+                # the fused step writes the next UNet input straight into the graph's static input buffer
+                dpmpp2m_step(x, st["eps"], den_prev, None if last else unet_in,
+                             sig[i - 1] if i > 0 else 0.0, sig[i], sig[i + 1], guidance_scale, first=(i == 0))
+            return x
         unet_in = torch.cat([x, x]).mul_(sched.c_in(0)).to(dt).contiguous()
         unet_in_next = torch.empty_like(unet_in)
         for i in range(num_inference_steps):
