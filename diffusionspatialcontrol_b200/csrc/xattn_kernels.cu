@@ -18,6 +18,7 @@
 //   the 77-key score rows live in registers (10 n-tiles x 4), softmax row reductions are quad shuffles,
 //   the W tile is read once per slice and reused by all heads of the group,
 //   O overwrites the warp's Q slice in shared memory and leaves through TMA bulk stores.
+#include <cuda.h>  // CUtensorMap (types only; the encoder comes from cudaGetDriverEntryPoint)
 #include <stdlib.h>
 
 #include "dsc_device.cuh"
@@ -26,6 +27,20 @@
 namespace dsc {
 
 constexpr float kLog2e = 1.4426950408889634f;
+
+// TMA tensor-map box load.  The Q / K / V tensors are described as [B, rows, H*D/2] arrays of 32-bit words so that one
+// box of (G*D/2 + 4) words x R rows lands in shared memory as R rows of PITCH = G*D*2 + 16 bytes -- the padded,
+// ldmatrix-conflict-free layout -- with ONE TMA instruction (a 1-D bulk copy per row costs ~30 ns of TMA issue each,
+// profiles/r1_tma_copy_rate.jsonl: 154 row copies for K and V alone were 4.6 us of every CTA's prologue).  Rows beyond
+// the tensor (keys >= S, queries >= L) and words beyond H*D are zero-filled by the TMA.
+__device__ __forceinline__ void tma_box_load(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t bar,
+                                             uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, "
+      "%5}], [%2], %6;" ::"r"(dst),
+      "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 
 template <int D>
 struct Tile {
@@ -141,7 +156,8 @@ __device__ __forceinline__ Seg seg_of(long long idx, long long cta_end, int n_sl
 // pass 1
 // =============================================================================================
 template <typename T, int D>
-__global__ void __launch_bounds__(256, 1) xattn_stats_kernel(const XattnParams p) {
+__global__ void __launch_bounds__(256, 1)
+xattn_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k) {
   using TL = Tile<D>;
   constexpr int PITCH = TL::PITCH;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -170,32 +186,29 @@ __global__ void __launch_bounds__(256, 1) xattn_stats_kernel(const XattnParams p
   const long long total = p.total;
   const long long cta_begin = total * blockIdx.x / gridDim.x;
   const long long cta_end = total * (blockIdx.x + 1) / gridDim.x;
-  const T* __restrict__ q = reinterpret_cast<const T*>(p.q);
-  const T* __restrict__ k = reinterpret_cast<const T*>(p.k);
   const uint64_t pol_q = policy_evict_last();  // Q is read again by pass 2: ask L2 to keep it
+  const uint64_t pol_kv = policy_evict_last();
 
   double dsum = 0.0, dsq = 0.0;
   uint32_t it = 0, kphase = 0;
 
   for (long long idx = cta_begin; idx < cta_end;) {
     const Seg sg = seg_of<D>(idx, cta_end, p.n_sl, p.n_hg, p.H);
-    const uint32_t row_bytes = sg.nheads * D * 2;
     __syncthreads();  // every warp is done with the previous K
-    if (tid == 0) mbar_arrive_expect_tx(kbar, row_bytes * p.S);
-    __syncthreads();
-    for (int r = tid; r < p.S; r += 256)
-      bulk_g2s(sK + r * PITCH, k + sg.b * p.k_sb + r * p.k_ss + sg.hg * TL::GW, row_bytes, kbar);
+    if (tid == 0) {
+      mbar_arrive_expect_tx(kbar, TL::KV_BYTES);  // the whole 80-row box counts (rows >= S arrive as zeros)
+      tma_box_load(sK, &tm_k, sg.hg * (TL::GW / 2), 0, sg.b, kbar, pol_kv);
+    }
 
     auto issue = [&](long long sl_idx, uint32_t stage) {
       const int l0 = static_cast<int>(sl_idx % p.n_sl) * TL::ROWS;
       const int rows = min(TL::ROWS, p.L - l0);
       const uint32_t bar = qbar + stage * 8;
-      if (lane == 0) mbar_arrive_expect_tx(bar, rows * row_bytes);
-      __syncwarp();
-      if (lane < rows)
-        bulk_g2s_hint(sQ + stage * TL::QS_BYTES + lane * PITCH,
-                      q + sg.b * p.q_sb + static_cast<long long>(l0 + lane) * p.q_sl + sg.hg * TL::GW, row_bytes, bar,
-                      pol_q);
+      (void)rows;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar, TL::QS_BYTES);
+        tma_box_load(sQ + stage * TL::QS_BYTES, &tm_q, sg.hg * (TL::GW / 2), l0, sg.b, bar, pol_q);
+      }
     };
 
     const long long first = idx + warp;
@@ -307,7 +320,9 @@ __global__ void __launch_bounds__(256, 1) xattn_stats_kernel(const XattnParams p
 // pass 2
 // =============================================================================================
 template <typename T, int D>
-__global__ void __launch_bounds__(256, 1) xattn_forward_kernel(const XattnParams p) {
+__global__ void __launch_bounds__(256, 1)
+xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                     const __grid_constant__ CUtensorMap tm_v) {
   using TL = Tile<D>;
   constexpr int PITCH = TL::PITCH;
   constexpr int ND = TL::ND;
@@ -342,9 +357,6 @@ __global__ void __launch_bounds__(256, 1) xattn_forward_kernel(const XattnParams
   const long long total = p.total;
   const long long cta_begin = total * blockIdx.x / gridDim.x;
   const long long cta_end = total * (blockIdx.x + 1) / gridDim.x;
-  const T* __restrict__ q = reinterpret_cast<const T*>(p.q);
-  const T* __restrict__ k = reinterpret_cast<const T*>(p.k);
-  const T* __restrict__ v = reinterpret_cast<const T*>(p.v);
   T* __restrict__ out = reinterpret_cast<T*>(p.out);
   const uint64_t pol_stream = policy_evict_first();  // Q and W are dead after this pass
 
@@ -362,14 +374,11 @@ __global__ void __launch_bounds__(256, 1) xattn_forward_kernel(const XattnParams
     const uint32_t row_bytes = sg.nheads * D * 2;
     const float* Wb = p.W + static_cast<long long>(sg.b / w_rep) * p.L * p.S;
     __syncthreads();  // every warp is done with the previous K/V
-    if (tid == 0) mbar_arrive_expect_tx(kvbar, 2 * row_bytes * p.S);
-    __syncthreads();
-    for (int r = tid; r < 2 * p.S; r += 256) {
-      const int rr = r < p.S ? r : r - p.S;
-      if (r < p.S)
-        bulk_g2s(sK + rr * PITCH, k + sg.b * p.k_sb + rr * p.k_ss + sg.hg * TL::GW, row_bytes, kvbar);
-      else
-        bulk_g2s(sV + rr * PITCH, v + sg.b * p.v_sb + rr * p.v_ss + sg.hg * TL::GW, row_bytes, kvbar);
+    if (tid == 0) {
+      mbar_arrive_expect_tx(kvbar, 2 * TL::KV_BYTES);  // two 80-row boxes; rows >= S arrive as zeros
+      const uint64_t pol_kv = policy_evict_last();
+      tma_box_load(sK, &tm_k, sg.hg * (TL::GW / 2), 0, sg.b, kvbar, pol_kv);
+      tma_box_load(sV, &tm_v, sg.hg * (TL::GW / 2), 0, sg.b, kvbar, pol_kv);
     }
 
     auto issue = [&](long long sl_idx) {
@@ -378,11 +387,10 @@ __global__ void __launch_bounds__(256, 1) xattn_forward_kernel(const XattnParams
       const float* wsrc = Wb + static_cast<long long>(l0) * p.S;
       const uint32_t wbytes = rows * p.S * 4;
       const bool w_bulk = ((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0;
-      if (lane == 0) mbar_arrive_expect_tx(qbar, rows * row_bytes + (w_bulk ? wbytes : 0));
-      __syncwarp();
-      if (lane < rows)
-        bulk_g2s_hint(sQ + lane * PITCH, q + sg.b * p.q_sb + static_cast<long long>(l0 + lane) * p.q_sl + sg.hg * TL::GW,
-                      row_bytes, qbar, pol_stream);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(qbar, TL::QS_BYTES + (w_bulk ? wbytes : 0));
+        tma_box_load(sQ, &tm_q, sg.hg * (TL::GW / 2), l0, sg.b, qbar, pol_stream);
+      }
       if (w_bulk) {
         if (lane == 16) bulk_g2s_hint(sW, wsrc, wbytes, qbar, pol_stream);
       } else {  // odd tail / unaligned W: plain loads (visible to this warp after the __syncwarp below)
@@ -502,36 +510,73 @@ static int grid_for(long long total) {
   return static_cast<int>(want < sms ? want : sms);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// [B, rows, cols] 16-bit tensor (element strides sb, sr, 1) seen as 32-bit words; box = (box_words, box_rows, 1)
+static bool make_map32(CUtensorMap* m, const void* base, int cols, int rows, int B, long long sr, long long sb,
+                       int box_words, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols / 2), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(sr) * 2, static_cast<cuuint64_t>(B > 1 ? sb : sr * rows) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_words), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename T, int D>
 static cudaError_t launch_stats(const XattnParams& p, cudaStream_t st) {
+  using TL = Tile<D>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
     cudaError_t e = cudaFuncSetAttribute(xattn_stats_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Tile<D>::STATS_SMEM);
+                                         TL::STATS_SMEM);
     if (e != cudaSuccess) return e;
     configured_dev = dev;
   }
-  xattn_stats_kernel<T, D><<<grid_for(p.total), 256, Tile<D>::STATS_SMEM, st>>>(p);
+  CUtensorMap tm_q, tm_k;
+  if (!make_map32(&tm_q, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, TL::PITCH / 4, TL::ROWS) ||
+      !make_map32(&tm_k, p.k, p.H * D, p.S, p.B, p.k_ss, p.k_sb, TL::PITCH / 4, TL::KV_ROWS))
+    return cudaErrorInvalidValue;
+  xattn_stats_kernel<T, D><<<grid_for(p.total), 256, TL::STATS_SMEM, st>>>(p, tm_q, tm_k);
   return cudaGetLastError();
 }
 
 template <typename T, int D>
 static cudaError_t launch_forward(const XattnParams& p, cudaStream_t st) {
+  using TL = Tile<D>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
     cudaError_t e = cudaFuncSetAttribute(xattn_forward_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Tile<D>::FWD_SMEM);
+                                         TL::FWD_SMEM);
     if (e != cudaSuccess) return e;
     configured_dev = dev;
   }
+  CUtensorMap tm_q, tm_k, tm_v;
+  if (!make_map32(&tm_q, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, TL::PITCH / 4, TL::ROWS) ||
+      !make_map32(&tm_k, p.k, p.H * D, p.S, p.B, p.k_ss, p.k_sb, TL::PITCH / 4, TL::KV_ROWS) ||
+      !make_map32(&tm_v, p.v, p.H * D, p.S, p.B, p.v_ss, p.v_sb, TL::PITCH / 4, TL::KV_ROWS))
+    return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid_for(p.total));
   cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = Tile<D>::FWD_SMEM;
+  cfg.dynamicSmemBytes = TL::FWD_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -539,7 +584,7 @@ static cudaError_t launch_forward(const XattnParams& p, cudaStream_t st) {
   const char* nopdl = getenv("DSC_NO_PDL");
   cfg.attrs = attr;
   cfg.numAttrs = (nopdl && nopdl[0] == '1') ? 0 : 1;  // may overlap the tail of pass 1 (griddepcontrol.wait before beta)
-  return cudaLaunchKernelEx(&cfg, xattn_forward_kernel<T, D>, p);
+  return cudaLaunchKernelEx(&cfg, xattn_forward_kernel<T, D>, p, tm_q, tm_k, tm_v);
 }
 
 int heads_per_group(int D) {

@@ -97,6 +97,33 @@ def bench_shape(B, H, L, D, S, dtype, flush, iters=30, ref=True):
 
     for _ in range(5):
         both()
+    # sustained: calls back to back over NSET rotating input/output sets whose total footprint exceeds L2
+    nset = max(2, int(math.ceil(3 * 126e6 / alg_bytes(B, H, L, D, S, B))))
+    sets = []
+    for i in range(nset):
+        qi, ki, vi, oi = torch.randn_like(q), torch.randn_like(k), torch.randn_like(v), torch.empty_like(out)
+        Wi = W.clone()
+        sets.append((qi, ki, vi, Wi, oi))
+
+    def call_set(t):
+        qi, ki, vi, Wi, oi = t
+        check(lib.dsc_xattn_stats(qi.data_ptr(), ki.data_ptr(), qs, ks, None, B, H, L, D, S, scale, dt, ws.data_ptr(), st))
+        check(lib.dsc_xattn_forward(qi.data_ptr(), ki.data_ptr(), vi.data_ptr(), qs, ks, vs, Wi.data_ptr(), B, None, 7.0,
+                                    ws.data_ptr(), oi.data_ptr(), os_, B, H, L, D, S, scale, dt, st))
+
+    for t in sets:
+        call_set(t)
+    reps = 5
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        for t in sets:
+            call_set(t)
+    b.record()
+    b.synchronize()
+    ms_sustained = a.elapsed_time(b) / (reps * nset)
+    del sets
     fns = [k1, k2, both] + ([eager] if ref else [])
     if ref:
         eager()
@@ -108,6 +135,8 @@ def bench_shape(B, H, L, D, S, dtype, flush, iters=30, ref=True):
         "ms_stats": t[0], "ms_forward": t[1], "ms_both": t[2], "ms_sum": t[0] + t[1],
         "alg_bytes": nbytes, "gbs": nbytes / (t[2] * 1e-3) / 1e9, "frac": nbytes / (t[2] * 1e-3) / 1e9 / peak,
         "peak_gbs": peak, "peak": how,
+        "ms_call_sustained": ms_sustained, "sustained_sets": nset,
+        "gbs_sustained": nbytes / (ms_sustained * 1e-3) / 1e9, "frac_sustained": nbytes / (ms_sustained * 1e-3) / 1e9 / peak,
     }
     if ref:
         rec["ms_eager_fp16_reference_sequence"] = t[3]
