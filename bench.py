@@ -180,8 +180,12 @@ def attention_roofline(device):
     ach = d["bytes"] / (d["ms_call"] * 1e-3) / 1e9
     tot_b = sum(per_shape[s]["bytes"] for s in cross_attention_shapes(HEIGHT, WIDTH))
     tot_t = sum(per_shape[s]["ms_call"] for s in cross_attention_shapes(HEIGHT, WIDTH))
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of both passes from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.isfile(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_call")
     return {
-        "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
         "peak_source": how,
         "kernel": "one attention call = dsc_xattn_stats + dsc_xattn_forward, timed as a pair (one CUDA-event pair around the "
                   "two launches; pass 2 is a programmatic dependent launch of pass 1, as in the pipeline)",

@@ -191,3 +191,11 @@ class RegionAttnProcessor:
             hidden_states = hidden_states + residual
         hidden_states = hidden_states / getattr(attn, "rescale_output_factor", 1.0)
         return hidden_states
+
+
+class RegionAttnProcessorBaddbmm(RegionAttnProcessor):
+    """Drop-in for the reference's ``AttnProcessor`` (source/modules/attention_modify.py:107-207), the
+    ``torch.baddbmm`` variant the reference falls back to when ``F.scaled_dot_product_attention`` is missing
+    (source/app.py:479-481).  Its region branch (:164-175 via ``get_attention_scores`` :39-70) computes exactly the
+    same scores, std, bias, softmax and PV as the SDPA-style function (bit-identical on CPU fp32), so
+    the same two CUDA passes serve it; the class exists so either reference processor can be swapped by name."""

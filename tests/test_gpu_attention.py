@@ -249,3 +249,30 @@ def test_processor_matches_reference_processor_restatement(C, D, L):
         proc(attn16, hs, encoder_hidden_states=ctx, region_prompt={**rp, "weight_func": lambda w, s, qk: w * s})
     with pytest.raises(KeyError):
         proc(attn16, hs[:, :64], encoder_hidden_states=ctx, region_prompt=rp)
+
+
+def test_tc5_two_warpgroup_variant_matches_oracle(monkeypatch):
+    """D = 40 has two tcgen05 variants; the default tests exercise x4, this one forces x2 (software-pipelined heads)."""
+    dsc, _ = _dsc()
+    monkeypatch.setenv("DSC_XATTN_IMPL", "tc5")
+    monkeypatch.setenv("DSC_TC5_VARIANT", "x2")
+    for (B, H, L, S) in [(2, 8, 1024, 77), (16, 8, 4096, 77), (3, 12, 200, 40)]:
+        q, k, v = make_qkv(B, H, L, 40, S, seed=L + S, device="cuda")
+        W = synthetic_w(B, L, S).cuda()
+        out = dsc.region_attention(q, k, v, W, 6.0)
+        assert rel_l2(out.float(), _oracle(q, k, v, W, 6.0)) <= TOL
+
+
+def test_config3_shapes_768_batch4_with_suppression():
+    """BASELINE configs[2]: 768x768 (9216 / 2304 / 576 / 144 queries), batch 4 + CFG = 8, maps with negative entries
+    (nonzero S' suppression) from the reference-generated golden region maps."""
+    dsc, _ = _dsc()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "region_768_4reg.npz"))
+    for (L, D) in [(9216, 40), (2304, 80), (576, 160), (144, 160)]:
+        W1 = torch.from_numpy(z[f"W_{L}"])  # [2, L, 77], uncond == cond rows (reference quirk)
+        assert (W1 < 0).any() and (W1 > 0).any()
+        W = W1.repeat(4, 1, 1).cuda()       # encode_region_map(...).repeat(num_images_per_prompt): [8, L, 77]
+        q, k, v = make_qkv(8, 8, L, D, 77, seed=L, device="cuda")
+        for sigma in (14.6146, 0.3350):
+            out = dsc.region_attention(q, k, v, W, sigma)
+            assert rel_l2(out.float(), _oracle(q, k, v, W, sigma)) <= TOL

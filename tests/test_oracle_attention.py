@@ -85,3 +85,38 @@ def test_batch_coupling_is_part_of_the_contract():
     q2[1] *= 3.0
     other = oa.region_attention(q2, k, v, W.clone(), 10.0)
     assert not torch.allclose(full[0], other[0])
+
+
+class _AttnFull(_Attn):
+    """adds what the baddbmm variant touches (attention_modify.py:160-191, :41-68)"""
+
+    upcast_attention = False
+    upcast_softmax = False
+
+    def head_to_batch_dim(self, t, out_dim=3):
+        b, n, c = t.shape
+        t = t.reshape(b, n, self.heads, c // self.heads).permute(0, 2, 1, 3)
+        return t.reshape(b * self.heads, n, c // self.heads) if out_dim == 3 else t
+
+    def batch_to_head_dim(self, t):
+        bh, n, d = t.shape
+        return t.reshape(bh // self.heads, self.heads, n, d).permute(0, 2, 1, 3).reshape(bh // self.heads, n, d * self.heads)
+
+    def prepare_attention_mask(self, m, *_a, **_k):
+        return m
+
+
+@needs_ref
+def test_reference_baddbmm_processor_equals_sdpa_style_processor():
+    """AttnProcessor (:107-207) and AttnProcessor2_0 (:414-503) agree on the region path, so one
+    restatement (and one pair of kernels) covers both."""
+    ref = ref_loader.attention_modify()
+    torch.manual_seed(5)
+    attn = _AttnFull(320, 8, 40)
+    hs, ctx = torch.randn(2, 64, 320), torch.randn(2, 77, 768)
+    rp = {"region_state": {64: synthetic_w(2, 64, 77)}, "sigma": torch.tensor(3.0), "weight_func": weight_func}
+    with torch.no_grad():
+        a = ref.AttnProcessor()(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)
+        b = ref.AttnProcessor2_0()(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)
+        c = oa.processor_forward(attn, hs, ctx, rp)
+    assert torch.allclose(a, b, atol=2e-6, rtol=1e-5) and torch.equal(b, c)
