@@ -804,29 +804,92 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
 }
 
 // =============================================================================================
-// Four consumer warpgroups, one head each (D = 40: the 4 heads of a 160-column tile are processed concurrently).
+// Four consumer warpgroups, ONE HEAD EACH: xattn_tc5x4_kernel (D = 40 and D = 80).
 //
 // Same producer / TMA ring / resident K, V^T / TMEM-operand scheme as xattn_tc5_kernel, but 16 consumer warps
 // (4 per SM sub-partition instead of 2) hide the TMEM and mbarrier round trips of the per-head chain
 //   Q row -> TMEM | S = Q K^T | S row -> softmax -> P -> TMEM | O = P [V|1] | O row -> smem
 // behind each other.  TMEM: 128 columns per warpgroup: S (80 fp32; P overwrites its first 40 columns once the row is
-// in registers) and O (48 fp32; the Q operand occupies its first 24 columns until S is done).  The beta*W row is
-// streamed from the shared W tile (registers are 112 per consumer thread here).  One MMA warp: lane g issues for
-// warpgroup g.
+// in registers) and O (48 fp32; the Q operand occupies its first 24 / 40 columns until S is done).  The beta*W row is
+// streamed from the shared W tile (96 registers per thread here).
+//   D = 40: a 160-column tile holds 4 heads -> warpgroup g = head g, all four on the same tile.
+//   D = 80: a tile holds 2 heads -> warpgroups {0,1} take the even tiles of the CTA's list, {2,3} the odd ones (two
+//           tiles in flight, one per ring stage); O = P V is issued as two N = 48 halves (40 V columns + the ones
+//           column) so that the O region stays 48 columns wide.  V^T is staged as 40-column "virtual heads" in both
+//           cases.
+// Service warps 16..19: lane 0 of warp 16+g issues the tensor-core work of warpgroup g; lane 16 of warp 19 is the TMA
+// producer.
 constexpr int kX4Consumers = 512;
-constexpr int kX4Threads = 640;   // warps 0-15 consumers | 16 producer | 17 MMA issuers (lanes 0-3) | 18, 19 idle
-// 640 threads -> 96 registers per thread from __launch_bounds__; the consumer path fits without spills, so no
-// setmaxnreg here (a CTA's register pool is what it was launched with: 640 x 96 leaves nothing to hand over).
+constexpr int kX4Threads = 640;
+// 640 threads -> 96 registers per thread from __launch_bounds__; the consumer path fits, so no setmaxnreg here (a
+// CTA's register pool is what it was launched with: 640 x 96 leaves nothing to hand over).
 
-template <typename T, bool STATS>
+template <int D>
+struct X4 {
+  using C = TC<D>;
+  static constexpr int HPT = 160 / D;  // heads per tile
+  static constexpr int PAR = 4 / HPT;  // tile-parity groups of warpgroups
+  static constexpr int NH = D / 40;    // O = P V halves (40 V columns each)
+  static constexpr int QW = D / 2;     // 32-bit words of one Q row-head
+  static constexpr int VH_BYTES = TC<40>::VT_HEAD_BYTES;  // V^T of one 40-column virtual head (10 chunks x 48 rows x 16 B)
+  static constexpr int VT_OFF = C::K_BYTES;
+  static constexpr int KV_FWD = ((C::K_BYTES + 4 * VH_BYTES + 1023) / 1024) * 1024;
+  static constexpr int FWD_SMEM = KV_FWD + C::FWD_STAGES * (C::QT_BYTES + C::WT_BYTES) + C::BAR_BYTES;
+  static constexpr int STATS_SMEM = C::K_BYTES_PAD + C::STATS_STAGES * C::QT_BYTES + C::BAR_BYTES;
+};
+
+// V (160 columns of the head group = n_vh virtual heads of 40) -> V^T canonical [key chunk][row d][8 keys], row 40 = ones
+template <typename T, int NTHR>
+__device__ __forceinline__ void stage_vt40(unsigned char* sVt, const XattnParams& p, const Item& it, int gw, int n_vh,
+                                           int ctid) {
+  constexpr int NPAIR = 21;  // 20 column pairs + the (ones, zero) pair
+  constexpr int MAXV = (4 * 10 * NPAIR + NTHR - 1) / NTHR;
+  const T* __restrict__ vg = reinterpret_cast<const T*>(p.v) + it.b * p.v_sb + it.hg * gw;
+  const int vss = static_cast<int>(p.v_ss);
+  const int n_v = n_vh * 10 * NPAIR;
+  const uint32_t one = std::is_same<T, __half>::value ? 0x3C00u : 0x3F80u;
+  uint32_t ve[MAXV][8];
+  int vsoff[MAXV];
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    const int e = min(ctid + u * NTHR, n_v - 1);
+    const int hk = e / NPAIR, dp = e - hk * NPAIR;
+    const int vh = hk / 10, kc = hk - vh * 10;
+    vsoff[u] = vh * TC<40>::VT_HEAD_BYTES + kc * TC<40>::VT_CH_BYTES + dp * 32;
+    const int col = vh * 40 + min(dp, 19) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = kc * 8 + j;
+      const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(vg + (min(key, p.S - 1) * vss + col)));
+      ve[u][j] = key >= p.S ? 0u : (dp == 20 ? one : x);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    if (ctid + u * NTHR < n_v) {
+      uint4 lo, hi;
+      lo.x = __byte_perm(ve[u][0], ve[u][1], 0x5410); hi.x = __byte_perm(ve[u][0], ve[u][1], 0x7632);
+      lo.y = __byte_perm(ve[u][2], ve[u][3], 0x5410); hi.y = __byte_perm(ve[u][2], ve[u][3], 0x7632);
+      lo.z = __byte_perm(ve[u][4], ve[u][5], 0x5410); hi.z = __byte_perm(ve[u][4], ve[u][5], 0x7632);
+      lo.w = __byte_perm(ve[u][6], ve[u][7], 0x5410); hi.w = __byte_perm(ve[u][6], ve[u][7], 0x7632);
+      *reinterpret_cast<uint4*>(sVt + vsoff[u]) = lo;
+      *reinterpret_cast<uint4*>(sVt + vsoff[u] + 16) = hi;
+    }
+  }
+  fence_proxy_async();
+}
+
+template <typename T, int D, bool STATS>
 __global__ void __launch_bounds__(kX4Threads, 1)
 xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_o) {
-  constexpr int D = 40;
   using C = TC<D>;
+  using X = X4<D>;
+  constexpr int HPT = X::HPT, PAR = X::PAR, NH = X::NH;
   constexpr int NST = STATS ? C::STATS_STAGES : C::FWD_STAGES;
   constexpr int STAGE_BYTES = STATS ? C::QT_BYTES : (C::QT_BYTES + C::WT_BYTES);
-  constexpr int KV_BYTES = STATS ? C::K_BYTES_PAD : (C::K_BYTES + C::VT_BYTES);
+  constexpr int KV_BYTES = STATS ? C::K_BYTES_PAD : X::KV_FWD;
   constexpr int S_COL = 0, O_COL = 80, WG_COLS = 128;  // P aliases S, the Q operand aliases O
+  constexpr int STAGE_CONSUMERS = HPT * 128;           // threads that hand a ring stage back
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TRACE_DECL_X4
@@ -835,7 +898,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   if constexpr (STATS) pdl_launch_dependents();  // let pass 2 start its prologue on SMs as they free up
   {  // first thing: start pulling this CTA's first K / V head group into L2
     const int begin0 = static_cast<int>(p.total * blockIdx.x / gridDim.x);
-    if (tid < kX4Consumers && begin0 < p.total) prefetch_kv<T, 40, STATS, kX4Consumers>(p, decode<40>(begin0, p), tid);
+    if (tid < kX4Consumers && begin0 < p.total) prefetch_kv<T, D, STATS, kX4Consumers>(p, decode<D>(begin0, p), tid);
   }
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sStage = s0 + KV_BYTES;
@@ -849,7 +912,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_odone + 8 * s, kX4Consumers);
+      mbar_init(b_odone + 8 * s, STAGE_CONSUMERS);
     }
     for (int g = 0; g < 4; ++g) {
       mbar_init(b_qrdy + 8 * g, 128);
@@ -876,8 +939,6 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   const int n_items = static_cast<int>(p.total * (blockIdx.x + 1) / gridDim.x) - begin;
 
   if (warp >= 16) {
-    // Service warps 16..19: lane 0 of warp 16+g issues the tensor-core work of warpgroup g; lane 16 of warp 19 is
-    // the TMA producer.  (Two lanes of one warp in different loops simply interleave.)
     const int wsvc = __shfl_sync(0xffffffffu, warp, 0) - 16;  // warp-uniform
     if (wsvc == 3 && lane == 16) {
       // ============================== producer: TMA loads and stores ===============================
@@ -924,17 +985,18 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
       }
     } else if (lane == 0) {
       // ============================== MMA issuer of warpgroup g ====================================
-      const int g = wsvc;
+      const int g = wsvc, h = g % HPT, par = g / HPT;
       constexpr uint32_t idesc_qk = idesc_f16<T>(80);
-      constexpr uint32_t idesc_pv = idesc_f16<T>(C::N_PV);  // A (= P) and B (= V^T) share the input dtype
+      constexpr uint32_t idesc_pv = idesc_f16<T>(48);
       const uint32_t tw = tmem_base + g * WG_COLS;
-      const uint64_t kdesc = smem_desc(s0 + g * C::K_HEAD_BYTES, C::K_CH_BYTES, 128);
-      const uint64_t vdesc = smem_desc(s0 + C::K_BYTES + g * C::VT_HEAD_BYTES, C::VT_CH_BYTES, 128);
-      uint32_t n = 0;
+      const uint64_t kdesc = smem_desc(s0 + h * C::K_HEAD_BYTES, C::K_CH_BYTES, 128);
+      uint32_t nq = 0, np = 0;
       for (int i = 0; i < n_items; ++i) {
+        if (PAR > 1 && (i % PAR) != par) continue;
         const Item it = decode<D>(begin + i, p);
-        if (g >= it.nheads) continue;
-        mbar_wait_relaxed(b_qrdy + 8 * g, n & 1);
+        if (h >= it.nheads) continue;
+        mbar_wait_relaxed(b_qrdy + 8 * g, nq & 1);
+        ++nq;
         TRACE(21);
         tc_fence_after();
 #pragma unroll
@@ -943,22 +1005,26 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         tc_commit(b_srdy + 8 * g);
         TRACE(22);
         if constexpr (!STATS) {
-          mbar_wait_relaxed(b_prdy + 8 * g, n & 1);
-          TRACE(24);
-          tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 5; ++kk)
-            umma_ts(tw + O_COL, tw + S_COL + kk * 8, vdesc + static_cast<uint64_t>((kk * 2 * C::VT_CH_BYTES) >> 4), idesc_pv, kk);
-          tc_commit(b_ordy + 8 * g);
-          TRACE(25);
+          for (int j = 0; j < NH; ++j) {  // O half j = P [V_half j | 1]
+            const uint64_t vdesc = smem_desc(s0 + X::VT_OFF + (h * NH + j) * X::VH_BYTES, TC<40>::VT_CH_BYTES, 128);
+            mbar_wait_relaxed(b_prdy + 8 * g, np & 1);
+            ++np;
+            TRACE(24);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk)
+              umma_ts(tw + O_COL, tw + S_COL + kk * 8, vdesc + static_cast<uint64_t>((kk * 2 * TC<40>::VT_CH_BYTES) >> 4), idesc_pv, kk);
+            tc_commit(b_ordy + 8 * g);
+            TRACE(25);
+          }
         }
-        ++n;
       }
     }
     __syncwarp();
   } else {
-    // ============================== consumers: warpgroup g = head g, one thread per query row ======
-    const int g = warp >> 2;
+    // ============================== consumers: one head per warpgroup, one thread per query row ====
+    const int g = warp >> 2, h = g % HPT, par = g / HPT;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t row_off = row * 64, row_sw = (row >> 1) & 3;
     auto chunk_off = [&](int cg) -> uint32_t {
@@ -969,42 +1035,47 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
     bool have_beta = STATS;
     const float scale_l2 = p.scale * kLog2eT;
     double dsum = 0.0, dsq = 0.0;
-    uint32_t n = 0;
-    const unsigned stagger_ns = p.stagger_ns;
+    uint32_t n_s = 0, n_o = 0;
     for (int r0 = 0; r0 < n_items;) {
       const Item it0 = decode<D>(begin + r0, p);
       const int r1 = min(n_items, r0 + p.n_sl - it0.tile);
       TRACE(3);
       asm volatile("bar.sync 1, 512;" ::: "memory");
-      stage_kv<T, D, STATS, kX4Consumers>(smem, p, it0, tid);
+      stage_kv<T, D, true, kX4Consumers>(smem, p, it0, tid);  // K of the head group
+      if constexpr (!STATS) stage_vt40<T, kX4Consumers>(smem + X::VT_OFF, p, it0, C::GW, it0.nheads * NH, tid);
       asm volatile("bar.sync 1, 512;" ::: "memory");
       TRACE(4);
       if (r1 < n_items) prefetch_kv<T, D, STATS, kX4Consumers>(p, decode<D>(begin + r1, p), tid);
-      const bool active = g < it0.nheads;
-      if (stagger_ns) __nanosleep(stagger_ns * (g >> 1));  // de-phase the warpgroup pairs {0,1} / {2,3} (experiment)
-      // Q row of head g of tile i -> TMEM (first 24 columns of the O region; columns 20..23 = zero K padding)
+      const bool active = h < it0.nheads;
+      const int first = r0 + ((par - (r0 % PAR)) + PAR) % PAR;  // first tile of this warpgroup's parity in the run
+      // Q row of head h of tile i -> TMEM (first D/2 (+4 zero) columns of the O region)
       auto stage_q = [&](int i) {
         const int s = i % NST;
         const unsigned char* qtile = smem + KV_BYTES + s * STAGE_BYTES;
         MBAR_WAIT(b_full + 8 * s, (i / NST) & 1, 6);
         TRACE(5);
-        uint32_t qw[24];
+        uint32_t qw[D == 40 ? 24 : 40];
 #pragma unroll
         for (int c = 0; c < C::DCH; ++c) {
-          const uint4 v = *reinterpret_cast<const uint4*>(qtile + chunk_off(g * C::DCH + c));
+          const uint4 v = *reinterpret_cast<const uint4*>(qtile + chunk_off(h * C::DCH + c));
           qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
         }
-        qw[20] = qw[21] = qw[22] = qw[23] = 0u;
-        tmem_st_x16(tw + O_COL, qw);
-        tmem_st_x8(tw + O_COL + 16, qw + 16);
+        if constexpr (D == 40) {
+          qw[20] = qw[21] = qw[22] = qw[23] = 0u;  // zero K padding of the odd half k-step
+          tmem_st_x16(tw + O_COL, qw);
+          tmem_st_x8(tw + O_COL + 16, qw + 16);
+        } else {
+          tmem_st_x32(tw + O_COL, qw);
+          tmem_st_x8(tw + O_COL + 32, qw + 32);
+        }
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(b_qrdy + 8 * g);
         TRACE(6);
         if constexpr (STATS) mbar_arrive(b_odone + 8 * s);  // pass 1 only reads Q
       };
-      if (!active) {  // no head for this warpgroup in these tiles: just hand them back
-        for (int i = r0; i < r1; ++i) {
+      if (!active) {  // no head for this warpgroup in these tiles: just hand its tiles back
+        for (int i = first; i < r1; i += PAR) {
           MBAR_WAIT(b_full + 8 * (i % NST), (i / NST) & 1, 6);
           if constexpr (!STATS) fence_proxy_async();
           mbar_arrive(b_odone + 8 * (i % NST));
@@ -1012,15 +1083,17 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         r0 = r1;
         continue;
       }
-      stage_q(r0);
-      for (int i = r0; i < r1; ++i) {
+      if (first < r1) stage_q(first);
+      for (int i = first; i < r1; i += PAR) {
         const int s = i % NST;
         const int l0 = (it0.tile + (i - r0)) * C::ROWS;
         const int rows = min(C::ROWS, p.L - l0);
         unsigned char* qtile = smem + KV_BYTES + s * STAGE_BYTES;
+        const bool has_next = i + PAR < r1;
         // ---- S row
         TRACE(10);
-        MBAR_WAIT(b_srdy + 8 * g, n & 1, 8);
+        MBAR_WAIT(b_srdy + 8 * g, n_s & 1, 8);
+        ++n_s;
         TRACE(11);
         tc_fence_after();
         float sc[80];
@@ -1029,9 +1102,9 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         tc_wait_ld();
         TRACE(12);
         if constexpr (STATS) {
-          if (i + 1 < r1) {  // S is in registers: the next tile's Q K^T may run under this tile's accumulation
+          if (has_next) {  // S is in registers: the next tile's Q K^T may run under this tile's accumulation
             tc_fence_before();
-            stage_q(i + 1);
+            stage_q(i + PAR);
           }
           float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -1091,33 +1164,40 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
           tc_fence_before();
           mbar_arrive(b_prdy + 8 * g);
           TRACE(16);
-          // ---- O row
-          MBAR_WAIT(b_ordy + 8 * g, n & 1, 5);
-          TRACE(17);
-          tc_fence_after();
-          float o[48];
-          tmem_ld_x32(tw + O_COL, reinterpret_cast<uint32_t*>(o));
-          tmem_ld_x16(tw + O_COL + 32, reinterpret_cast<uint32_t*>(o) + 32);
-          tc_wait_ld();
-          if (i + 1 < r1) {  // the O columns are free again: next tile's Q -> TMEM now, its Q K^T runs under the O store
-            tc_fence_before();
-            stage_q(i + 1);
-          }
-          const float inv = 1.f / o[D];
+          // ---- O row, one 40-column half at a time
+          float inv = 0.f;
 #pragma unroll
-          for (int c = 0; c < C::DCH; ++c) {
-            uint4 v;
-            v.x = Mma<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
-            v.y = Mma<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
-            v.z = Mma<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
-            v.w = Mma<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
-            *reinterpret_cast<uint4*>(qtile + chunk_off(g * C::DCH + c)) = v;
+          for (int j = 0; j < NH; ++j) {
+            MBAR_WAIT(b_ordy + 8 * g, n_o & 1, 5);
+            ++n_o;
+            TRACE(17);
+            tc_fence_after();
+            float o[48];
+            tmem_ld_x32(tw + O_COL, reinterpret_cast<uint32_t*>(o));
+            tmem_ld_x16(tw + O_COL + 32, reinterpret_cast<uint32_t*>(o) + 32);
+            tc_wait_ld();
+            if (j == 0) inv = 1.f / o[40];  // the ones column: softmax row sum of the rounded P
+            tc_fence_before();
+            if (j + 1 < NH) {
+              mbar_arrive(b_prdy + 8 * g);  // the O columns are free: the second V half may be multiplied
+            } else if (PAR == 1 && has_next) {
+              stage_q(i + PAR);  // ... or the next tile's Q goes to TMEM now; its Q K^T runs under the O store
+            }
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+              uint4 v;
+              v.x = Mma<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
+              v.y = Mma<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+              v.z = Mma<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+              v.w = Mma<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+              *reinterpret_cast<uint4*>(qtile + chunk_off(h * C::DCH + j * 5 + c)) = v;
+            }
           }
           TRACE(18);
           fence_proxy_async();
           mbar_arrive(b_odone + 8 * s);
+          if (PAR > 1 && has_next) stage_q(i + PAR);  // same ring stage: only after it has been handed back and refilled
         }
-        ++n;
       }
       r0 = r1;
     }
@@ -1261,29 +1341,29 @@ extern "C" int dsc_debug_trace(long long* out /*HOST 4*512*2*/, int* counts /*HO
 }
 #endif
 
-template <typename T, bool STATS>
+template <typename T, int D, bool STATS>
 static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
-  using C = TC<40>;
-  constexpr int smem = STATS ? C::STATS_SMEM : C::FWD_SMEM;
+  using C = TC<D>;
+  constexpr int smem = STATS ? X4<D>::STATS_SMEM : X4<D>::FWD_SMEM;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(xattn_tc5x4_kernel<T, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(xattn_tc5x4_kernel<T, D, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured_dev = dev;
   }
   CUtensorMap tm_q, tm_o;
-  if (!make_map(&tm_q, p.q, p.H * 40, p.L, p.B, p.q_sl, p.q_sb)) return cudaErrorInvalidValue;
+  if (!make_map(&tm_q, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb)) return cudaErrorInvalidValue;
   if (STATS) tm_o = tm_q;
-  else if (!make_map(&tm_o, p.out, p.H * 40, p.L, p.B, p.o_sl, p.o_sb)) return cudaErrorInvalidValue;
+  else if (!make_map(&tm_o, p.out, p.H * D, p.L, p.B, p.o_sl, p.o_sb)) return cudaErrorInvalidValue;
   p.n_hg = (p.H + C::G - 1) / C::G;
   p.n_sl = (p.L + C::ROWS - 1) / C::ROWS;
   p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
   if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
   const int sms = sm_count_cached();
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
-  { const char* e = getenv("DSC_X4_STAGGER_NS"); p.stagger_ns = e ? static_cast<unsigned>(atoi(e)) : 0u; }
+  p.stagger_ns = 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kX4Threads);
@@ -1295,13 +1375,13 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   const char* nopdl = getenv("DSC_NO_PDL");
   cfg.attrs = attr;
   cfg.numAttrs = (!STATS && !(nopdl && nopdl[0] == '1')) ? 1 : 0;  // pass 2 may overlap the tail of pass 1
-  return cudaLaunchKernelEx(&cfg, xattn_tc5x4_kernel<T, STATS>, p, tm_q, tm_o);
+  return cudaLaunchKernelEx(&cfg, xattn_tc5x4_kernel<T, D, STATS>, p, tm_q, tm_o);
 }
 
-// D = 40 has two tcgen05 variants: "x4" (4 consumer warpgroups, one head each; default) and "x2" (2 warpgroups,
-// software-pipelined heads).  DSC_TC5_VARIANT=x2 selects the latter for A/B runs.
+// Two tcgen05 variants: "x4" (4 consumer warpgroups, one head each; default) and "x2" (2 warpgroups, software-
+// pipelined heads).  DSC_TC5_VARIANT=x2 selects the latter for A/B runs.
 static bool use_x4(int D) {
-  if (D != 40) return false;
+  if (D != 40 && D != 80) return false;
   const char* e = getenv("DSC_TC5_VARIANT");
   return !(e && e[0] == 'x' && e[1] == '2');
 }
@@ -1309,14 +1389,20 @@ static bool use_x4(int D) {
 bool tc5_supports(int D) { return D == 40 || D == 80; }
 
 cudaError_t run_stats_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st) {
-  if (use_x4(D)) return dtype == DSC_DTYPE_F16 ? launch_tc5x4<__half, true>(p, st) : launch_tc5x4<__nv_bfloat16, true>(p, st);
+  if (use_x4(D)) {
+    if (dtype == DSC_DTYPE_F16) return D == 40 ? launch_tc5x4<__half, 40, true>(p, st) : launch_tc5x4<__half, 80, true>(p, st);
+    return D == 40 ? launch_tc5x4<__nv_bfloat16, 40, true>(p, st) : launch_tc5x4<__nv_bfloat16, 80, true>(p, st);
+  }
   if (dtype == DSC_DTYPE_F16)
     return D == 40 ? launch_tc5<__half, 40, true>(p, st) : launch_tc5<__half, 80, true>(p, st);
   return D == 40 ? launch_tc5<__nv_bfloat16, 40, true>(p, st) : launch_tc5<__nv_bfloat16, 80, true>(p, st);
 }
 
 cudaError_t run_forward_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st) {
-  if (use_x4(D)) return dtype == DSC_DTYPE_F16 ? launch_tc5x4<__half, false>(p, st) : launch_tc5x4<__nv_bfloat16, false>(p, st);
+  if (use_x4(D)) {
+    if (dtype == DSC_DTYPE_F16) return D == 40 ? launch_tc5x4<__half, 40, false>(p, st) : launch_tc5x4<__half, 80, false>(p, st);
+    return D == 40 ? launch_tc5x4<__nv_bfloat16, 40, false>(p, st) : launch_tc5x4<__nv_bfloat16, 80, false>(p, st);
+  }
   if (dtype == DSC_DTYPE_F16)
     return D == 40 ? launch_tc5<__half, 40, false>(p, st) : launch_tc5<__half, 80, false>(p, st);
   return D == 40 ? launch_tc5<__nv_bfloat16, 40, false>(p, st) : launch_tc5<__nv_bfloat16, 80, false>(p, st);
