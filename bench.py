@@ -147,6 +147,7 @@ def attention_roofline(device):
         v = torch.randn(B, S, H * D, device=device, dtype=torch.float16)
         W = torch.zeros(B, L, S, device=device)
         W[:, : L // 2, 1:3] = 0.5
+        W = att.padded_region_map(W)  # the device layout encode_region_map produces (rows 80 floats apart)
         out = torch.empty_like(q)
         vw = lambda t: t.view(B, -1, H, D).transpose(1, 2)
         qs, ks, vs, os_ = I4(*vw(q).stride()), I4(*vw(k).stride()), I4(*vw(v).stride()), I3(*out.stride())
@@ -156,7 +157,7 @@ def attention_roofline(device):
             check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), qs, ks, None, B, H, L, D, S, sc, 0, ws.data_ptr(), st))
 
         def k2():
-            check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, None, 7.0,
+            check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, W.stride(1), None, 7.0,
                                         ws.data_ptr(), out.data_ptr(), os_, B, H, L, D, S, sc, 0, st))
 
         def call():  # one attention call = pass 1 + pass 2 back to back (pass 2 is a programmatic dependent launch)

@@ -91,6 +91,31 @@ def read_stats(workspace: torch.Tensor) -> dict:
     return {"ticket": ticket, "n_partials": n_part, "std": std, "mean": mean, "sum": s, "sumsq": ss, "n": n}
 
 
+MAX_KEYS = 80  # DSC_MAX_KEYS
+
+
+def _region_layout_ok(W: torch.Tensor) -> bool:
+    """[B', L, S] fp32 with unit key stride, row pitch in [S, 80] and batch stride L * pitch (dense or padded)."""
+    Bw, L, S = W.shape
+    pitch = W.stride(1)
+    return (W.stride(2) == 1 and S <= pitch <= MAX_KEYS and (Bw == 1 or W.stride(0) == L * pitch)
+            and W.data_ptr() % 4 == 0)
+
+
+def padded_region_map(W: torch.Tensor) -> torch.Tensor:
+    """The same [B', L, S] values in the fast device layout: rows 80 floats apart (16-byte aligned rows that the
+    kernels fetch with TMA boxes and read as 128-bit words).  Returns a [B', L, S] VIEW of a zero-padded
+    [B', L, 80] buffer, so it still indexes, compares and prints like the reference's tensor."""
+    Bw, L, S = W.shape
+    if S > MAX_KEYS:
+        raise NotImplementedError(f"at most {MAX_KEYS} keys are supported, got {S}")
+    if W.stride(1) == MAX_KEYS and _region_layout_ok(W):
+        return W
+    buf = torch.zeros((Bw, L, MAX_KEYS), dtype=torch.float32, device=W.device)
+    buf[:, :, :S] = W
+    return buf[:, :, :S]
+
+
 def region_attention(
     query: torch.Tensor,  # [B, H, L, D]
     key: torch.Tensor,  # [B, H, S, D]
@@ -116,8 +141,8 @@ def region_attention(
         raise ValueError(f"region_state batch {W.shape[0]} does not divide B*H={B * H}")  # reference: shape error at :97
     if B % W.shape[0] != 0:
         raise NotImplementedError(f"region_state batch {W.shape[0]} must divide the attention batch {B}")
-    if W.dtype != torch.float32 or not W.is_contiguous() or W.device != q.device:
-        W = W.to(device=q.device, dtype=torch.float32).contiguous()
+    if W.dtype != torch.float32 or W.device != q.device or not _region_layout_ok(W):
+        W = padded_region_map(W.to(device=q.device, dtype=torch.float32))
     scale = 1.0 / math.sqrt(D) if scale is None else float(scale)
     ws = get_workspace(q.device) if workspace is None else workspace
     out = torch.empty((B, L, H * D), dtype=q.dtype, device=q.device)
@@ -141,6 +166,6 @@ def region_attention(
         check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), qs, ks, None, B, H, L, D, S, scale, dt,
                                   ws.data_ptr(), st))
         check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), W.shape[0],
-                                    sigma_ptr, sigma_host, ws.data_ptr(), out.data_ptr(), _I64x3(*out.stride()),
+                                    W.stride(1), sigma_ptr, sigma_host, ws.data_ptr(), out.data_ptr(), _I64x3(*out.stride()),
                                     B, H, L, D, S, scale, dt, st))
     return out.view(B, L, H, D).transpose(1, 2)

@@ -17,7 +17,7 @@ from typing import Callable, Optional
 import torch
 import torch.nn.functional as F
 
-from .attention import region_attention
+from .attention import padded_region_map, region_attention
 
 
 def _is_reference_weight_func(fn: Callable) -> bool:
@@ -56,7 +56,7 @@ class RegionAttnProcessor:
         if hit is not None and hit[0] is w:
             self._w_cache.move_to_end(key)
             return hit[1]
-        dev = w.to(device=device, dtype=torch.float32, non_blocking=False).contiguous()
+        dev = padded_region_map(w.to(device=device, dtype=torch.float32, non_blocking=False))
         self._w_cache[key] = (w, dev)  # keeps `w` alive, so data_ptr cannot be recycled under the key
         while len(self._w_cache) > self._max_cached_maps:
             self._w_cache.popitem(last=False)

@@ -12,7 +12,8 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
-LIB_PATH = PKG_DIR / "libdsc_b200.so"
+# DSC_LIB: alternative library file (debug builds such as -DDSC_TRACE kept next to the product build)
+LIB_PATH = Path(os.environ.get("DSC_LIB", str(PKG_DIR / "libdsc_b200.so")))
 SOURCES = ["xattn_kernels.cu", "xattn_tc5.cu", "region_kernels.cu", "sampler_kernels.cu", "dsc_capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

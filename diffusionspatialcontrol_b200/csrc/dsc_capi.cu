@@ -38,12 +38,15 @@ int sm_count_cached() {
 
 // Kernel family per call.  DSC_XATTN_IMPL=mma forces the legacy mma.sync kernels, =tc5 forces tcgen05/TMEM
 // wherever it is implemented (D = 40, 80); default "auto" = whichever measured faster on B200 for the head dim
-// (profiles/): tcgen05 at D = 40, mma.sync elsewhere.
-static bool use_tc5(int D) {
+// (profiles/): tcgen05 at D = 40 (both passes) and D = 80 (pass 2; its pass 1 is 2 us faster on mma.sync), mma.sync
+// elsewhere.  The two passes only share the std in the workspace, so the families mix freely.
+static bool use_tc5(int D, bool stats) {
   const char* e = getenv("DSC_XATTN_IMPL");
+  const char* es = getenv("DSC_XATTN_STATS_IMPL");  // pass 1 alone (A/B runs)
+  if (stats && es) e = es;
   if (e && strcmp(e, "mma") == 0) return false;
   if (e && strcmp(e, "tc5") == 0) return tc5_supports(D);
-  return D == 40;
+  return D == 40 || (D == 80 && !stats);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -119,13 +122,14 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
   p.scale = scale;
   p.ws = static_cast<Workspace*>(workspace);
   if (stats_grid(p.total) > kMaxPartials) return fail(DSC_ERR_UNSUPPORTED, "grid exceeds workspace partial slots");
-  cudaError_t e = use_tc5(D) ? run_stats_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
+  cudaError_t e = use_tc5(D, true) ? run_stats_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
                              : run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_stats");
 }
 
 int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],
-                      const int64_t v_str[4], const float* W, int Bw, const float* sigma_dev_or_null, float sigma_host,
+                      const int64_t v_str[4], const float* W, int Bw, int w_pitch, const float* sigma_dev_or_null,
+                      float sigma_host,
                       const void* workspace, void* out, const int64_t o_str[3], int B, int H, int L, int D, int S,
                       float scale, int dtype, void* stream) {
   int rc = check_dims(B, H, L, D, S, dtype);
@@ -139,6 +143,8 @@ int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t
   if (!aligned16(out) || o_str[2] != 1 || o_str[1] % 8 != 0 || o_str[0] % 8 != 0)
     return fail(DSC_ERR_LAYOUT, "out: need 16-byte base, unit inner stride, row/batch strides multiple of 8");
   if ((reinterpret_cast<uintptr_t>(W) & 3) != 0) return fail(DSC_ERR_LAYOUT, "W must be 4-byte aligned");
+  if (w_pitch < S || w_pitch > DSC_MAX_KEYS)
+    return fail(DSC_ERR_LAYOUT, "w_pitch=%d must be in [S=%d, %d]", w_pitch, S, DSC_MAX_KEYS);
   XattnParams p{};
   fill_partition(p, B, H, L, D, S);
   p.q = q;
@@ -147,6 +153,7 @@ int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t
   p.out = out;
   p.W = W;
   p.Bw = Bw;
+  p.w_pitch = w_pitch;
   p.sigma_dev = sigma_dev_or_null;
   p.sigma_host = sigma_host;
   p.scale = scale;
@@ -159,7 +166,7 @@ int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t
   p.o_sb = o_str[0];
   p.o_sl = o_str[1];
   p.ws = const_cast<Workspace*>(static_cast<const Workspace*>(workspace));
-  cudaError_t e = use_tc5(D) ? run_forward_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
+  cudaError_t e = use_tc5(D, false) ? run_forward_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
                              : run_forward(p, D, dtype, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_forward");
 }

@@ -31,7 +31,8 @@ struct XattnParams {
   int n_sl;         // 16-row slices per (batch, head-group)
   long long total;  // B * n_hg * n_sl
   Workspace* ws;
-  unsigned stagger_ns;  // experiment knob of the 4-warpgroup tcgen05 kernel (0 = off)
+  int w_pitch;          // floats between consecutive query rows of W (S <= w_pitch <= 80)
+  unsigned flags;       // 4-warpgroup tcgen05 kernel: launcher-set mode bits (see launch_tc5x4)
 };
 
 int sm_count_cached();

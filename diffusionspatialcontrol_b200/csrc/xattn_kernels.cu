@@ -372,7 +372,7 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
   for (long long idx = cta_begin; idx < cta_end;) {
     const Seg sg = seg_of<D>(idx, cta_end, p.n_sl, p.n_hg, p.H);
     const uint32_t row_bytes = sg.nheads * D * 2;
-    const float* Wb = p.W + static_cast<long long>(sg.b / w_rep) * p.L * p.S;
+    const float* Wb = p.W + static_cast<long long>(sg.b / w_rep) * p.L * p.w_pitch;
     __syncthreads();  // every warp is done with the previous K/V
     if (tid == 0) {
       mbar_arrive_expect_tx(kvbar, 2 * TL::KV_BYTES);  // two 80-row boxes; rows >= S arrive as zeros
@@ -384,8 +384,8 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
     auto issue = [&](long long sl_idx) {
       const int l0 = static_cast<int>(sl_idx % p.n_sl) * TL::ROWS;
       const int rows = min(TL::ROWS, p.L - l0);
-      const float* wsrc = Wb + static_cast<long long>(l0) * p.S;
-      const uint32_t wbytes = rows * p.S * 4;
+      const float* wsrc = Wb + static_cast<long long>(l0) * p.w_pitch;
+      const uint32_t wbytes = rows * p.w_pitch * 4;
       const bool w_bulk = ((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0;
       if (lane == 0) {
         mbar_arrive_expect_tx(qbar, TL::QS_BYTES + (w_bulk ? wbytes : 0));
@@ -395,7 +395,7 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
         if (lane == 16) bulk_g2s_hint(sW, wsrc, wbytes, qbar, pol_stream);
       } else {  // odd tail / unaligned W: plain loads (visible to this warp after the __syncwarp below)
         float* wdst = const_cast<float*>(wsm);
-        for (int i = lane; i < rows * p.S; i += 32) wdst[i] = __ldg(wsrc + i);
+        for (int i = lane; i < rows * p.w_pitch; i += 32) wdst[i] = __ldg(wsrc + i);
       }
       __syncwarp();
     };
@@ -427,7 +427,7 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
         for (int i = 0; i < 4; ++i) {
           const int col = 8 * j + 2 * t + (i & 1);
           const int row = g + 8 * (i >> 1);
-          bw[j][i] = (col < p.S) ? wsm[row * p.S + col] * beta_l2 : -INFINITY;
+          bw[j][i] = (col < p.S) ? wsm[row * p.w_pitch + col] * beta_l2 : -INFINITY;
         }
       }
 

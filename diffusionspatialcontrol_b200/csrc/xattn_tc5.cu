@@ -475,8 +475,8 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
           const float* wsrc = nullptr;
           uint32_t wbytes = 0;
           if constexpr (!STATS) {
-            wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.S;
-            wbytes = it.rows * p.S * 4;
+            wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.w_pitch;
+            wbytes = it.rows * p.w_pitch * 4;
             if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
           }
           mbar_arrive_expect_tx(b_full + 8 * s, tx);
@@ -638,7 +638,7 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
         r0 = r1;
         continue;
       }
-      const float* wbase = STATS ? nullptr : p.W + (static_cast<long long>(it0.b / (p.B / p.Bw)) * p.L) * p.S;
+      const float* wbase = STATS ? nullptr : p.W + (static_cast<long long>(it0.b / (p.B / p.Bw)) * p.L) * p.w_pitch;
       MBAR_WAIT(b_full + 8 * (r0 % NST), (r0 / NST) & 1, 7);
       TRACE(5);
       stage_q(r0, g);
@@ -700,10 +700,10 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
               have_beta = true;
             }
             if (hi == 0) {  // beta*W row (log2 domain), shared by this row's heads; keys >= S get -inf
-              const float* wsrc = wbase + static_cast<long long>(l0) * p.S;
-              const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.S * 4)) & 15) == 0;
+              const float* wsrc = wbase + static_cast<long long>(l0) * p.w_pitch;
+              const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.w_pitch * 4)) & 15) == 0;
               if (bulk) {  // all loads first (independent, conflict-free: row pitch = S words), then the scaling
-                const float* wt = reinterpret_cast<const float*>(smem + KV_BYTES + (i % NST) * STAGE_BYTES + C::QT_BYTES) + row * p.S;
+                const float* wt = reinterpret_cast<const float*>(smem + KV_BYTES + (i % NST) * STAGE_BYTES + C::QT_BYTES) + row * p.w_pitch;
                 if (p.S == 77) {
 #pragma unroll
                   for (int j = 0; j < 77; ++j) bw[j] = wt[j];
@@ -713,7 +713,7 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
                   for (int j = 0; j < 80; ++j) bw[j] = (j < p.S) ? wt[j] : -INFINITY;
                 }
               } else {
-                const float* wr = wsrc + static_cast<long long>(row < rows ? row : 0) * p.S;
+                const float* wr = wsrc + static_cast<long long>(row < rows ? row : 0) * p.w_pitch;
 #pragma unroll
                 for (int j = 0; j < 80; ++j) bw[j] = (j < p.S) ? __ldg(wr + j) : -INFINITY;
               }
@@ -834,7 +834,13 @@ struct X4 {
   static constexpr int VH_BYTES = TC<40>::VT_HEAD_BYTES;  // V^T of one 40-column virtual head (10 chunks x 48 rows x 16 B)
   static constexpr int VT_OFF = C::K_BYTES;
   static constexpr int KV_FWD = ((C::K_BYTES + 4 * VH_BYTES + 1023) / 1024) * 1024;
-  static constexpr int FWD_SMEM = KV_FWD + C::FWD_STAGES * (C::QT_BYTES + C::WT_BYTES) + C::BAR_BYTES;
+  // W tile: 128 rows at a pitch of 84 floats (336 B = 21 x 16 B, 21 odd: a quarter-warp's 128-bit reads of 8
+  // consecutive rows hit 8 distinct bank groups); the tensor-map box is 84 wide over rows of 80 floats, the 4
+  // out-of-range columns arrive as zeros.  Dense (unpadded) W tiles are bulk-copied at their own pitch <= 80.
+  static constexpr int W_SMEM_PITCH = 84;
+  static constexpr int WT_BYTES = C::ROWS * W_SMEM_PITCH * 4;
+  static_assert(WT_BYTES % 1024 == 0, "stage alignment");
+  static constexpr int FWD_SMEM = KV_FWD + C::FWD_STAGES * (C::QT_BYTES + WT_BYTES) + C::BAR_BYTES;
   static constexpr int STATS_SMEM = C::K_BYTES_PAD + C::STATS_STAGES * C::QT_BYTES + C::BAR_BYTES;
 };
 
@@ -881,18 +887,22 @@ __device__ __forceinline__ void stage_vt40(unsigned char* sVt, const XattnParams
 
 template <typename T, int D, bool STATS>
 __global__ void __launch_bounds__(kX4Threads, 1)
-xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_o) {
+xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_o,
+                   const __grid_constant__ CUtensorMap tm_w) {
   using C = TC<D>;
   using X = X4<D>;
   constexpr int HPT = X::HPT, PAR = X::PAR, NH = X::NH;
   constexpr int NST = STATS ? C::STATS_STAGES : C::FWD_STAGES;
-  constexpr int STAGE_BYTES = STATS ? C::QT_BYTES : (C::QT_BYTES + C::WT_BYTES);
+  constexpr int STAGE_BYTES = STATS ? C::QT_BYTES : (C::QT_BYTES + X::WT_BYTES);
   constexpr int KV_BYTES = STATS ? C::K_BYTES_PAD : X::KV_FWD;
   constexpr int S_COL = 0, O_COL = 80, WG_COLS = 128;  // P aliases S, the Q operand aliases O
   constexpr int STAGE_CONSUMERS = HPT * 128;           // threads that hand a ring stage back
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TRACE_DECL_X4
+  const bool warp_arrive = (p.flags & 1u) != 0, issuer_spin = (p.flags & 2u) != 0;
+  // padded W (rows 80 floats apart, 16-byte aligned, 77 keys): TMA box per tile, 128-bit reads, packed fp32 math
+  const bool w_fast = !STATS && (p.flags & 4u) != 0;
   TRACE(1);
   CTA_TIME(0);
   if constexpr (STATS) pdl_launch_dependents();  // let pass 2 start its prologue on SMs as they free up
@@ -912,12 +922,12 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_odone + 8 * s, STAGE_CONSUMERS);
+      mbar_init(b_odone + 8 * s, warp_arrive ? STAGE_CONSUMERS / 32 : STAGE_CONSUMERS);
     }
     for (int g = 0; g < 4; ++g) {
-      mbar_init(b_qrdy + 8 * g, 128);
+      mbar_init(b_qrdy + 8 * g, warp_arrive ? 4 : 128);
       mbar_init(b_srdy + 8 * g, 1);
-      mbar_init(b_prdy + 8 * g, 128);
+      mbar_init(b_prdy + 8 * g, warp_arrive ? 4 : 128);
       mbar_init(b_ordy + 8 * g, 1);
     }
     fence_mbar_init();
@@ -968,15 +978,22 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         const float* wsrc = nullptr;
         uint32_t wbytes = 0;
         if constexpr (!STATS) {
-          wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.S;
-          wbytes = it.rows * p.S * 4;
-          if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
+          if (w_fast) {
+            tx += X::WT_BYTES;  // the whole box is counted, zero-filled parts included
+          } else {
+            wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.w_pitch;
+            wbytes = it.rows * p.w_pitch * 4;
+            if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
+          }
         }
         mbar_arrive_expect_tx(b_full + 8 * s, tx);
 #pragma unroll
         for (int j = 0; j < C::NBOX; ++j)
           tma_load_3d(sQ + j * C::BOX_BYTES, &tm_q, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, b_full + 8 * s, pol);
-        if (wbytes != 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
+        if constexpr (!STATS) {
+          if (w_fast) tma_load_3d(sQ + C::QT_BYTES, &tm_w, 0, it.l0, it.b / (p.B / p.Bw), b_full + 8 * s, pol);
+          else if (wbytes != 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
+        }
         TRACE(40);
       }
       for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) {
@@ -995,7 +1012,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         if (PAR > 1 && (i % PAR) != par) continue;
         const Item it = decode<D>(begin + i, p);
         if (h >= it.nheads) continue;
-        mbar_wait_relaxed(b_qrdy + 8 * g, nq & 1);
+        if (issuer_spin) mbar_wait(b_qrdy + 8 * g, nq & 1); else mbar_wait_relaxed(b_qrdy + 8 * g, nq & 1);
         ++nq;
         TRACE(21);
         tc_fence_after();
@@ -1008,7 +1025,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
 #pragma unroll
           for (int j = 0; j < NH; ++j) {  // O half j = P [V_half j | 1]
             const uint64_t vdesc = smem_desc(s0 + X::VT_OFF + (h * NH + j) * X::VH_BYTES, TC<40>::VT_CH_BYTES, 128);
-            mbar_wait_relaxed(b_prdy + 8 * g, np & 1);
+            if (issuer_spin) mbar_wait(b_prdy + 8 * g, np & 1); else mbar_wait_relaxed(b_prdy + 8 * g, np & 1);
             ++np;
             TRACE(24);
             tc_fence_after();
@@ -1026,6 +1043,14 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
     // ============================== consumers: one head per warpgroup, one thread per query row ====
     const int g = warp >> 2, h = g % HPT, par = g / HPT;
     const int row = (warp & 3) * 32 + lane;
+    auto arrive = [&](uint32_t bar) {  // whole (converged) warp
+      if (warp_arrive) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
+      } else {
+        mbar_arrive(bar);
+      }
+    };
     const uint32_t row_off = row * 64, row_sw = (row >> 1) & 3;
     auto chunk_off = [&](int cg) -> uint32_t {
       return (cg >> 2) * C::BOX_BYTES + row_off + ((static_cast<uint32_t>(cg & 3) ^ row_sw) << 4);
@@ -1070,15 +1095,15 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         }
         tc_wait_st();
         tc_fence_before();
-        mbar_arrive(b_qrdy + 8 * g);
+        arrive(b_qrdy + 8 * g);
         TRACE(6);
-        if constexpr (STATS) mbar_arrive(b_odone + 8 * s);  // pass 1 only reads Q
+        if constexpr (STATS) arrive(b_odone + 8 * s);  // pass 1 only reads Q
       };
       if (!active) {  // no head for this warpgroup in these tiles: just hand its tiles back
         for (int i = first; i < r1; i += PAR) {
           MBAR_WAIT(b_full + 8 * (i % NST), (i / NST) & 1, 6);
           if constexpr (!STATS) fence_proxy_async();
-          mbar_arrive(b_odone + 8 * (i % NST));
+          arrive(b_odone + 8 * (i % NST));
         }
         r0 = r1;
         continue;
@@ -1108,9 +1133,11 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
           }
           float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 80; ++j) {
-            fs[j & 3] += sc[j];
-            fq[j & 3] = fmaf(sc[j], sc[j], fq[j & 3]);
+          for (int j = 0; j < 80; j += 4) {  // element j -> accumulator j & 3, two fp32 lanes per instruction
+            fadd2(fs[0], fs[1], fs[0], fs[1], sc[j], sc[j + 1]);
+            fadd2(fs[2], fs[3], fs[2], fs[3], sc[j + 2], sc[j + 3]);
+            ffma2(fq[0], fq[1], sc[j], sc[j + 1], sc[j], sc[j + 1], fq[0], fq[1]);
+            ffma2(fq[2], fq[3], sc[j + 2], sc[j + 3], sc[j + 2], sc[j + 3], fq[2], fq[3]);
           }
           if (row < rows) {
             dsum += static_cast<double>((fs[0] + fs[1]) + (fs[2] + fs[3]));
@@ -1124,37 +1151,61 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
             have_beta = true;
           }
           // logits in the log2 domain: s*scale*log2e + beta*log2e*W, W streamed from the shared tile
-          const float* wsrc = p.W + ((static_cast<long long>(it0.b / (p.B / p.Bw)) * p.L + l0) * p.S);
-          const bool bulk = ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.S * 4)) & 15) == 0;
-          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          if (bulk) {
-            const float* wt = reinterpret_cast<const float*>(qtile + C::QT_BYTES) + row * p.S;
-            if (p.S == 77) {
+          uint32_t pw[40];
+          if (w_fast && beta_l2 > 1e-20f) {
+            // x = beta * y with y = s * (scale/beta) + W: the row max is taken on y, 2^(x - max) = 2^(beta*y - beta*ymax)
+            const float4* wt4 = reinterpret_cast<const float4*>(qtile + C::QT_BYTES + row * (X::W_SMEM_PITCH * 4));
+            const float cy = scale_l2 / beta_l2;
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-              for (int j = 0; j < 77; ++j) {
-                sc[j] = fmaf(sc[j], scale_l2, wt[j] * beta_l2);
-                mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
-              }
-              sc[77] = sc[78] = sc[79] = -INFINITY;
-            } else {
+            for (int j = 0; j < 20; ++j) {
+              const float4 w = wt4[j];
+              ffma2(sc[4 * j], sc[4 * j + 1], sc[4 * j], sc[4 * j + 1], cy, cy, w.x, w.y);
+              ffma2(sc[4 * j + 2], sc[4 * j + 3], sc[4 * j + 2], sc[4 * j + 3], cy, cy, w.z, w.w);
+            }
+            sc[77] = sc[78] = sc[79] = -INFINITY;  // pad keys
 #pragma unroll
-              for (int j = 0; j < 80; ++j) {
-                sc[j] = (j < p.S) ? fmaf(sc[j], scale_l2, wt[j] * beta_l2) : -INFINITY;
-                mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
-              }
+            for (int j = 0; j < 80; ++j) mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+            const float nb = -beta_l2 * fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+#pragma unroll
+            for (int j = 0; j < 40; ++j) {
+              float e0, e1;
+              ffma2(e0, e1, sc[2 * j], sc[2 * j + 1], beta_l2, beta_l2, nb, nb);
+              pw[j] = Mma<T>::pack(ex2_approx(e0), ex2_approx(e1));
             }
           } else {
-            const float* wr = wsrc + static_cast<long long>(row < rows ? row : 0) * p.S;
+            const float* wsrc = p.W + ((static_cast<long long>(it0.b / (p.B / p.Bw)) * p.L + l0) * p.w_pitch);
+            const bool bulk = w_fast || ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.w_pitch * 4)) & 15) == 0;
+            const int wp = w_fast ? X::W_SMEM_PITCH : p.w_pitch;
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (bulk) {
+              const float* wt = reinterpret_cast<const float*>(qtile + C::QT_BYTES) + row * wp;
+              if (p.S == 77) {
 #pragma unroll
-            for (int j = 0; j < 80; ++j) {
-              sc[j] = (j < p.S) ? fmaf(sc[j], scale_l2, __ldg(wr + j) * beta_l2) : -INFINITY;
-              mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+                for (int j = 0; j < 77; ++j) {
+                  sc[j] = fmaf(sc[j], scale_l2, wt[j] * beta_l2);
+                  mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+                }
+                sc[77] = sc[78] = sc[79] = -INFINITY;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 80; ++j) {
+                  sc[j] = (j < p.S) ? fmaf(sc[j], scale_l2, wt[j] * beta_l2) : -INFINITY;
+                  mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+                }
+              }
+            } else {
+              const float* wr = wsrc + static_cast<long long>(row < rows ? row : 0) * p.w_pitch;
+#pragma unroll
+              for (int j = 0; j < 80; ++j) {
+                sc[j] = (j < p.S) ? fmaf(sc[j], scale_l2, __ldg(wr + j) * beta_l2) : -INFINITY;
+                mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+              }
             }
-          }
-          const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-          uint32_t pw[40];
+            const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
 #pragma unroll
-          for (int j = 0; j < 40; ++j) pw[j] = Mma<T>::pack(ex2_approx(sc[2 * j] - m), ex2_approx(sc[2 * j + 1] - m));
+            for (int j = 0; j < 40; ++j) pw[j] = Mma<T>::pack(ex2_approx(sc[2 * j] - m), ex2_approx(sc[2 * j + 1] - m));
+          }
           // (ex2.approx.f16x2 was tried to halve the MUFU work: on sm_100a it lowers to two MUFU.EX2.F16 plus
           //  repacking, i.e. more issue slots for the same MUFU count -- measured slower)
           TRACE(14);
@@ -1162,7 +1213,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
           tmem_st_x8(tw + S_COL + 32, pw + 32);
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(b_prdy + 8 * g);
+          arrive(b_prdy + 8 * g);
           TRACE(16);
           // ---- O row, one 40-column half at a time
           float inv = 0.f;
@@ -1179,23 +1230,28 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
             if (j == 0) inv = 1.f / o[40];  // the ones column: softmax row sum of the rounded P
             tc_fence_before();
             if (j + 1 < NH) {
-              mbar_arrive(b_prdy + 8 * g);  // the O columns are free: the second V half may be multiplied
+              arrive(b_prdy + 8 * g);  // the O columns are free: the second V half may be multiplied
             } else if (PAR == 1 && has_next) {
               stage_q(i + PAR);  // ... or the next tile's Q goes to TMEM now; its Q K^T runs under the O store
             }
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
               uint4 v;
-              v.x = Mma<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
-              v.y = Mma<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
-              v.z = Mma<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
-              v.w = Mma<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+              float* oc = o + 8 * c;
+              fmul2(oc[0], oc[1], oc[0], oc[1], inv, inv);
+              fmul2(oc[2], oc[3], oc[2], oc[3], inv, inv);
+              fmul2(oc[4], oc[5], oc[4], oc[5], inv, inv);
+              fmul2(oc[6], oc[7], oc[6], oc[7], inv, inv);
+              v.x = Mma<T>::pack(oc[0], oc[1]);
+              v.y = Mma<T>::pack(oc[2], oc[3]);
+              v.z = Mma<T>::pack(oc[4], oc[5]);
+              v.w = Mma<T>::pack(oc[6], oc[7]);
               *reinterpret_cast<uint4*>(qtile + chunk_off(h * C::DCH + j * 5 + c)) = v;
             }
           }
           TRACE(18);
           fence_proxy_async();
-          mbar_arrive(b_odone + 8 * s);
+          arrive(b_odone + 8 * s);
           if (PAR > 1 && has_next) stage_q(i + PAR);  // same ring stage: only after it has been handed back and refilled
         }
       }
@@ -1271,6 +1327,19 @@ static bool make_map(CUtensorMap* m, const void* base, int cols, int L, int B, l
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// padded region-weight map fp32 [Bw, L, 80] -> boxes of 84 columns (4 out of range: zero-filled) x 128 rows
+static bool make_map_w(CUtensorMap* m, const float* base, int L, int Bw) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {DSC_MAX_KEYS, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(Bw)};
+  cuuint64_t gstr[2] = {DSC_MAX_KEYS * 4ull, static_cast<cuuint64_t>(L) * DSC_MAX_KEYS * 4ull};
+  cuuint32_t box[3] = {84, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -1363,7 +1432,15 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
   const int sms = sm_count_cached();
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
-  p.stagger_ns = 0;
+  // experiment knobs (A/B runs): bit 0 one mbarrier arrival per warp, bit 1 MMA issuers spin instead of
+  // nanosleep-polling, bit 3 do not use the padded-W fast path
+  static const unsigned env_flags = [] { const char* e = getenv("DSC_TC5_FLAGS"); return e ? static_cast<unsigned>(atoi(e)) : 0u; }();
+  p.flags = env_flags & 3u;
+  CUtensorMap tm_w = tm_q;
+  if (!STATS && !(env_flags & 8u) && p.w_pitch == DSC_MAX_KEYS && p.S == 77 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0) {
+    if (!make_map_w(&tm_w, p.W, p.L, p.Bw)) return cudaErrorInvalidValue;
+    p.flags |= 4u;  // W tiles arrive as TMA boxes at a pitch of 84 floats
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kX4Threads);
@@ -1375,7 +1452,7 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   const char* nopdl = getenv("DSC_NO_PDL");
   cfg.attrs = attr;
   cfg.numAttrs = (!STATS && !(nopdl && nopdl[0] == '1')) ? 1 : 0;  // pass 2 may overlap the tail of pass 1
-  return cudaLaunchKernelEx(&cfg, xattn_tc5x4_kernel<T, D, STATS>, p, tm_q, tm_o);
+  return cudaLaunchKernelEx(&cfg, xattn_tc5x4_kernel<T, D, STATS>, p, tm_q, tm_o, tm_w);
 }
 
 // Two tcgen05 variants: "x4" (4 consumer warpgroups, one head each; default) and "x2" (2 warpgroups, software-

@@ -182,4 +182,7 @@ def encode_region_map(pipe, state, width, height, num_images_per_prompt, text_id
     for d in lst_prompt_map:
         for key, tensor in d.items():
             region_state_sp[key] = torch.cat((region_state_sp[key], tensor)) if key in region_state_sp else tensor
-    return {key: tensor.repeat(num_images_per_prompt, 1, 1) for key, tensor in region_state_sp.items()}
+    # same values and shape as the reference's dict; rows are laid out 80 floats apart (the kernels' fast W layout)
+    from .attention import padded_region_map
+
+    return {key: padded_region_map(tensor.repeat(num_images_per_prompt, 1, 1)) for key, tensor in region_state_sp.items()}

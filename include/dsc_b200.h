@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSC_VERSION 100 /* major*10000 + minor*100 + patch */
+#define DSC_VERSION 101 /* major*10000 + minor*100 + patch */
 
 #define DSC_DTYPE_F16 0
 #define DSC_DTYPE_BF16 1
@@ -73,15 +73,19 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4] /*HOST*
 /* Pass 2.  out = softmax(scale * Q K^T + beta * W) V with beta = sigma * std, std read from
  * `workspace` (written by dsc_xattn_stats earlier on the same stream).
  *
- * W: fp32 [Bw, L, S] contiguous region-weight map; row b of the batch uses W[b / (B / Bw)]
- *    (the batch-major repeat_interleave of attention_modify.py:96-99); requires B % Bw == 0.
+ * W: fp32 [Bw, L, S] region-weight map whose query rows are w_pitch floats apart (S <= w_pitch <=
+ *    DSC_MAX_KEYS; w_pitch == S is the reference's dense tensor; batch stride = L * w_pitch); row b
+ *    of the batch uses W[b / (B / Bw)] (the batch-major repeat_interleave of
+ *    attention_modify.py:96-99); requires B % Bw == 0.  The padded form w_pitch == DSC_MAX_KEYS with
+ *    a 16-byte aligned base is the fast path (rows fetched by TMA boxes and read as 128-bit words);
+ *    the pad columns are never read as weights.
  * sigma: if sigma_dev_or_null != NULL it points to ONE fp32 on the device (no host sync),
  *    else sigma_host is used.
  * out: [B, L, H*D] addressed through o_str[3] (element strides of B, L, and 1 for the last dim).
  * v: [B,H,S,D] through v_str, same layout contract as k. */
 int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t q_str[4] /*HOST*/,
                       const int64_t k_str[4] /*HOST*/, const int64_t v_str[4] /*HOST*/, const float* W, int Bw,
-                      const float* sigma_dev_or_null, float sigma_host, const void* workspace, void* out,
+                      int w_pitch, const float* sigma_dev_or_null, float sigma_host, const void* workspace, void* out,
                       const int64_t o_str[3] /*HOST*/, int B, int H, int L, int D, int S, float scale, int dtype,
                       void* stream);
 

@@ -70,6 +70,8 @@ def bench_shape(B, H, L, D, S, dtype, flush, iters=30, ref=True):
     W = torch.zeros(B, L, S, device=dev)
     W[:, : L // 2, 1:3] = 0.5
     W[:, L // 3 :, 6] = 0.7
+    if os.environ.get("DSC_W_LAYOUT", "padded") == "padded":  # the layout encode_region_map / the processor cache produce
+        W = att.padded_region_map(W)
     view = lambda t: t.view(B, -1, H, D).transpose(1, 2)
     q4, k4, v4 = view(q), view(k), view(v)
     out = torch.empty(B, L, H * D, device=dev, dtype=dtype)
@@ -83,7 +85,7 @@ def bench_shape(B, H, L, D, S, dtype, flush, iters=30, ref=True):
         check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), qs, ks, None, B, H, L, D, S, scale, dt, ws.data_ptr(), st))
 
     def k2():
-        check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, None, 7.0,
+        check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, W.stride(1), None, 7.0,
                                     ws.data_ptr(), out.data_ptr(), os_, B, H, L, D, S, scale, dt, st))
 
     def both():
@@ -102,13 +104,13 @@ def bench_shape(B, H, L, D, S, dtype, flush, iters=30, ref=True):
     sets = []
     for i in range(nset):
         qi, ki, vi, oi = torch.randn_like(q), torch.randn_like(k), torch.randn_like(v), torch.empty_like(out)
-        Wi = W.clone()
+        Wi = att.padded_region_map(W.clone()) if W.stride(1) == 80 else W.clone()
         sets.append((qi, ki, vi, Wi, oi))
 
     def call_set(t):
         qi, ki, vi, Wi, oi = t
         check(lib.dsc_xattn_stats(qi.data_ptr(), ki.data_ptr(), qs, ks, None, B, H, L, D, S, scale, dt, ws.data_ptr(), st))
-        check(lib.dsc_xattn_forward(qi.data_ptr(), ki.data_ptr(), vi.data_ptr(), qs, ks, vs, Wi.data_ptr(), B, None, 7.0,
+        check(lib.dsc_xattn_forward(qi.data_ptr(), ki.data_ptr(), vi.data_ptr(), qs, ks, vs, Wi.data_ptr(), B, Wi.stride(1), None, 7.0,
                                     ws.data_ptr(), oi.data_ptr(), os_, B, H, L, D, S, scale, dt, st))
 
     for t in sets:
@@ -150,10 +152,13 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--batches", default="2,8,16,32")
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--shapes", default="", help="e.g. 4096x40,1024x80 (default: the four SD-1.5 shapes)")
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     shapes = [(4096, 40), (1024, 80), (256, 160), (64, 160)]
+    if a.shapes:
+        shapes = [tuple(int(x) for x in t.split("x")) for t in a.shapes.split(",")]
     batches = [16] if a.quick else [int(x) for x in a.batches.split(",")]
     with open(a.out, "w") as f:
         for dtype in ([torch.float16] if a.quick else [torch.float16, torch.bfloat16]):

@@ -41,6 +41,9 @@ if mode == "stats":
     print("ratio sumsq", st["sumsq"] / float((a * a).sum()), "ratio sum", st["sum"] / float(a.sum()))
 else:
     W = torch.zeros(B, L, S); W[:, : L // 2, 1:3] = 0.5; W[:, L // 3:, 6 % S] += 0.7; W = W.cuda()
+    if os.environ.get("DSC_W_LAYOUT", "padded") == "padded":
+        from diffusionspatialcontrol_b200.attention import padded_region_map
+        W = padded_region_map(W)
     out = dsc.region_attention(q4, k4, v4, W, 5.0)
     torch.cuda.synchronize()
     ref = oa.region_attention(q4.float(), k4.float(), v4.float(), W.clone(), 5.0)

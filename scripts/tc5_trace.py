@@ -7,6 +7,9 @@ from diffusionspatialcontrol_b200 import _lib
 B, L, D = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]); H, S = 8, 77
 q = torch.randn(B, L, H * D, device="cuda", dtype=torch.float16); k = torch.randn(B, S, H * D, device="cuda", dtype=torch.float16); v = torch.randn_like(k)
 W = torch.zeros(B, L, S, device="cuda"); W[:, : L // 2, 1:3] = 0.5
+if os.environ.get("DSC_W_LAYOUT", "padded") == "padded":
+    from diffusionspatialcontrol_b200.attention import padded_region_map
+    W = padded_region_map(W)
 view = lambda t: t.view(B, -1, H, D).transpose(1, 2)
 raw = ctypes.CDLL(str(_lib.LIB_PATH))
 out = (ctypes.c_longlong * (4 * 512 * 2))(); cnt = (ctypes.c_int * 4)()

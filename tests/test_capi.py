@@ -31,7 +31,7 @@ def test_version_and_workspace_size():
     from diffusionspatialcontrol_b200 import _lib
     from diffusionspatialcontrol_b200.attention import workspace_bytes
 
-    assert _lib.lib.dsc_version() == 100
+    assert _lib.lib.dsc_version() == 101
     assert workspace_bytes(16, 8, 4096, 40, 77) >= 64 + 16 * 148
     n = ctypes.c_size_t(0)
     assert _lib.lib.dsc_xattn_workspace_bytes(0, 8, 64, 40, 77, ctypes.byref(n)) == _lib.ERR_INVALID_ARGUMENT
@@ -60,7 +60,7 @@ def test_argument_validation_returns_codes_not_crashes():
     assert lib.dsc_xattn_stats(None, fake, ok_q, ok_k, None, 2, 8, 4096, 40, 77, 0.1, 0, fake, None) == _lib.ERR_INVALID_ARGUMENT
     # forward: region-map batch must divide the attention batch (the reference raises on the shape mismatch)
     I3 = ctypes.c_int64 * 3
-    rc = lib.dsc_xattn_forward(fake, fake, fake, ok_q, ok_k, ok_k, fake, 3, None, 1.0, fake, fake, I3(4096 * 320, 320, 1),
+    rc = lib.dsc_xattn_forward(fake, fake, fake, ok_q, ok_k, ok_k, fake, 3, 77, None, 1.0, fake, fake, I3(4096 * 320, 320, 1),
                                2, 8, 4096, 40, 77, 0.1, 0, None)
     assert rc == _lib.ERR_SHAPE and b"Bw=3" in lib.dsc_last_error()
     # sampler step
