@@ -818,7 +818,13 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
 //           column) so that the O region stays 48 columns wide.  V^T is staged as 40-column "virtual heads" in both
 //           cases.
 // Service warps 16..19: lane 0 of warp 16+g issues the tensor-core work of warpgroup g; lane 16 of warp 19 is the TMA
-// producer.
+// producer (its first ring fill is issued before the CTA-wide start-up barrier).
+// (A fifth service warp does not fit: 21 warps x 96 registers cannot be launched -- registers are handed out per
+//  4-warp group -- and tensor-core issue from the consumer warps themselves measured 10 % slower: five tcgen05.mma
+//  plus the commit keep the issuing warp busy for 400-600 cycles per batch.)
+#ifndef DSC_POLY_PATTERN
+#define DSC_POLY_PATTERN 0x00  // bit i: key pairs with (pair & 7) == i take the polynomial 2^x below (0 = all on MUFU)
+#endif
 constexpr int kX4Consumers = 512;
 constexpr int kX4Threads = 640;
 // 640 threads -> 96 registers per thread from __launch_bounds__; the consumer path fits, so no setmaxnreg here (a
@@ -897,6 +903,9 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   constexpr int KV_BYTES = STATS ? C::K_BYTES_PAD : X::KV_FWD;
   constexpr int S_COL = 0, O_COL = 80, WG_COLS = 128;  // P aliases S, the Q operand aliases O
   constexpr int STAGE_CONSUMERS = HPT * 128;           // threads that hand a ring stage back
+  // pass 1, D = 40: the 48 columns behind S hold TWO Q-operand buffers (24 columns each), so the next tile's Q rows
+  // are in TMEM before this tile's S has been read and its Q K^T starts the moment the S columns are free
+  constexpr bool QDB = STATS && D == 40;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TRACE_DECL_X4
@@ -910,6 +919,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
     const int begin0 = static_cast<int>(p.total * blockIdx.x / gridDim.x);
     if (tid < kX4Consumers && begin0 < p.total) prefetch_kv<T, D, STATS, kX4Consumers>(p, decode<D>(begin0, p), tid);
   }
+  TRACE(50);
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sStage = s0 + KV_BYTES;
   const uint32_t bars = sStage + NST * STAGE_BYTES;
@@ -919,11 +929,47 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV_BYTES + NST * STAGE_BYTES + 240);
 
   for (int i = tid; i < KV_BYTES / 16; i += kX4Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) {
+  TRACE(51);
+  const int begin = static_cast<int>(p.total * blockIdx.x / gridDim.x);
+  const int n_items = static_cast<int>(p.total * (blockIdx.x + 1) / gridDim.x) - begin;
+  const uint64_t pol = STATS ? policy_evict_last() : policy_evict_first();
+  // producer: TMA loads of tile i (Q boxes + W tile) into ring stage i % NST
+  auto load_tile = [&](int i) {
+    const int s = i % NST;
+    const Item it = decode<D>(begin + i, p);
+    const uint32_t sQ = sStage + s * STAGE_BYTES;
+    uint32_t tx = C::QT_BYTES;
+    const float* wsrc = nullptr;
+    uint32_t wbytes = 0;
+    if constexpr (!STATS) {
+      if (w_fast) {
+        tx += X::WT_BYTES;  // the whole box is counted, zero-filled parts included
+      } else {
+        wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.w_pitch;
+        wbytes = it.rows * p.w_pitch * 4;
+        if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
+      }
+    }
+    mbar_arrive_expect_tx(b_full + 8 * s, tx);
+#pragma unroll
+    for (int j = 0; j < C::NBOX; ++j)
+      tma_load_3d(sQ + j * C::BOX_BYTES, &tm_q, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, b_full + 8 * s, pol);
+    if constexpr (!STATS) {
+      if (w_fast) tma_load_3d(sQ + C::QT_BYTES, &tm_w, 0, it.l0, it.b / (p.B / p.Bw), b_full + 8 * s, pol);
+      else if (wbytes != 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
+    }
+    TRACE(40);
+  };
+  constexpr int kProducerTid = 19 * 32 + 16;
+  if (tid == kProducerTid) {  // the producer owns the ring barriers and fills the ring right away
     for (int s = 0; s < NST; ++s) {
       mbar_init(b_full + 8 * s, 1);
       mbar_init(b_odone + 8 * s, warp_arrive ? STAGE_CONSUMERS / 32 : STAGE_CONSUMERS);
     }
+    fence_mbar_init();
+    for (int i = 0; i < min(NST, n_items); ++i) load_tile(i);
+  }
+  if (tid == 0) {
     for (int g = 0; g < 4; ++g) {
       mbar_init(b_qrdy + 8 * g, warp_arrive ? 4 : 128);
       mbar_init(b_srdy + 8 * g, 1);
@@ -938,6 +984,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  TRACE(52);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -945,14 +992,10 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   const uint32_t tmem_base = *tmem_ptr_smem;
   TRACE(2);
 
-  const int begin = static_cast<int>(p.total * blockIdx.x / gridDim.x);
-  const int n_items = static_cast<int>(p.total * (blockIdx.x + 1) / gridDim.x) - begin;
-
   if (warp >= 16) {
     const int wsvc = __shfl_sync(0xffffffffu, warp, 0) - 16;  // warp-uniform
-    if (wsvc == 3 && lane == 16) {
+    if (tid == kProducerTid) {
       // ============================== producer: TMA loads and stores ===============================
-      const uint64_t pol = STATS ? policy_evict_last() : policy_evict_first();
       auto store_tile = [&](int i) {
         if constexpr (!STATS) {
           const Item it = decode<D>(begin + i, p);
@@ -964,37 +1007,13 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
           bulk_wait_read0();
         }
       };
-      for (int i = 0; i < n_items; ++i) {
+      for (int i = NST; i < n_items; ++i) {
         const int s = i % NST;
-        if (i >= NST) {
-          mbar_wait_relaxed(b_odone + 8 * s, ((i / NST) - 1) & 1);
-          TRACE(41);
-          store_tile(i - NST);
-          TRACE(42);
-        }
-        const Item it = decode<D>(begin + i, p);
-        const uint32_t sQ = sStage + s * STAGE_BYTES;
-        uint32_t tx = C::QT_BYTES;
-        const float* wsrc = nullptr;
-        uint32_t wbytes = 0;
-        if constexpr (!STATS) {
-          if (w_fast) {
-            tx += X::WT_BYTES;  // the whole box is counted, zero-filled parts included
-          } else {
-            wsrc = p.W + (static_cast<long long>(it.b / (p.B / p.Bw)) * p.L + it.l0) * p.w_pitch;
-            wbytes = it.rows * p.w_pitch * 4;
-            if (((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0) tx += wbytes; else wbytes = 0;
-          }
-        }
-        mbar_arrive_expect_tx(b_full + 8 * s, tx);
-#pragma unroll
-        for (int j = 0; j < C::NBOX; ++j)
-          tma_load_3d(sQ + j * C::BOX_BYTES, &tm_q, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, b_full + 8 * s, pol);
-        if constexpr (!STATS) {
-          if (w_fast) tma_load_3d(sQ + C::QT_BYTES, &tm_w, 0, it.l0, it.b / (p.B / p.Bw), b_full + 8 * s, pol);
-          else if (wbytes != 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
-        }
-        TRACE(40);
+        mbar_wait_relaxed(b_odone + 8 * s, ((i / NST) - 1) & 1);
+        TRACE(41);
+        store_tile(i - NST);
+        TRACE(42);
+        load_tile(i);
       }
       for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) {
         mbar_wait_relaxed(b_odone + 8 * (i % NST), (i / NST) & 1);
@@ -1013,12 +1032,13 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         const Item it = decode<D>(begin + i, p);
         if (h >= it.nheads) continue;
         if (issuer_spin) mbar_wait(b_qrdy + 8 * g, nq & 1); else mbar_wait_relaxed(b_qrdy + 8 * g, nq & 1);
+        const uint32_t qa = tw + O_COL + (QDB ? (nq & 1) * 24 : 0);
         ++nq;
         TRACE(21);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < C::KSTEPS; ++ks)  // descriptor start address advances by 2 chunks per k-step
-          umma_ts(tw + S_COL, tw + O_COL + ks * 8, kdesc + static_cast<uint64_t>((ks * 2 * C::K_CH_BYTES) >> 4), idesc_qk, ks);
+          umma_ts(tw + S_COL, qa + ks * 8, kdesc + static_cast<uint64_t>((ks * 2 * C::K_CH_BYTES) >> 4), idesc_qk, ks);
         tc_commit(b_srdy + 8 * g);
         TRACE(22);
         if constexpr (!STATS) {
@@ -1060,7 +1080,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
     bool have_beta = STATS;
     const float scale_l2 = p.scale * kLog2eT;
     double dsum = 0.0, dsq = 0.0;
-    uint32_t n_s = 0, n_o = 0;
+    uint32_t n_s = 0, n_o = 0, n_q = 0;
     for (int r0 = 0; r0 < n_items;) {
       const Item it0 = decode<D>(begin + r0, p);
       const int r1 = min(n_items, r0 + p.n_sl - it0.tile);
@@ -1074,7 +1094,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
       const bool active = h < it0.nheads;
       const int first = r0 + ((par - (r0 % PAR)) + PAR) % PAR;  // first tile of this warpgroup's parity in the run
       // Q row of head h of tile i -> TMEM (first D/2 (+4 zero) columns of the O region)
-      auto stage_q = [&](int i) {
+      auto store_q = [&](int i) {  // smem -> registers -> tcgen05.st (not yet waited for)
         const int s = i % NST;
         const unsigned char* qtile = smem + KV_BYTES + s * STAGE_BYTES;
         MBAR_WAIT(b_full + 8 * s, (i / NST) & 1, 6);
@@ -1087,17 +1107,25 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         }
         if constexpr (D == 40) {
           qw[20] = qw[21] = qw[22] = qw[23] = 0u;  // zero K padding of the odd half k-step
-          tmem_st_x16(tw + O_COL, qw);
-          tmem_st_x8(tw + O_COL + 16, qw + 16);
+          const uint32_t qa = tw + O_COL + (QDB ? (n_q & 1) * 24 : 0);
+          tmem_st_x16(qa, qw);
+          tmem_st_x8(qa + 16, qw + 16);
         } else {
           tmem_st_x32(tw + O_COL, qw);
           tmem_st_x8(tw + O_COL + 32, qw + 32);
         }
+        ++n_q;
+      };
+      auto publish_q = [&](int i) {  // operand rows (and, before them, this thread's S reads) are complete
         tc_wait_st();
         tc_fence_before();
         arrive(b_qrdy + 8 * g);
         TRACE(6);
-        if constexpr (STATS) arrive(b_odone + 8 * s);  // pass 1 only reads Q
+        if constexpr (STATS) arrive(b_odone + 8 * (i % NST));  // pass 1 only reads Q
+      };
+      auto stage_q = [&](int i) {
+        store_q(i);
+        publish_q(i);
       };
       if (!active) {  // no head for this warpgroup in these tiles: just hand its tiles back
         for (int i = first; i < r1; i += PAR) {
@@ -1115,6 +1143,9 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         const int rows = min(C::ROWS, p.L - l0);
         unsigned char* qtile = smem + KV_BYTES + s * STAGE_BYTES;
         const bool has_next = i + PAR < r1;
+        if constexpr (QDB) {
+          if (has_next) store_q(i + PAR);  // into the other operand buffer, while this tile's Q K^T may still run
+        }
         // ---- S row
         TRACE(10);
         MBAR_WAIT(b_srdy + 8 * g, n_s & 1, 8);
@@ -1129,7 +1160,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         if constexpr (STATS) {
           if (has_next) {  // S is in registers: the next tile's Q K^T may run under this tile's accumulation
             tc_fence_before();
-            stage_q(i + PAR);
+            if constexpr (QDB) publish_q(i + PAR); else stage_q(i + PAR);
           }
           float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -1167,12 +1198,36 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
 #pragma unroll
             for (int j = 0; j < 80; ++j) mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
             const float nb = -beta_l2 * fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            // 2^e for 77 keys.  Optional (-DDSC_POLY_PATTERN=0x52 ...): the selected key pairs go through the FMA pipe
+            // instead of MUFU.EX2: e = j + f, j = round(e) taken from the mantissa of e + 1.5*2^23, 2^f on [-0.5, 0.5]
+            // as a cubic (max. relative error 7.5e-5), exponent added with an integer shift-add.  Measured on B200 at
+            // 2/8, 3/8, 4/8 of the pairs: no change of the kernel time (6/8: +2 us) -- the softmax phase is bound by
+            // issue slots and latency, not by the 4/clk MUFU -- so the default keeps every exp on MUFU.
 #pragma unroll
-            for (int j = 0; j < 40; ++j) {
+            for (int j = 0; j < 39; ++j) {
               float e0, e1;
               ffma2(e0, e1, sc[2 * j], sc[2 * j + 1], beta_l2, beta_l2, nb, nb);
-              pw[j] = Mma<T>::pack(ex2_approx(e0), ex2_approx(e1));
+              if (((DSC_POLY_PATTERN >> (j & 7)) & 1) && j < 38) {
+                constexpr float kMagic = 12582912.f;
+                e0 = fmaxf(e0, -126.f);
+                e1 = fmaxf(e1, -126.f);
+                float t0, t1, r0_, r1_, f0, f1, q0, q1;
+                fadd2(t0, t1, e0, e1, kMagic, kMagic);
+                fadd2(r0_, r1_, t0, t1, -kMagic, -kMagic);
+                ffma2(f0, f1, r0_, r1_, -1.f, -1.f, e0, e1);
+                ffma2(q0, q1, f0, f1, 0.0551716648f, 0.0551716648f, 0.2426111251f, 0.2426111251f);
+                ffma2(q0, q1, q0, q1, f0, f1, 0.6932609677f, 0.6932609677f);
+                ffma2(q0, q1, q0, q1, f0, f1, 0.9999280572f, 0.9999280572f);
+                q0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+                q1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+                pw[j] = Mma<T>::pack(q0, q1);
+              } else if (j < 38) {
+                pw[j] = Mma<T>::pack(ex2_approx(e0), ex2_approx(e1));
+              } else {
+                pw[j] = Mma<T>::pack(ex2_approx(e0), 0.f);  // key 77 is a pad key
+              }
             }
+            pw[39] = 0u;  // pad keys 78, 79
           } else {
             const float* wsrc = p.W + ((static_cast<long long>(it0.b / (p.B / p.Bw)) * p.L + l0) * p.w_pitch);
             const bool bulk = w_fast || ((reinterpret_cast<uintptr_t>(wsrc) | static_cast<uintptr_t>(rows * p.w_pitch * 4)) & 15) == 0;

@@ -22,9 +22,9 @@ for it in range(3):
         dsc.region_attention(view(q), view(k), view(v), W, 7.0)
     torch.cuda.synchronize()
     raw.dsc_debug_trace(out, cnt)   # also resets; stats+fwd traces are concatenated per call
-names = {31: "kv.enter", 32: "kv.loads_issued", 33: "kv.k_stored", 34: "kv.v_stored", 35: "kv.fenced", 1: "k.start", 2: "k.init_done", 3: "c.run_begin", 4: "c.kv_staged", 5: "c.first_tile_landed", 6: "c.first_q_staged", 7: "c.run_loop_done", 8: "c.run_drained", 9: "k.pre_final_sync", 30: "k.final_sync_done", 17: "c.o_ready", 18: "c.o_stored", 40: "p.loads_issued", 41: "p.stage_free", 42: "p.stored", 10: "c.pre_s_wait", 11: "c.s_ready", 12: "c.S_loaded", 13: "c.lookahead_done", 14: "c.softmax_done", 15: "c.o_drained", 16: "c.p_arrived",
+names = {50: "k.prefetch_issued", 51: "k.smem_zeroed", 52: "k.bars_tmem_ready", 31: "kv.enter", 32: "kv.loads_issued", 33: "kv.k_stored", 34: "kv.v_stored", 35: "kv.fenced", 1: "k.start", 2: "k.init_done", 3: "c.run_begin", 4: "c.kv_staged", 5: "c.first_tile_landed", 6: "c.first_q_staged", 7: "c.run_loop_done", 8: "c.run_drained", 9: "k.pre_final_sync", 30: "k.final_sync_done", 17: "c.o_ready", 18: "c.o_stored", 40: "p.loads_issued", 41: "p.stage_free", 42: "p.stored", 10: "c.pre_s_wait", 11: "c.s_ready", 12: "c.S_loaded", 13: "c.lookahead_done", 14: "c.softmax_done", 15: "c.o_drained", 16: "c.p_arrived",
          20: "m.pre_q_wait", 21: "m.q_ready", 22: "m.qk_issued", 23: "m.pre_p_wait", 24: "m.p_ready", 25: "m.pv_issued"}
-for wi, wn in enumerate(["consumer wg0 (warp0)", "consumer wg1 (warp4)", "mma wg0 (warp9)", "mma wg1 (warp10)"]):
+for wi, wn in enumerate(["consumer wg0 (warp0)", "consumer wg1 (warp4)", "x4: producer (warp16) / x2: mma wg0", "x4: consumer wg2 (warp8) / x2: mma wg1"]):
     n = cnt[wi]; ev = [(out[(wi * 512 + j) * 2], out[(wi * 512 + j) * 2 + 1]) for j in range(n)]
     print("==", wn, n, "events")
     if not ev: continue

@@ -73,8 +73,14 @@ def test_device_resident_maps_are_not_reuploaded():
     from diffusionspatialcontrol_b200 import RegionAttnProcessor
 
     proc = RegionAttnProcessor()
-    w = torch.zeros(2, 64, 77, device="cuda")
-    assert proc._device_map(w, w.device).data_ptr() == w.data_ptr()  # already fp32/contiguous/on device: no copy
+    from diffusionspatialcontrol_b200 import padded_region_map
+
+    w = padded_region_map(torch.zeros(2, 64, 77, device="cuda"))  # what encode_region_map returns
+    assert w.shape == (2, 64, 77) and w.stride() == (64 * 80, 80, 1)
+    assert proc._device_map(w, w.device).data_ptr() == w.data_ptr()  # device-resident fast layout: no copy
+    dense = torch.zeros(2, 64, 77, device="cuda")
+    d = proc._device_map(dense, dense.device)  # dense device tensor: re-laid out once, then cached
+    assert d.stride(1) == 80 and proc._device_map(dense, dense.device) is d
     cpu = torch.zeros(2, 64, 77)
     a = proc._device_map(cpu, w.device)
     assert proc._device_map(cpu, w.device) is a  # cached
