@@ -29,14 +29,15 @@ def workspace_bytes(B: int = 1, H: int = 1, L: int = 1, D: int = 40, S: int = 77
     return int(n.value)
 
 
-def get_workspace(device: torch.device) -> torch.Tensor:
+def get_workspace(device: torch.device, nbytes: int = 0) -> torch.Tensor:
     """One zero-initialised workspace per (device, stream); calls on a stream are serialised, so all
-    layers can share it.  Allocated through PyTorch's caching allocator (CUDA-graph friendly)."""
+    layers can share it.  Allocated through PyTorch's caching allocator (CUDA-graph friendly).  Long prompts
+    (more than 80 keys) need room for their per-chunk outputs: the buffer grows to the largest request."""
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream)
     ws = _WORKSPACES.get(key)
-    if ws is None:
-        ws = torch.zeros(workspace_bytes(), dtype=torch.uint8, device=device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(workspace_bytes(), nbytes), dtype=torch.uint8, device=device)
         _WORKSPACES[key] = ws
     return ws
 
@@ -91,27 +92,37 @@ def read_stats(workspace: torch.Tensor) -> dict:
     return {"ticket": ticket, "n_partials": n_part, "std": std, "mean": mean, "sum": s, "sumsq": ss, "n": n}
 
 
-MAX_KEYS = 80  # DSC_MAX_KEYS
+MAX_KEYS = 80  # DSC_MAX_KEYS: keys per kernel pass
+MAX_KEYS_TOTAL = 480  # DSC_MAX_KEYS_TOTAL: long prompts (77*k tokens) run as chunks of 80 keys
+
+
+def _padded_pitch(S: int) -> int:
+    return MAX_KEYS * ((S + MAX_KEYS - 1) // MAX_KEYS)
 
 
 def _region_layout_ok(W: torch.Tensor) -> bool:
-    """[B', L, S] fp32 with unit key stride, row pitch in [S, 80] and batch stride L * pitch (dense or padded)."""
+    """[B', L, S] fp32 with unit key stride and batch stride L * pitch; row pitch in [S, 80] (dense or padded), or,
+    for long prompts, any multiple of 4 floats with a 16-byte aligned base."""
     Bw, L, S = W.shape
     pitch = W.stride(1)
-    return (W.stride(2) == 1 and S <= pitch <= MAX_KEYS and (Bw == 1 or W.stride(0) == L * pitch)
-            and W.data_ptr() % 4 == 0)
+    if W.stride(2) != 1 or pitch < S or (Bw > 1 and W.stride(0) != L * pitch):
+        return False
+    if S <= MAX_KEYS:
+        return pitch <= MAX_KEYS and W.data_ptr() % 4 == 0
+    return pitch % 4 == 0 and W.data_ptr() % 16 == 0
 
 
 def padded_region_map(W: torch.Tensor) -> torch.Tensor:
-    """The same [B', L, S] values in the fast device layout: rows 80 floats apart (16-byte aligned rows that the
-    kernels fetch with TMA boxes and read as 128-bit words).  Returns a [B', L, S] VIEW of a zero-padded
-    [B', L, 80] buffer, so it still indexes, compares and prints like the reference's tensor."""
+    """The same [B', L, S] values in the fast device layout: rows 80 floats apart (a multiple of 80 for long
+    prompts), i.e. 16-byte aligned rows that the kernels fetch with TMA boxes and read as 128-bit words.  Returns a
+    [B', L, S] VIEW of a zero-padded buffer, so it still indexes, compares and prints like the reference's tensor."""
     Bw, L, S = W.shape
-    if S > MAX_KEYS:
-        raise NotImplementedError(f"at most {MAX_KEYS} keys are supported, got {S}")
-    if W.stride(1) == MAX_KEYS and _region_layout_ok(W):
+    if S > MAX_KEYS_TOTAL:
+        raise NotImplementedError(f"at most {MAX_KEYS_TOTAL} keys are supported, got {S}")
+    pitch = _padded_pitch(S)
+    if W.stride(1) == pitch and _region_layout_ok(W):
         return W
-    buf = torch.zeros((Bw, L, MAX_KEYS), dtype=torch.float32, device=W.device)
+    buf = torch.zeros((Bw, L, pitch), dtype=torch.float32, device=W.device)
     buf[:, :, :S] = W
     return buf[:, :, :S]
 
@@ -144,7 +155,10 @@ def region_attention(
     if W.dtype != torch.float32 or W.device != q.device or not _region_layout_ok(W):
         W = padded_region_map(W.to(device=q.device, dtype=torch.float32))
     scale = 1.0 / math.sqrt(D) if scale is None else float(scale)
-    ws = get_workspace(q.device) if workspace is None else workspace
+    need = workspace_bytes(B, H, L, D, S) if S > MAX_KEYS else 0
+    ws = get_workspace(q.device, need) if workspace is None else workspace
+    if ws.numel() < need:
+        raise ValueError(f"workspace too small for S={S} keys: {ws.numel()} < {need} bytes")
     out = torch.empty((B, L, H * D), dtype=q.dtype, device=q.device)
 
     sigma_ptr, sigma_host = None, 0.0

@@ -68,7 +68,7 @@ static int check_dims(int B, int H, int L, int D, int S, int dtype) {
     return fail(DSC_ERR_INVALID_ARGUMENT, "non-positive dimension (B=%d H=%d L=%d D=%d S=%d)", B, H, L, D, S);
   if (dtype != DSC_DTYPE_F16 && dtype != DSC_DTYPE_BF16) return fail(DSC_ERR_INVALID_ARGUMENT, "bad dtype code %d", dtype);
   if (heads_per_group(D) == 0) return fail(DSC_ERR_UNSUPPORTED, "head dim %d not in {40,64,80,128,160}", D);
-  if (S > DSC_MAX_KEYS) return fail(DSC_ERR_UNSUPPORTED, "S=%d keys > %d", S, DSC_MAX_KEYS);
+  if (S > DSC_MAX_KEYS_TOTAL) return fail(DSC_ERR_UNSUPPORTED, "S=%d keys > %d", S, DSC_MAX_KEYS_TOTAL);
   return DSC_OK;
 }
 
@@ -82,6 +82,13 @@ static void fill_partition(XattnParams& p, int B, int H, int L, int D, int S) {
   p.n_sl = (L + 15) / 16;
   p.total = static_cast<long long>(B) * p.n_hg * p.n_sl;
 }
+
+// Long prompts (S > DSC_MAX_KEYS; the reference concatenates 77-token windows, prompt_parser.py:161-194): the keys are
+// processed as chunks of <= 80.  The workspace then also holds the per-chunk outputs and log-sum-exps.
+static int n_chunks(int S) { return (S + DSC_MAX_KEYS - 1) / DSC_MAX_KEYS; }
+static size_t stats_bytes() { return static_cast<size_t>(kWorkspaceHeader) + sizeof(double) * 2 * kMaxPartials; }
+static size_t chunk_out_bytes(int B, int H, int L, int D) { return static_cast<size_t>(B) * L * H * D * 2; }
+static size_t chunk_lse_bytes(int B, int H, int L) { return (static_cast<size_t>(B) * H * L * 4 + 15) / 16 * 16; }
 
 }  // namespace dsc
 
@@ -98,7 +105,8 @@ int dsc_sm_count(void) { return sm_count_cached(); }
 int dsc_xattn_workspace_bytes(int B, int H, int L, int D, int S, size_t* out) {
   if (!out) return fail(DSC_ERR_INVALID_ARGUMENT, "out is null");
   if (B <= 0 || H <= 0 || L <= 0 || D <= 0 || S <= 0) return fail(DSC_ERR_INVALID_ARGUMENT, "non-positive dimension");
-  *out = static_cast<size_t>(kWorkspaceHeader) + sizeof(double) * 2 * kMaxPartials;
+  *out = stats_bytes();
+  if (S > DSC_MAX_KEYS) *out += n_chunks(S) * (chunk_out_bytes(B, H, L, D) + chunk_lse_bytes(B, H, L));
   return DSC_OK;
 }
 
@@ -121,9 +129,25 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
   p.k_ss = k_str[2];
   p.scale = scale;
   p.ws = static_cast<Workspace*>(workspace);
-  if (stats_grid(p.total) > kMaxPartials) return fail(DSC_ERR_UNSUPPORTED, "grid exceeds workspace partial slots");
-  cudaError_t e = use_tc5(D, true) ? run_stats_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
-                             : run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
+  const int C = n_chunks(S);
+  if (static_cast<long long>(stats_grid(p.total)) * C > kMaxPartials)
+    return fail(DSC_ERR_UNSUPPORTED, "grid x key chunks exceeds the workspace's partial slots");
+  p.n_total = static_cast<double>(B) * H * static_cast<double>(L) * S;
+  p.fold_chunks = 1;
+  cudaError_t e = cudaSuccess;
+  if (C == 1) {
+    e = use_tc5(D, true) ? run_stats_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
+                         : run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
+  } else {  // sums over key chunks; the last launch folds every chunk's partials into the std of the WHOLE call
+    const size_t esz = 2;
+    for (int c = 0; c < C && e == cudaSuccess; ++c) {
+      p.k = static_cast<const char*>(k) + static_cast<size_t>(c) * DSC_MAX_KEYS * k_str[2] * esz;
+      p.S = (c == C - 1) ? S - c * DSC_MAX_KEYS : DSC_MAX_KEYS;
+      p.chunk = c;
+      p.fold_chunks = (c == C - 1) ? C : 0;
+      e = run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
+    }
+  }
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_stats");
 }
 
@@ -143,8 +167,12 @@ int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t
   if (!aligned16(out) || o_str[2] != 1 || o_str[1] % 8 != 0 || o_str[0] % 8 != 0)
     return fail(DSC_ERR_LAYOUT, "out: need 16-byte base, unit inner stride, row/batch strides multiple of 8");
   if ((reinterpret_cast<uintptr_t>(W) & 3) != 0) return fail(DSC_ERR_LAYOUT, "W must be 4-byte aligned");
-  if (w_pitch < S || w_pitch > DSC_MAX_KEYS)
+  const int C = n_chunks(S);
+  if (w_pitch < S || (C == 1 && w_pitch > DSC_MAX_KEYS))
     return fail(DSC_ERR_LAYOUT, "w_pitch=%d must be in [S=%d, %d]", w_pitch, S, DSC_MAX_KEYS);
+  if (C > 1 && (w_pitch % 4 != 0 || !aligned16(W)))
+    return fail(DSC_ERR_LAYOUT, "S=%d > %d keys: W rows must be 16-byte aligned (w_pitch %% 4 == 0, got %d)", S,
+                DSC_MAX_KEYS, w_pitch);
   XattnParams p{};
   fill_partition(p, B, H, L, D, S);
   p.q = q;
@@ -166,8 +194,31 @@ int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t
   p.o_sb = o_str[0];
   p.o_sl = o_str[1];
   p.ws = const_cast<Workspace*>(static_cast<const Workspace*>(workspace));
-  cudaError_t e = use_tc5(D, false) ? run_forward_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
-                             : run_forward(p, D, dtype, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaSuccess;
+  if (C == 1) {
+    e = use_tc5(D, false) ? run_forward_tc5(p, D, dtype, st) : run_forward(p, D, dtype, st);
+  } else {
+    // per key chunk: softmax over the chunk's keys (with the std of the WHOLE call) -> dense chunk output + log2-sum-exp
+    // in the workspace (layout: stats | C chunk outputs | C lse planes; see dsc_xattn_workspace_bytes); then one merge
+    char* wsb = static_cast<char*>(const_cast<void*>(workspace));
+    char* chunk_out = wsb + stats_bytes();
+    float* lse = reinterpret_cast<float*>(chunk_out + C * chunk_out_bytes(B, H, L, D));
+    const size_t lse_stride = chunk_lse_bytes(B, H, L) / 4;
+    for (int c = 0; c < C && e == cudaSuccess; ++c) {
+      p.k = static_cast<const char*>(k) + static_cast<size_t>(c) * DSC_MAX_KEYS * k_str[2] * 2;
+      p.v = static_cast<const char*>(v) + static_cast<size_t>(c) * DSC_MAX_KEYS * v_str[2] * 2;
+      p.S = (c == C - 1) ? S - c * DSC_MAX_KEYS : DSC_MAX_KEYS;
+      p.w_col0 = c * DSC_MAX_KEYS;
+      p.out = chunk_out + c * chunk_out_bytes(B, H, L, D);
+      p.o_sb = static_cast<long long>(L) * H * D;
+      p.o_sl = static_cast<long long>(H) * D;
+      p.lse = lse + c * lse_stride;
+      e = run_forward(p, D, dtype, st);
+    }
+    if (e == cudaSuccess)
+      e = run_merge_chunks(chunk_out, lse, C, out, o_str[0], o_str[1], B, H, L, D, dtype, st);
+  }
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_forward");
 }
 

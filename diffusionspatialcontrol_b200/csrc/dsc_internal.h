@@ -31,7 +31,14 @@ struct XattnParams {
   int n_sl;         // 16-row slices per (batch, head-group)
   long long total;  // B * n_hg * n_sl
   Workspace* ws;
-  int w_pitch;          // floats between consecutive query rows of W (S <= w_pitch <= 80)
+  int w_pitch;          // floats between consecutive query rows of W
+  // long prompts (more than DSC_MAX_KEYS keys) run as chunks of <= 80 keys: pass 1 accumulates its partials per
+  // chunk and folds them all at the last one; pass 2 writes per-chunk outputs + log-sum-exp, merged afterwards
+  int chunk;            // index of this key chunk (partials slot = chunk * gridDim.x + blockIdx.x)
+  int fold_chunks;      // pass 1: number of chunk slots to fold into the std at the end of this launch (0 = none)
+  double n_total;       // pass 1: number of scores of the WHOLE call (all chunks)
+  int w_col0;           // pass 2: first W column of this chunk
+  float* lse;           // pass 2: optional [B, H, L] log2-sum-exp of each row's logits (nullptr = not wanted)
   unsigned flags;       // 4-warpgroup tcgen05 kernel: launcher-set mode bits (see launch_tc5x4)
 };
 
@@ -40,6 +47,9 @@ int heads_per_group(int D);  // 0 if D is unsupported
 int stats_grid(long long total);
 cudaError_t run_stats(const XattnParams& p, int D, int dtype, cudaStream_t st);
 cudaError_t run_forward(const XattnParams& p, int D, int dtype, cudaStream_t st);
+// out[b, l, h*D + d] = sum_c w_c * chunk_out[c][b, l, h*D + d], w_c = 2^(lse[c][b,h,l] - max) / sum (chunk outputs dense)
+cudaError_t run_merge_chunks(const void* chunk_out, const float* lse, int n_chunks, void* out, long long o_sb, long long o_sl,
+                             int B, int H, int L, int D, int dtype, cudaStream_t st);
 
 // tcgen05 / TMEM implementation of the same two passes (xattn_tc5.cu), D in {40, 80}
 bool tc5_supports(int D);

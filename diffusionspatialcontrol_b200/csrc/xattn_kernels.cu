@@ -278,8 +278,9 @@ xattn_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
       a += red[w];
       b += red[8 + w];
     }
-    partials[2 * blockIdx.x] = a;
-    partials[2 * blockIdx.x + 1] = b;
+    const unsigned int slot = p.chunk * gridDim.x + blockIdx.x;
+    partials[2 * slot] = a;
+    partials[2 * slot + 1] = b;
     __threadfence();
     const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
     s_last = (t == gridDim.x - 1) ? 1u : 0u;
@@ -288,7 +289,8 @@ xattn_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   if (s_last && warp == 0) {
     __threadfence();
     double a = 0.0, b = 0.0;
-    for (unsigned int i = lane; i < gridDim.x; i += 32) {  // fixed assignment + fixed tree = deterministic
+    const unsigned int n_fold = p.fold_chunks * gridDim.x;  // 0: an earlier key chunk of a long prompt, nothing to publish yet
+    for (unsigned int i = lane; i < n_fold; i += 32) {  // fixed assignment + fixed tree = deterministic
       a += __ldcg(partials + 2 * i);
       b += __ldcg(partials + 2 * i + 1);
     }
@@ -297,9 +299,13 @@ xattn_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
       a += __shfl_xor_sync(0xffffffffu, a, o);
       b += __shfl_xor_sync(0xffffffffu, b, o);
     }
-    if (lane == 0) {
+    if (lane == 0 && n_fold == 0) {
+      __threadfence();
+      p.ws->ticket = 0u;
+    }
+    if (lane == 0 && n_fold != 0) {
       const double sc = static_cast<double>(p.scale);
-      const double n = static_cast<double>(p.B) * p.H * static_cast<double>(p.L) * p.S;
+      const double n = p.n_total;
       const double sum = a * sc, sumsq = b * sc * sc;
       const double mean = sum / n;
       double var = (n > 1.0) ? (sumsq - sum * mean) / (n - 1.0) : nan("");
@@ -309,7 +315,7 @@ xattn_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
       p.ws->sum = sum;
       p.ws->sumsq = sumsq;
       p.ws->n = n;
-      p.ws->n_partials = gridDim.x;
+      p.ws->n_partials = n_fold;
       __threadfence();
       p.ws->ticket = 0u;  // reusable without a memset
     }
@@ -322,7 +328,7 @@ xattn_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
 template <typename T, int D>
 __global__ void __launch_bounds__(256, 1)
 xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                     const __grid_constant__ CUtensorMap tm_v) {
+                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_w) {
   using TL = Tile<D>;
   constexpr int PITCH = TL::PITCH;
   constexpr int ND = TL::ND;
@@ -366,6 +372,8 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
   bool have_beta = false;
   const float scale_l2 = p.scale * kLog2e;
   const int w_rep = p.B / p.Bw;
+  const bool w_tmap = (p.flags & 1u) != 0;          // W rows 16-byte aligned: slices arrive as one 80 x 16 box
+  const int wp = w_tmap ? TL::KV_ROWS : p.w_pitch;  // floats between W rows in shared memory
 
   uint32_t it = 0, kvphase = 0;
 
@@ -388,10 +396,12 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
       const uint32_t wbytes = rows * p.w_pitch * 4;
       const bool w_bulk = ((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0;
       if (lane == 0) {
-        mbar_arrive_expect_tx(qbar, TL::QS_BYTES + (w_bulk ? wbytes : 0));
+        mbar_arrive_expect_tx(qbar, TL::QS_BYTES + (w_tmap ? TL::WS_BYTES : w_bulk ? wbytes : 0));
         tma_box_load(sQ, &tm_q, sg.hg * (TL::GW / 2), l0, sg.b, qbar, pol_stream);
+        if (w_tmap) tma_box_load(sW, &tm_w, p.w_col0, l0, sg.b / w_rep, qbar, pol_stream);  // columns >= pitch: zeros
       }
-      if (w_bulk) {
+      if (w_tmap) {
+      } else if (w_bulk) {
         if (lane == 16) bulk_g2s_hint(sW, wsrc, wbytes, qbar, pol_stream);
       } else {  // odd tail / unaligned W: plain loads (visible to this warp after the __syncwarp below)
         float* wdst = const_cast<float*>(wsm);
@@ -427,7 +437,7 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
         for (int i = 0; i < 4; ++i) {
           const int col = 8 * j + 2 * t + (i & 1);
           const int row = g + 8 * (i >> 1);
-          bw[j][i] = (col < p.S) ? wsm[row * p.w_pitch + col] * beta_l2 : -INFINITY;
+          bw[j][i] = (col < p.S) ? wsm[row * wp + col] * beta_l2 : -INFINITY;
         }
       }
 
@@ -466,6 +476,11 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
         sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
         sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
         const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+        if (p.lse != nullptr && t == 0) {  // log2-sum-exp of the row's logits (key chunks of a long prompt are merged with it)
+          float* lrow = p.lse + (static_cast<long long>(sg.b) * p.H + sg.hg * TL::G + h) * p.L + l0;
+          if (g < rows) lrow[g] = mx0 + log2f(sum0);
+          if (g + 8 < rows) lrow[g + 8] = mx1 + log2f(sum1);
+        }
 
         __syncwarp();  // Q_h has been consumed by every lane: its columns may now be overwritten by O_h
 #pragma unroll
@@ -557,7 +572,8 @@ static cudaError_t launch_stats(const XattnParams& p, cudaStream_t st) {
 }
 
 template <typename T, int D>
-static cudaError_t launch_forward(const XattnParams& p, cudaStream_t st) {
+static cudaError_t launch_forward(const XattnParams& p_in, cudaStream_t st) {
+  XattnParams p = p_in;
   using TL = Tile<D>;
   static thread_local int configured_dev = -1;
   int dev = 0;
@@ -573,6 +589,21 @@ static cudaError_t launch_forward(const XattnParams& p, cudaStream_t st) {
       !make_map32(&tm_k, p.k, p.H * D, p.S, p.B, p.k_ss, p.k_sb, TL::PITCH / 4, TL::KV_ROWS) ||
       !make_map32(&tm_v, p.v, p.H * D, p.S, p.B, p.v_ss, p.v_sb, TL::PITCH / 4, TL::KV_ROWS))
     return cudaErrorInvalidValue;
+  CUtensorMap tm_w = tm_q;
+  p.flags = 0;
+  if (p.w_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0) {  // fp32 [Bw, L, pitch] -> boxes of 80 x 16
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return cudaErrorInvalidValue;
+    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.w_pitch), static_cast<cuuint64_t>(p.L), static_cast<cuuint64_t>(p.Bw)};
+    cuuint64_t gstr[2] = {static_cast<cuuint64_t>(p.w_pitch) * 4, static_cast<cuuint64_t>(p.L) * p.w_pitch * 4};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(TL::KV_ROWS), static_cast<cuuint32_t>(TL::ROWS), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.W), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    p.flags = 1;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid_for(p.total));
   cfg.blockDim = dim3(256);
@@ -584,7 +615,7 @@ static cudaError_t launch_forward(const XattnParams& p, cudaStream_t st) {
   const char* nopdl = getenv("DSC_NO_PDL");
   cfg.attrs = attr;
   cfg.numAttrs = (nopdl && nopdl[0] == '1') ? 0 : 1;  // may overlap the tail of pass 1 (griddepcontrol.wait before beta)
-  return cudaLaunchKernelEx(&cfg, xattn_forward_kernel<T, D>, p, tm_q, tm_k, tm_v);
+  return cudaLaunchKernelEx(&cfg, xattn_forward_kernel<T, D>, p, tm_q, tm_k, tm_v, tm_w);
 }
 
 int heads_per_group(int D) {
@@ -624,6 +655,62 @@ cudaError_t run_forward(const XattnParams& p, int D, int dtype, cudaStream_t st)
   } else {
     DSC_DISPATCH_D(launch_forward, __nv_bfloat16)
   }
+}
+
+// =============================================================================================
+// long prompts: merge of the per-chunk outputs (each normalised over its own <= 80 keys) with their log2-sum-exp
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) merge_chunks_kernel(const T* __restrict__ chunk_out, const float* __restrict__ lse,
+                                                           int n_chunks, T* __restrict__ out, long long o_sb, long long o_sl,
+                                                           int B, int H, int L, int D) {
+  // one thread per (b, l, h, 8-column group); chunk_out: [C][B][L][H*D] dense, lse: [C][B][H][L]
+  const int vec_per_head = D / 8;
+  const long long n = static_cast<long long>(B) * L * H * vec_per_head;
+  const long long chunk_elems = static_cast<long long>(B) * L * H * D;
+  const long long lse_elems = static_cast<long long>(B) * H * L;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vq = static_cast<int>(i % vec_per_head);
+    const int h = static_cast<int>((i / vec_per_head) % H);
+    const long long bl = i / (static_cast<long long>(vec_per_head) * H);
+    const int l = static_cast<int>(bl % L);
+    const int b = static_cast<int>(bl / L);
+    const long long li = (static_cast<long long>(b) * H + h) * L + l;
+    float m = -INFINITY;
+    for (int c = 0; c < n_chunks; ++c) m = fmaxf(m, __ldg(lse + c * lse_elems + li));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float wsum = 0.f;
+    const long long src = (bl * H + h) * D + vq * 8;
+    for (int c = 0; c < n_chunks; ++c) {
+      const float w = exp2f(__ldg(lse + c * lse_elems + li) - m);
+      wsum += w;
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(chunk_out + c * chunk_elems + src));
+      const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, static_cast<float>(v[j]), acc[j]);
+    }
+    const float inv = 1.f / wsum;
+    uint4 o;
+    o.x = Mma<T>::pack(acc[0] * inv, acc[1] * inv);
+    o.y = Mma<T>::pack(acc[2] * inv, acc[3] * inv);
+    o.z = Mma<T>::pack(acc[4] * inv, acc[5] * inv);
+    o.w = Mma<T>::pack(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(out + b * o_sb + l * o_sl + h * D + vq * 8) = o;
+  }
+}
+
+cudaError_t run_merge_chunks(const void* chunk_out, const float* lse, int n_chunks, void* out, long long o_sb, long long o_sl,
+                             int B, int H, int L, int D, int dtype, cudaStream_t st) {
+  const long long n = static_cast<long long>(B) * L * H * (D / 8);
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 16));
+  if (dtype == 0)
+    merge_chunks_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(chunk_out), lse, n_chunks,
+                                                     static_cast<__half*>(out), o_sb, o_sl, B, H, L, D);
+  else
+    merge_chunks_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(chunk_out), lse, n_chunks,
+                                                            static_cast<__nv_bfloat16*>(out), o_sb, o_sl, B, H, L, D);
+  return cudaGetLastError();
 }
 
 }  // namespace dsc

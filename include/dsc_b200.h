@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSC_VERSION 101 /* major*10000 + minor*100 + patch */
+#define DSC_VERSION 102 /* major*10000 + minor*100 + patch */
 
 #define DSC_DTYPE_F16 0
 #define DSC_DTYPE_BF16 1
@@ -41,7 +41,8 @@ extern "C" {
 #define DSC_ERR_LAYOUT (-3)           /* stride / alignment contract violated */
 #define DSC_ERR_SHAPE (-4)            /* shape contract violated (e.g. B % Bw != 0), mirrors the reference raising */
 
-#define DSC_MAX_KEYS 80 /* S (text tokens) supported by the tuned kernels; SD-1.5 uses 77 */
+#define DSC_MAX_KEYS 80 /* keys (text tokens) per kernel pass: the tuned case; SD-1.5 uses 77 */
+#define DSC_MAX_KEYS_TOTAL 480 /* long prompts (77*k tokens, reference prompt_parser.py:161-194) run as chunks of 80 keys */
 
 int dsc_version(void);
 
@@ -51,8 +52,9 @@ const char* dsc_last_error(void);
 /* Number of SMs the persistent kernels will be sized for on the current device (148 on B200). */
 int dsc_sm_count(void);
 
-/* Bytes of device workspace one attention call needs (stats + per-CTA partials + ticket).
- * The workspace must be zero-filled ONCE after allocation; calls leave it reusable. */
+/* Bytes of device workspace one attention call needs (stats + per-CTA partials + ticket; for
+ * S > DSC_MAX_KEYS also the per-key-chunk outputs and log-sum-exps that dsc_xattn_forward merges).
+ * The first 64 + 16384 bytes must be zero-filled ONCE after allocation; calls leave it reusable. */
 int dsc_xattn_workspace_bytes(int B, int H, int L, int D, int S, size_t* out /*HOST*/);
 
 /* Pass 1.  a = scale * Q K^T over the whole call; writes to `workspace`
@@ -63,7 +65,7 @@ int dsc_xattn_workspace_bytes(int B, int H, int L, int D, int S, size_t* out /*H
  * Layout contract (DSC_ERR_LAYOUT otherwise): stride(D)==1, stride(H)==D, stride(L) and stride(B)
  * multiples of 8 elements, base pointers 16-byte aligned -- i.e. the [B, L, H*D] projection output
  * viewed as heads, which is exactly what the reference processor produces
- * (attention_modify.py:471-474).  D in {40,64,80,128,160}; 1 <= S <= DSC_MAX_KEYS.
+ * (attention_modify.py:471-474).  D in {40,64,80,128,160}; 1 <= S <= DSC_MAX_KEYS_TOTAL.
  * mask_or_null: additive attention mask; only NULL is implemented (DSC_ERR_UNSUPPORTED otherwise;
  * SD-1.5 never passes one). */
 int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4] /*HOST*/, const int64_t k_str[4] /*HOST*/,
@@ -74,7 +76,8 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4] /*HOST*
  * `workspace` (written by dsc_xattn_stats earlier on the same stream).
  *
  * W: fp32 [Bw, L, S] region-weight map whose query rows are w_pitch floats apart (S <= w_pitch <=
- *    DSC_MAX_KEYS; w_pitch == S is the reference's dense tensor; batch stride = L * w_pitch); row b
+ *    DSC_MAX_KEYS; w_pitch == S is the reference's dense tensor; batch stride = L * w_pitch; for
+ *    S > DSC_MAX_KEYS any w_pitch >= S that is a multiple of 4, with a 16-byte aligned base); row b
  *    of the batch uses W[b / (B / Bw)] (the batch-major repeat_interleave of
  *    attention_modify.py:96-99); requires B % Bw == 0.  The padded form w_pitch == DSC_MAX_KEYS with
  *    a 16-byte aligned base is the fast path (rows fetched by TMA boxes and read as 128-bit words);

@@ -31,7 +31,7 @@ def test_version_and_workspace_size():
     from diffusionspatialcontrol_b200 import _lib
     from diffusionspatialcontrol_b200.attention import workspace_bytes
 
-    assert _lib.lib.dsc_version() == 101
+    assert _lib.lib.dsc_version() == 102
     assert workspace_bytes(16, 8, 4096, 40, 77) >= 64 + 16 * 148
     n = ctypes.c_size_t(0)
     assert _lib.lib.dsc_xattn_workspace_bytes(0, 8, 64, 40, 77, ctypes.byref(n)) == _lib.ERR_INVALID_ARGUMENT
@@ -48,7 +48,7 @@ def test_argument_validation_returns_codes_not_crashes():
     # unsupported head dim / too many keys / bad dtype / non-positive sizes
     assert lib.dsc_xattn_stats(fake, fake, ok_q, ok_k, None, 2, 8, 4096, 48, 77, 0.1, 0, fake, None) == _lib.ERR_UNSUPPORTED
     assert b"head dim" in lib.dsc_last_error()
-    assert lib.dsc_xattn_stats(fake, fake, ok_q, ok_k, None, 2, 8, 4096, 40, 81, 0.1, 0, fake, None) == _lib.ERR_UNSUPPORTED
+    assert lib.dsc_xattn_stats(fake, fake, ok_q, ok_k, None, 2, 8, 4096, 40, 481, 0.1, 0, fake, None) == _lib.ERR_UNSUPPORTED
     assert lib.dsc_xattn_stats(fake, fake, ok_q, ok_k, None, 2, 8, 4096, 40, 77, 0.1, 7, fake, None) == _lib.ERR_INVALID_ARGUMENT
     assert lib.dsc_xattn_stats(fake, fake, ok_q, ok_k, None, 2, 8, 0, 40, 77, 0.1, 0, fake, None) == _lib.ERR_INVALID_ARGUMENT
     # additive mask: not implemented, says so

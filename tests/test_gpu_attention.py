@@ -285,3 +285,26 @@ def test_config3_shapes_768_batch4_with_suppression():
         for sigma in (14.6146, 0.3350):
             out = dsc.region_attention(q, k, v, W, sigma)
             assert rel_l2(out.float(), _oracle(q, k, v, W, sigma)) <= TOL
+
+
+@pytest.mark.parametrize("L,D,S,B", [(1024, 80, 154, 2), (4096, 40, 231, 2), (256, 160, 154, 4), (200, 40, 100, 3),
+                                     (64, 160, 81, 2), (1024, 80, 308, 1)])
+def test_long_prompts_run_as_key_chunks(L, D, S, B):
+    """Long-prompt modes of the reference concatenate 77-token windows (S = 77 k, prompt_parser.py:161-194; the region
+    map follows the id length, encode_region_map_function.py:30).  More than 80 keys run as chunks of 80 with the std
+    of the WHOLE call and a log-sum-exp merge: same result as the oracle's single softmax over all keys."""
+    dsc, att = _dsc()
+    q, k, v = make_qkv(B, 8, L, D, S, seed=S + L, device="cuda")
+    W = synthetic_w(B, L, S).cuda()
+    W[:, : L // 3, S - 3] = -0.4  # weights in the last chunk too
+    for sigma in (9.0, 0.05):
+        out = dsc.region_attention(q, k, v, W, sigma)
+        ref = _oracle(q, k, v, W, sigma)
+        err = rel_l2(out.float(), ref)
+        assert err <= TOL, f"L={L} D={D} S={S} sigma={sigma}: rel-L2 {err:.3e}"
+    st = att.read_stats(att.score_stats(q, k))
+    want, _, _ = _std64(q, k)
+    assert abs(st["std"] - want) / want <= STD_TOL and st["n"] == B * 8 * L * S
+    with pytest.raises(Exception):
+        qq, kk, vv = make_qkv(1, 8, 64, 40, 481, seed=1, device="cuda")
+        dsc.region_attention(qq, kk, vv, torch.zeros(1, 64, 481, device="cuda"), 1.0)
