@@ -136,8 +136,12 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
   p.fold_chunks = 1;
   cudaError_t e = cudaSuccess;
   if (C == 1) {
-    e = use_tc5(D, true) ? run_stats_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
-                         : run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
+    const char* es = getenv("DSC_XATTN_STATS_IMPL");
+    const bool gram = es ? strcmp(es, "gram") == 0 : false;
+    if (gram && gram_supports(D, S)) e = run_stats_gram(p, D, dtype, static_cast<cudaStream_t>(stream));
+    else
+      e = use_tc5(D, true) ? run_stats_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
+                           : run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
   } else {  // sums over key chunks; the last launch folds every chunk's partials into the std of the WHOLE call
     const size_t esz = 2;
     for (int c = 0; c < C && e == cudaSuccess; ++c) {

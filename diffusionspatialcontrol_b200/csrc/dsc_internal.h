@@ -47,6 +47,9 @@ int heads_per_group(int D);  // 0 if D is unsupported
 int stats_grid(long long total);
 cudaError_t run_stats(const XattnParams& p, int D, int dtype, cudaStream_t st);
 cudaError_t run_forward(const XattnParams& p, int D, int dtype, cudaStream_t st);
+// pass 1 through the Gram identity (no scores formed); D = 40, S <= 80
+bool gram_supports(int D, int S);
+cudaError_t run_stats_gram(const XattnParams& p, int D, int dtype, cudaStream_t st);
 // out[b, l, h*D + d] = sum_c w_c * chunk_out[c][b, l, h*D + d], w_c = 2^(lse[c][b,h,l] - max) / sum (chunk outputs dense)
 cudaError_t run_merge_chunks(const void* chunk_out, const float* lse, int n_chunks, void* out, long long o_sb, long long o_sl,
                              int B, int H, int L, int D, int dtype, cudaStream_t st);

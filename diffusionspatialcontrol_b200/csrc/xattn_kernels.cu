@@ -21,6 +21,8 @@
 #include <cuda.h>  // CUtensorMap (types only; the encoder comes from cudaGetDriverEntryPoint)
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "dsc_device.cuh"
 #include "dsc_internal.h"
 
@@ -152,6 +154,74 @@ __device__ __forceinline__ Seg seg_of(long long idx, long long cta_end, int n_sl
   return s;
 }
 
+// CTA partial (raw, unscaled) in a fixed order -> workspace; the last CTA folds all partials.  Called by every thread
+// of the CTA (NW warps).
+template <int NW>
+__device__ __forceinline__ void publish_stats(const XattnParams& p, double dsum, double dsq) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    dsq += __shfl_xor_sync(0xffffffffu, dsq, o);
+  }
+  __shared__ double red[2 * NW];
+  __shared__ unsigned int s_last;
+  if (lane == 0) {
+    red[warp] = dsum;
+    red[NW + warp] = dsq;
+  }
+  __syncthreads();
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
+  if (tid == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < NW; ++w) {
+      a += red[w];
+      b += red[NW + w];
+    }
+    const unsigned int slot = p.chunk * gridDim.x + blockIdx.x;
+    partials[2 * slot] = a;
+    partials[2 * slot + 1] = b;
+    __threadfence();
+    const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    const unsigned int n_fold = p.fold_chunks * gridDim.x;  // 0: an earlier key chunk of a long prompt, nothing to publish yet
+    for (unsigned int i = lane; i < n_fold; i += 32) {  // fixed assignment + fixed tree = deterministic
+      a += __ldcg(partials + 2 * i);
+      b += __ldcg(partials + 2 * i + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0 && n_fold == 0) {
+      __threadfence();
+      p.ws->ticket = 0u;
+    }
+    if (lane == 0 && n_fold != 0) {
+      const double sc = static_cast<double>(p.scale);
+      const double n = p.n_total;
+      const double sum = a * sc, sumsq = b * sc * sc;
+      const double mean = sum / n;
+      double var = (n > 1.0) ? (sumsq - sum * mean) / (n - 1.0) : nan("");
+      if (var < 0.0) var = 0.0;
+      p.ws->std_unbiased = static_cast<float>(sqrt(var));
+      p.ws->mean = static_cast<float>(mean);
+      p.ws->sum = sum;
+      p.ws->sumsq = sumsq;
+      p.ws->n = n;
+      p.ws->n_partials = n_fold;
+      __threadfence();
+      p.ws->ticket = 0u;  // reusable without a memset
+    }
+  }
+}
+
 // =============================================================================================
 // pass 1
 // =============================================================================================
@@ -258,68 +328,175 @@ xattn_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
     idx = sg.end;
   }
 
-  // CTA partial (raw, unscaled) in a fixed order -> workspace; the last CTA folds all partials.
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-    dsq += __shfl_xor_sync(0xffffffffu, dsq, o);
-  }
-  __shared__ double red[2 * 8];
-  __shared__ unsigned int s_last;
-  if (lane == 0) {
-    red[warp] = dsum;
-    red[8 + warp] = dsq;
-  }
-  __syncthreads();
-  double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
+  publish_stats<TL::WARPS>(p, dsum, dsq);
+}
+
+// =============================================================================================
+// pass 1 through the Gram identity (D = 40):   sum a^2 = scale^2 <Q_h^T Q_h, K_h^T K_h>_F ,  sum a = scale (sum_l q_l).(sum_s k_s)
+//
+// The scores are never formed: per (batch, head) a warp accumulates the 40 x 40 Gram matrix of its head's Q columns over
+// all query rows (A = Q^T and B = Q are the SAME ldmatrix.trans fragments of the row-major tile: 3 ldmatrix.x4 feed
+// 15 + 3 mma.sync per 16 rows), the column sums ride along as a product with a ones fragment, and at the end of the
+// (batch, head-group) run the Gram matrix of K (80 zero-padded keys) is formed in the same fragment layout and the two
+// are contracted element by element.  No per-score work at all: pass 1 becomes a pure stream of Q.
+// 8 consumer warps = the 8 heads of a 320-column tile, warp 8 = TMA producer (64-row tiles, 3-stage ring).
+#ifdef DSC_TRACE
+__device__ unsigned long long g_gram_times[160][8];  // globaltimer (ns) per CTA at the stamps below
+__device__ __forceinline__ unsigned long long gram_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define GRAM_STAMP(k) do { if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == ((k) == 2 || (k) == 3 || (k) == 4 ? 0 : 8) && blockIdx.x < 160) g_gram_times[blockIdx.x][k] = gram_now(); } while (0)
+#else
+#define GRAM_STAMP(k) do {} while (0)
+#endif
+
+template <int D>
+struct GramTile {
+  using TL = Tile<D>;
+  static constexpr int ROWS = 64;
+  static constexpr int STAGES = 3;
+  static constexpr int QT_BYTES = ROWS * TL::PITCH;
+  static constexpr int SMEM = TL::KV_BYTES + STAGES * QT_BYTES + 128;
+  static constexpr int MT = (D + 15) / 16;  // m-tiles; rows >= D of the last one are a neighbour's columns and are ignored
+  static constexpr int NT = D / 8;
+  static constexpr int THREADS = 288;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(GramTile<D>::THREADS, 1)
+xattn_gram_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k) {
+  using TL = Tile<D>;
+  using GT = GramTile<D>;
+  constexpr int PITCH = TL::PITCH, MT = GT::MT, NT = GT::NT, NST = GT::STAGES;
+  static_assert(TL::G == 8 && 2 * MT >= NT, "one warp per head; the A fragments must cover every n-tile");
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  GRAM_STAMP(0);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: pass 2 may start its prologue early
+  const uint32_t sK = smem_u32(smem);
+  const uint32_t sQ = sK + TL::KV_BYTES;
+  const uint32_t bars = sQ + NST * GT::QT_BYTES;
+  const uint32_t b_kfull = bars, b_kempty = bars + 8, b_full = bars + 16, b_empty = bars + 16 + 8 * NST;
   if (tid == 0) {
-    double a = 0.0, b = 0.0;
-    for (int w = 0; w < 8; ++w) {
-      a += red[w];
-      b += red[8 + w];
+    mbar_init(b_kfull, 1);
+    mbar_init(b_kempty, TL::WARPS);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_empty + 8 * s, TL::WARPS);
     }
-    const unsigned int slot = p.chunk * gridDim.x + blockIdx.x;
-    partials[2 * slot] = a;
-    partials[2 * slot + 1] = b;
-    __threadfence();
-    const unsigned int t = atomicAdd(&p.ws->ticket, 1u);
-    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    fence_mbar_init();
   }
+  fence_proxy_async();
   __syncthreads();
-  if (s_last && warp == 0) {
-    __threadfence();
-    double a = 0.0, b = 0.0;
-    const unsigned int n_fold = p.fold_chunks * gridDim.x;  // 0: an earlier key chunk of a long prompt, nothing to publish yet
-    for (unsigned int i = lane; i < n_fold; i += 32) {  // fixed assignment + fixed tree = deterministic
-      a += __ldcg(partials + 2 * i);
-      b += __ldcg(partials + 2 * i + 1);
+
+  const long long cta_begin = p.total * blockIdx.x / gridDim.x;
+  const long long cta_end = p.total * (blockIdx.x + 1) / gridDim.x;
+  double dsum = 0.0, dsq = 0.0;
+  GRAM_STAMP(1);
+
+  if (warp == TL::WARPS) {
+    if (lane == 0) {  // ---- producer
+      const uint64_t pol = policy_evict_last();  // Q is read again by pass 2, K by both
+      uint32_t i = 0, run = 0;
+      for (long long idx = cta_begin; idx < cta_end; ++run) {
+        const Seg sg = seg_of<D>(idx, cta_end, p.n_sl, p.n_hg, p.H);
+        if (run > 0) mbar_wait(b_kempty, (run - 1) & 1);
+        mbar_arrive_expect_tx(b_kfull, TL::KV_BYTES);  // 80-row box, keys >= S arrive as zeros
+        tma_box_load(sK, &tm_k, sg.hg * (TL::GW / 2), 0, sg.b, b_kfull, pol);
+        for (long long t = idx; t < sg.end; ++t, ++i) {
+          const uint32_t s = i % NST;
+          if (i >= NST) mbar_wait(b_empty + 8 * s, ((i / NST) - 1) & 1);
+          mbar_arrive_expect_tx(b_full + 8 * s, GT::QT_BYTES);  // rows >= L arrive as zeros
+          tma_box_load(sQ + s * GT::QT_BYTES, &tm_q, sg.hg * (TL::GW / 2), static_cast<int>(t % p.n_sl) * GT::ROWS, sg.b,
+                       b_full + 8 * s, pol);
+        }
+        idx = sg.end;
+      }
     }
+  } else {
+    // ---- consumers: warp = head of the group
+    const int h = warp, g = lane >> 2, t4 = lane & 3;
+    const uint32_t ones = std::is_same<T, __half>::value ? 0x3C003C00u : 0x3F803F80u;
+    // ldmatrix.x4.trans of m-tile mi at k-step ks: matrix q = lane / 8 -> rows (q / 2) * 8 + lane % 8, column block
+    // 2 mi + (q & 1); the four results are the mma A fragment of Q^T, and the B fragments of n-tiles 2 mi, 2 mi + 1
+    const uint32_t lane_off = (((lane >> 4) & 1) * 8 + (lane & 7)) * PITCH + (h * D + ((lane >> 3) & 1) * 8) * 2;
+    float cq[MT][NT][4], cs[MT][4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
+    for (int mi = 0; mi < MT; ++mi) {
+      cs[mi][0] = cs[mi][1] = cs[mi][2] = cs[mi][3] = 0.f;
+#pragma unroll
+      for (int nj = 0; nj < NT; ++nj) cq[mi][nj][0] = cq[mi][nj][1] = cq[mi][nj][2] = cq[mi][nj][3] = 0.f;
     }
-    if (lane == 0 && n_fold == 0) {
-      __threadfence();
-      p.ws->ticket = 0u;
-    }
-    if (lane == 0 && n_fold != 0) {
-      const double sc = static_cast<double>(p.scale);
-      const double n = p.n_total;
-      const double sum = a * sc, sumsq = b * sc * sc;
-      const double mean = sum / n;
-      double var = (n > 1.0) ? (sumsq - sum * mean) / (n - 1.0) : nan("");
-      if (var < 0.0) var = 0.0;
-      p.ws->std_unbiased = static_cast<float>(sqrt(var));
-      p.ws->mean = static_cast<float>(mean);
-      p.ws->sum = sum;
-      p.ws->sumsq = sumsq;
-      p.ws->n = n;
-      p.ws->n_partials = n_fold;
-      __threadfence();
-      p.ws->ticket = 0u;  // reusable without a memset
+    uint32_t i = 0, run = 0;
+    for (long long idx = cta_begin; idx < cta_end; ++run) {
+      const Seg sg = seg_of<D>(idx, cta_end, p.n_sl, p.n_hg, p.H);
+      const bool active = h < sg.nheads;
+      for (long long t = idx; t < sg.end; ++t, ++i) {
+        const uint32_t s = i % NST;
+        mbar_wait(b_full + 8 * s, (i / NST) & 1);
+        if (i == 0) GRAM_STAMP(2);
+        if (active) {
+          const uint32_t tile = sQ + s * GT::QT_BYTES + lane_off;
+#pragma unroll
+          for (int ks = 0; ks < GT::ROWS / 16; ++ks) {
+            uint32_t x[MT][4];
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi) ldsm_x4_t(x[mi], tile + ks * 16 * PITCH + mi * 32);
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi) {
+#pragma unroll
+              for (int nj = 0; nj < NT; ++nj) Mma<T>::k16(cq[mi][nj], x[mi], x[nj >> 1][nj & 1], x[nj >> 1][2 + (nj & 1)]);
+              Mma<T>::k16(cs[mi], x[mi], ones, ones);  // column sums of Q (every n column holds the same sum)
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_empty + 8 * s);
+      }
+      // ---- end of the (batch, head-group) run: contract with the Gram matrix of K
+      GRAM_STAMP(3);
+      mbar_wait(b_kfull, run & 1);
+      if (active) {
+        float acc2 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+          float ck[NT][4], csk[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int nj = 0; nj < NT; ++nj) ck[nj][0] = ck[nj][1] = ck[nj][2] = ck[nj][3] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < TL::KV_ROWS / 16; ++ks) {
+            uint32_t x[MT][4];
+#pragma unroll
+            for (int m2 = 0; m2 < MT; ++m2) ldsm_x4_t(x[m2], sK + lane_off + ks * 16 * PITCH + m2 * 32);
+#pragma unroll
+            for (int nj = 0; nj < NT; ++nj) Mma<T>::k16(ck[nj], x[mi], x[nj >> 1][nj & 1], x[nj >> 1][2 + (nj & 1)]);
+            Mma<T>::k16(csk, x[mi], ones, ones);
+          }
+          const bool v_lo = 16 * mi + g < D, v_hi = 16 * mi + g + 8 < D;
+#pragma unroll
+          for (int nj = 0; nj < NT; ++nj) {
+            if (v_lo) acc2 += cq[mi][nj][0] * ck[nj][0] + cq[mi][nj][1] * ck[nj][1];
+            if (v_hi) acc2 += cq[mi][nj][2] * ck[nj][2] + cq[mi][nj][3] * ck[nj][3];
+          }
+          if (t4 == 0) {
+            if (v_lo) acc1 += cs[mi][0] * csk[0];
+            if (v_hi) acc1 += cs[mi][2] * csk[2];
+          }
+          cs[mi][0] = cs[mi][1] = cs[mi][2] = cs[mi][3] = 0.f;
+#pragma unroll
+          for (int nj = 0; nj < NT; ++nj) cq[mi][nj][0] = cq[mi][nj][1] = cq[mi][nj][2] = cq[mi][nj][3] = 0.f;
+        }
+        dsq += static_cast<double>(acc2);
+        dsum += static_cast<double>(acc1);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_kempty);
+      idx = sg.end;
     }
   }
+  GRAM_STAMP(4);
+  __syncthreads();
+  GRAM_STAMP(5);
+  publish_stats<TL::WARPS + 1>(p, dsum, dsq);
+  GRAM_STAMP(6);
 }
 
 // =============================================================================================
@@ -572,6 +749,31 @@ static cudaError_t launch_stats(const XattnParams& p, cudaStream_t st) {
 }
 
 template <typename T, int D>
+static cudaError_t launch_gram_stats(const XattnParams& p_in, cudaStream_t st) {
+  using TL = Tile<D>;
+  using GT = GramTile<D>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_gram_stats_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT::SMEM);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  XattnParams p = p_in;
+  p.n_sl = (p.L + GT::ROWS - 1) / GT::ROWS;  // 64-row tiles here
+  p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
+  CUtensorMap tm_q, tm_k;
+  if (!make_map32(&tm_q, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, TL::PITCH / 4, GT::ROWS) ||
+      !make_map32(&tm_k, p.k, p.H * D, p.S, p.B, p.k_ss, p.k_sb, TL::PITCH / 4, TL::KV_ROWS))
+    return cudaErrorInvalidValue;
+  const int sms = sm_count_cached();
+  const int grid = static_cast<int>(p.total < sms ? p.total : sms);
+  xattn_gram_stats_kernel<T, D><<<grid, GT::THREADS, GT::SMEM, st>>>(p, tm_q, tm_k);
+  return cudaGetLastError();
+}
+
+template <typename T, int D>
 static cudaError_t launch_forward(const XattnParams& p_in, cudaStream_t st) {
   XattnParams p = p_in;
   using TL = Tile<D>;
@@ -649,6 +851,13 @@ cudaError_t run_stats(const XattnParams& p, int D, int dtype, cudaStream_t st) {
   }
 }
 
+bool gram_supports(int D, int S) { return D == 40 && S <= Tile<40>::KV_ROWS; }
+
+cudaError_t run_stats_gram(const XattnParams& p, int D, int dtype, cudaStream_t st) {
+  if (!gram_supports(D, p.S)) return cudaErrorInvalidValue;
+  return dtype == 0 ? launch_gram_stats<__half, 40>(p, st) : launch_gram_stats<__nv_bfloat16, 40>(p, st);
+}
+
 cudaError_t run_forward(const XattnParams& p, int D, int dtype, cudaStream_t st) {
   if (dtype == 0) {
     DSC_DISPATCH_D(launch_forward, __half)
@@ -714,3 +923,10 @@ cudaError_t run_merge_chunks(const void* chunk_out, const float* lse, int n_chun
 }
 
 }  // namespace dsc
+
+#ifdef DSC_TRACE
+extern "C" int dsc_debug_gram_times(unsigned long long* out /*HOST 160*8*/) {
+  cudaDeviceSynchronize();
+  return static_cast<int>(cudaMemcpyFromSymbol(out, dsc::g_gram_times, sizeof(unsigned long long) * 160 * 8));
+}
+#endif

@@ -308,3 +308,20 @@ def test_long_prompts_run_as_key_chunks(L, D, S, B):
     with pytest.raises(Exception):
         qq, kk, vv = make_qkv(1, 8, 64, 40, 481, seed=1, device="cuda")
         dsc.region_attention(qq, kk, vv, torch.zeros(1, 64, 481, device="cuda"), 1.0)
+
+
+@pytest.mark.parametrize("B,L,S", [(2, 1024, 77), (16, 4096, 77), (3, 200, 40), (1, 64, 77), (4, 9216, 80)])
+def test_gram_identity_stats_kernel(monkeypatch, B, L, S):
+    """DSC_XATTN_STATS_IMPL=gram: pass 1 without forming a single score (sum a^2 = scale^2 <Q^T Q, K^T K>, SURVEY 8(f)
+    rank 2), D = 40.  Same published statistics as the score-based kernels, and the forward pass that consumes them."""
+    dsc, att = _dsc()
+    monkeypatch.setenv("DSC_XATTN_STATS_IMPL", "gram")
+    q, k, v = make_qkv(B, 8, L, 40, S, seed=B + L, device="cuda")
+    st = att.read_stats(att.score_stats(q, k))
+    want, wsum, wsq = _std64(q, k)
+    assert st["n"] == B * 8 * L * S
+    assert abs(st["std"] - want) / want <= STD_TOL, (st["std"], want)
+    assert abs(st["sumsq"] - wsq) / wsq <= 1e-5 and abs(st["sum"] - wsum) <= 1e-5 * (wsq * st["n"]) ** 0.5
+    W = synthetic_w(B, L, S).cuda()
+    out = dsc.region_attention(q, k, v, W, 8.0)
+    assert rel_l2(out.float(), _oracle(q, k, v, W, 8.0)) <= TOL
