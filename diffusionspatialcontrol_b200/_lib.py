@@ -31,6 +31,13 @@ SIGNATURES = {
          c_int, c_void_p, c_float, c_void_p, c_void_p, POINTER(c_int64)]
         + [c_int] * 5 + [c_float, c_int, c_void_p],
     ),
+    "dsc_xattn_call_launches": (c_int, [c_int] * 5),
+    "dsc_xattn_call": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), c_void_p, c_int,
+         c_int, c_void_p, c_float, c_void_p, c_void_p, POINTER(c_int64)]
+        + [c_int] * 5 + [c_float, c_int, c_void_p],
+    ),
     "dsc_region_downsample": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]),
     "dsc_region_accumulate": (
         c_int,

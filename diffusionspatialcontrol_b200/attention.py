@@ -177,9 +177,7 @@ def region_attention(
     st = _stream_ptr(q.device)
     qs, ks, vs = _I64x4(*q.stride()), _I64x4(*k.stride()), _I64x4(*v.stride())
     with torch.cuda.device(q.device):
-        check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), qs, ks, None, B, H, L, D, S, scale, dt,
-                                  ws.data_ptr(), st))
-        check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), W.shape[0],
-                                    W.stride(1), sigma_ptr, sigma_host, ws.data_ptr(), out.data_ptr(), _I64x3(*out.stride()),
-                                    B, H, L, D, S, scale, dt, st))
+        check(lib.dsc_xattn_call(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), W.shape[0],
+                                 W.stride(1), sigma_ptr, sigma_host, ws.data_ptr(), out.data_ptr(), _I64x3(*out.stride()),
+                                 B, H, L, D, S, scale, dt, st))
     return out.view(B, L, H, D).transpose(1, 2)

@@ -155,11 +155,10 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_stats");
 }
 
-int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],
-                      const int64_t v_str[4], const float* W, int Bw, int w_pitch, const float* sigma_dev_or_null,
-                      float sigma_host,
-                      const void* workspace, void* out, const int64_t o_str[3], int B, int H, int L, int D, int S,
-                      float scale, int dtype, void* stream) {
+static int forward_impl(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],
+                        const int64_t v_str[4], const float* W, int Bw, int w_pitch, const float* sigma_dev_or_null,
+                        float sigma_host, const void* workspace, void* out, const int64_t o_str[3], int B, int H, int L, int D,
+                        int S, float scale, int dtype, void* stream, bool with_stats, const char* who) {
   int rc = check_dims(B, H, L, D, S, dtype);
   if (rc) return rc;
   if (!workspace || !W || !out || !o_str) return fail(DSC_ERR_INVALID_ARGUMENT, "null pointer");
@@ -200,6 +199,17 @@ int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t
   p.ws = const_cast<Workspace*>(static_cast<const Workspace*>(workspace));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
+  if (with_stats) {
+    // one attention call: a single cooperative launch when the problem fits on chip, else pass 1 then pass 2
+    if (dsc_xattn_call_launches(B, H, L, D, S) == 1) {
+      p.n_total = static_cast<double>(B) * H * static_cast<double>(L) * S;
+      p.fold_chunks = 1;
+      e = run_fused(p, D, dtype, st);
+      return e == cudaSuccess ? DSC_OK : cuda_fail(e, who);
+    }
+    rc = dsc_xattn_stats(q, k, q_str, k_str, nullptr, B, H, L, D, S, scale, dtype, const_cast<void*>(workspace), stream);
+    if (rc) return rc;
+  }
   if (C == 1) {
     e = use_tc5(D, false) ? run_forward_tc5(p, D, dtype, st) : run_forward(p, D, dtype, st);
   } else {
@@ -223,7 +233,33 @@ int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t
     if (e == cudaSuccess)
       e = run_merge_chunks(chunk_out, lse, C, out, o_str[0], o_str[1], B, H, L, D, dtype, st);
   }
-  return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_forward");
+  return e == cudaSuccess ? DSC_OK : cuda_fail(e, who);
+}
+
+int dsc_xattn_call_launches(int B, int H, int L, int D, int S) {
+  if (B <= 0 || H <= 0 || L <= 0 || S <= 0 || heads_per_group(D) == 0 || S > DSC_MAX_KEYS_TOTAL) return -1;
+  const int C = n_chunks(S);
+  if (C > 1) return 2 * C + 1;
+  const char* nf = getenv("DSC_NO_FUSED");
+  const char* impl = getenv("DSC_XATTN_IMPL");
+  const bool fused_ok = !(nf && nf[0] == '1') && !(impl && strcmp(impl, "tc5") == 0) && fused_plan(B, H, L, D, S, nullptr);
+  return fused_ok ? 1 : 2;
+}
+
+int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],
+                      const int64_t v_str[4], const float* W, int Bw, int w_pitch, const float* sigma_dev_or_null,
+                      float sigma_host, const void* workspace, void* out, const int64_t o_str[3], int B, int H, int L, int D,
+                      int S, float scale, int dtype, void* stream) {
+  return forward_impl(q, k, v, q_str, k_str, v_str, W, Bw, w_pitch, sigma_dev_or_null, sigma_host, workspace, out, o_str, B, H,
+                      L, D, S, scale, dtype, stream, false, "dsc_xattn_forward");
+}
+
+int dsc_xattn_call(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],
+                   const int64_t v_str[4], const float* W, int Bw, int w_pitch, const float* sigma_dev_or_null, float sigma_host,
+                   void* workspace, void* out, const int64_t o_str[3], int B, int H, int L, int D, int S, float scale, int dtype,
+                   void* stream) {
+  return forward_impl(q, k, v, q_str, k_str, v_str, W, Bw, w_pitch, sigma_dev_or_null, sigma_host, workspace, out, o_str, B, H,
+                      L, D, S, scale, dtype, stream, true, "dsc_xattn_call");
 }
 
 int dsc_region_downsample(const uint8_t* maps, int R, int Hpx, int Wpx, int w_r, int h_r, uint8_t* ds,

@@ -39,6 +39,7 @@ struct XattnParams {
   double n_total;       // pass 1: number of scores of the WHOLE call (all chunks)
   int w_col0;           // pass 2: first W column of this chunk
   float* lse;           // pass 2: optional [B, H, L] log2-sum-exp of each row's logits (nullptr = not wanted)
+  int fused_cps;        // fused single-launch kernel: CTAs per (batch, head-group) segment
   unsigned flags;       // 4-warpgroup tcgen05 kernel: launcher-set mode bits (see launch_tc5x4)
 };
 
@@ -47,6 +48,9 @@ int heads_per_group(int D);  // 0 if D is unsupported
 int stats_grid(long long total);
 cudaError_t run_stats(const XattnParams& p, int D, int dtype, cudaStream_t st);
 cudaError_t run_forward(const XattnParams& p, int D, int dtype, cudaStream_t st);
+// both passes in one cooperative launch when every CTA's share of Q fits in shared memory (small layers / batches)
+bool fused_plan(int B, int H, int L, int D, int S, int* cps_out);
+cudaError_t run_fused(const XattnParams& p, int D, int dtype, cudaStream_t st);
 // pass 1 through the Gram identity (no scores formed); D = 40, S <= 80
 bool gram_supports(int D, int S);
 cudaError_t run_stats_gram(const XattnParams& p, int D, int dtype, cudaStream_t st);

@@ -156,8 +156,11 @@ __device__ __forceinline__ Seg seg_of(long long idx, long long cta_end, int n_sl
 
 // CTA partial (raw, unscaled) in a fixed order -> workspace; the last CTA folds all partials.  Called by every thread
 // of the CTA (NW warps).
+// The fused single-launch kernel uses the publication as a grid barrier: the folding CTA bumps an epoch word behind the
+// public header once the std is visible; everybody else waits for the bump (see xattn_fused_kernel).
+constexpr int kEpochOffset = 48;  // bytes into the workspace header (the public dsc_xattn_stats_t ends at 40)
 template <int NW>
-__device__ __forceinline__ void publish_stats(const XattnParams& p, double dsum, double dsq) {
+__device__ __forceinline__ void publish_stats(const XattnParams& p, double dsum, double dsq, bool signal_epoch = false) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -218,6 +221,10 @@ __device__ __forceinline__ void publish_stats(const XattnParams& p, double dsum,
       p.ws->n_partials = n_fold;
       __threadfence();
       p.ws->ticket = 0u;  // reusable without a memset
+      if (signal_epoch) {
+        __threadfence();
+        atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(p.ws) + kEpochOffset), 1u);
+      }
     }
   }
 }
@@ -499,6 +506,86 @@ xattn_gram_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap
   GRAM_STAMP(6);
 }
 
+// One 16-row slice, all heads of the group: logits = S*scale + beta*W (log2 domain), softmax over the keys, O = P V.
+// Q_h columns of the slice (shared memory, qsm / sQ) are overwritten by O_h.  lse0: optional log2-sum-exp output of
+// (first head of the group, first row of the slice); heads are L floats apart.
+template <typename T, int D>
+__device__ __forceinline__ void softmax_pv_slice(int nheads, int S, float beta_l2, float scale_l2, uint32_t sQ, uint32_t sK,
+                                                 uint32_t sV, const float* wsm, int wp, unsigned char* qsm, float* lse0, int L,
+                                                 int rows, int lane) {
+  using TL = Tile<D>;
+  constexpr int PITCH = TL::PITCH;
+  constexpr int ND = TL::ND;
+  const int g = lane >> 2, t = lane & 3;
+  // beta*W in the accumulator layout, shared by all heads of the group; columns >= S get -inf
+  float bw[10][4];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = 8 * j + 2 * t + (i & 1);
+      const int row = g + 8 * (i >> 1);
+      bw[j][i] = (col < S) ? wsm[row * wp + col] * beta_l2 : -INFINITY;
+    }
+  }
+
+  for (int h = 0; h < nheads; ++h) {
+    float acc[10][4];
+    qk_tile<T, D>(acc, sQ + h * D * 2, sK + h * D * 2, lane);
+    // logits (log2 domain), row max
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      acc[j][0] = fmaf(acc[j][0], scale_l2, bw[j][0]);
+      acc[j][1] = fmaf(acc[j][1], scale_l2, bw[j][1]);
+      acc[j][2] = fmaf(acc[j][2], scale_l2, bw[j][2]);
+      acc[j][3] = fmaf(acc[j][3], scale_l2, bw[j][3]);
+      mx0 = fmaxf(mx0, fmaxf(acc[j][0], acc[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(acc[j][2], acc[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    // p = 2^(s - max), row sums, pack to the input dtype as the A operand of PV
+    float sum0 = 0.f, sum1 = 0.f;
+    uint32_t pa[5][4];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const float p0 = ex2_approx(acc[j][0] - mx0), p1 = ex2_approx(acc[j][1] - mx0);
+      const float p2 = ex2_approx(acc[j][2] - mx1), p3 = ex2_approx(acc[j][3] - mx1);
+      sum0 += p0 + p1;
+      sum1 += p2 + p3;
+      pa[j >> 1][(j & 1) * 2 + 0] = Mma<T>::pack(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = Mma<T>::pack(p2, p3);
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    if (lse0 != nullptr && t == 0) {  // log2-sum-exp of the row's logits (key chunks of a long prompt are merged with it)
+      float* lrow = lse0 + static_cast<long long>(h) * L;
+      if (g < rows) lrow[g] = mx0 + log2f(sum0);
+      if (g + 8 < rows) lrow[g + 8] = mx1 + log2f(sum1);
+    }
+
+    __syncwarp();  // Q_h has been consumed by every lane: its columns may now be overwritten by O_h
+#pragma unroll
+    for (int c = 0; c < TL::NCH; ++c) {
+      float o[ND][4];
+      pv_tile<T, D>(o, pa, sV + (h * D + c * TL::DCH) * 2, lane);
+      unsigned char* orow0 = qsm + g * PITCH + (h * D + c * TL::DCH + 2 * t) * 2;
+      unsigned char* orow1 = orow0 + 8 * PITCH;
+#pragma unroll
+      for (int n = 0; n < ND; ++n) {
+        *reinterpret_cast<uint32_t*>(orow0 + n * 16) = Mma<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
+        *reinterpret_cast<uint32_t*>(orow1 + n * 16) = Mma<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
+      }
+    }
+  }
+}
+
 // =============================================================================================
 // pass 2
 // =============================================================================================
@@ -606,73 +693,9 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
         beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2e;
         have_beta = true;
       }
-      // beta*W in the accumulator layout, shared by all heads of the group; columns >= S get -inf
-      float bw[10][4];
-#pragma unroll
-      for (int j = 0; j < 10; ++j) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int col = 8 * j + 2 * t + (i & 1);
-          const int row = g + 8 * (i >> 1);
-          bw[j][i] = (col < p.S) ? wsm[row * wp + col] * beta_l2 : -INFINITY;
-        }
-      }
-
-      for (int h = 0; h < sg.nheads; ++h) {
-        float acc[10][4];
-        qk_tile<T, D>(acc, sQ + h * D * 2, sK + h * D * 2, lane);
-        // logits (log2 domain), row max
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 10; ++j) {
-          acc[j][0] = fmaf(acc[j][0], scale_l2, bw[j][0]);
-          acc[j][1] = fmaf(acc[j][1], scale_l2, bw[j][1]);
-          acc[j][2] = fmaf(acc[j][2], scale_l2, bw[j][2]);
-          acc[j][3] = fmaf(acc[j][3], scale_l2, bw[j][3]);
-          mx0 = fmaxf(mx0, fmaxf(acc[j][0], acc[j][1]));
-          mx1 = fmaxf(mx1, fmaxf(acc[j][2], acc[j][3]));
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        // p = 2^(s - max), row sums, pack to the input dtype as the A operand of PV
-        float sum0 = 0.f, sum1 = 0.f;
-        uint32_t pa[5][4];
-#pragma unroll
-        for (int j = 0; j < 10; ++j) {
-          const float p0 = ex2_approx(acc[j][0] - mx0), p1 = ex2_approx(acc[j][1] - mx0);
-          const float p2 = ex2_approx(acc[j][2] - mx1), p3 = ex2_approx(acc[j][3] - mx1);
-          sum0 += p0 + p1;
-          sum1 += p2 + p3;
-          pa[j >> 1][(j & 1) * 2 + 0] = Mma<T>::pack(p0, p1);
-          pa[j >> 1][(j & 1) * 2 + 1] = Mma<T>::pack(p2, p3);
-        }
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-        const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
-        if (p.lse != nullptr && t == 0) {  // log2-sum-exp of the row's logits (key chunks of a long prompt are merged with it)
-          float* lrow = p.lse + (static_cast<long long>(sg.b) * p.H + sg.hg * TL::G + h) * p.L + l0;
-          if (g < rows) lrow[g] = mx0 + log2f(sum0);
-          if (g + 8 < rows) lrow[g + 8] = mx1 + log2f(sum1);
-        }
-
-        __syncwarp();  // Q_h has been consumed by every lane: its columns may now be overwritten by O_h
-#pragma unroll
-        for (int c = 0; c < TL::NCH; ++c) {
-          float o[ND][4];
-          pv_tile<T, D>(o, pa, sV + (h * D + c * TL::DCH) * 2, lane);
-          unsigned char* orow0 = qsm + g * PITCH + (h * D + c * TL::DCH + 2 * t) * 2;
-          unsigned char* orow1 = orow0 + 8 * PITCH;
-#pragma unroll
-          for (int n = 0; n < ND; ++n) {
-            *reinterpret_cast<uint32_t*>(orow0 + n * 16) = Mma<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
-            *reinterpret_cast<uint32_t*>(orow1 + n * 16) = Mma<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
-          }
-        }
-      }
+      softmax_pv_slice<T, D>(sg.nheads, p.S, beta_l2, scale_l2, sQ, sK, sV, wsm, wp, qsm,
+                             p.lse ? p.lse + (static_cast<long long>(sg.b) * p.H + sg.hg * TL::G) * p.L + l0 : nullptr, p.L, rows,
+                             lane);
 
       // O slice: shared -> global through the TMA, one row per lane
       fence_proxy_async();
@@ -690,6 +713,130 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
     idx = sg.end;
   }
   bulk_wait0();  // global writes of this thread's bulk stores are complete before the CTA retires
+}
+
+// =============================================================================================
+// both passes in ONE launch for problems that fit on chip (small layers, small batches)
+//
+// When every CTA can keep its share of Q resident in shared memory -- at most one 16-row slice per warp next to the K and
+// V of its (batch, head group): the footprint of the pass-2 kernel -- the two passes need not be two launches with Q
+// read twice: each warp loads its slice once, forms its scores for the statistics, the CTAs meet at a grid barrier
+// (cooperative launch; the barrier IS the deterministic fold of the per-CTA partials: the last arriver publishes the
+// std and bumps an epoch word), and the same warp then redoes Q K^T from shared memory for the softmax and P V.
+// One launch floor instead of two and Q read once.  CTAs per (batch, head-group) segment: p.fused_cps.
+template <typename T, int D>
+__global__ void __launch_bounds__(256, 1)
+xattn_fused_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_w) {
+  using TL = Tile<D>;
+  constexpr int PITCH = TL::PITCH;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ unsigned int s_epoch0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sK = smem_u32(smem);
+  const uint32_t sV = sK + TL::KV_BYTES;
+  const uint32_t sQ = sV + TL::KV_BYTES + warp * (TL::QS_BYTES + TL::WS_BYTES);
+  const uint32_t sW = sQ + TL::QS_BYTES;
+  const float* wsm = reinterpret_cast<const float*>(smem + 2 * TL::KV_BYTES + warp * (TL::QS_BYTES + TL::WS_BYTES) +
+                                                     TL::QS_BYTES);
+  unsigned char* qsm = smem + 2 * TL::KV_BYTES + warp * (TL::QS_BYTES + TL::WS_BYTES);
+  const uint32_t bars = sK + 2 * TL::KV_BYTES + TL::WARPS * (TL::QS_BYTES + TL::WS_BYTES);
+  const uint32_t kvbar = bars;
+  const uint32_t qbar = bars + 8 + warp * 8;
+  volatile unsigned int* epoch = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<unsigned char*>(p.ws) + kEpochOffset);
+  if (tid == 0) {
+    s_epoch0 = *epoch;  // read before this CTA arrives: the bump cannot have happened yet
+    mbar_init(kvbar, 1);
+    for (int w = 0; w < TL::WARPS; ++w) mbar_init(bars + 8 + w * 8, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  // this CTA: segment (batch, head group) and a run of <= 8 slices, one per warp
+  const int seg = blockIdx.x / p.fused_cps, part = blockIdx.x % p.fused_cps;
+  const int b = seg / p.n_hg, hg = seg % p.n_hg;
+  const int nheads = min(TL::G, p.H - hg * TL::G);
+  const int spc = (p.n_sl + p.fused_cps - 1) / p.fused_cps;
+  const int sl = part * spc + warp;
+  const bool have_slice = warp < spc && sl < p.n_sl;
+  const int l0 = sl * TL::ROWS;
+  const int rows = have_slice ? min(TL::ROWS, p.L - l0) : 0;
+  const int w_rep = p.B / p.Bw;
+  const bool w_tmap = (p.flags & 1u) != 0;
+  const int wp = w_tmap ? TL::KV_ROWS : p.w_pitch;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(kvbar, 2 * TL::KV_BYTES);  // two 80-row boxes; keys >= S arrive as zeros
+    const uint64_t pol_kv = policy_evict_last();
+    tma_box_load(sK, &tm_k, hg * (TL::GW / 2), 0, b, kvbar, pol_kv);
+    tma_box_load(sV, &tm_v, hg * (TL::GW / 2), 0, b, kvbar, pol_kv);
+  }
+  if (have_slice) {
+    const uint64_t pol_stream = policy_evict_first();
+    const float* wsrc = p.W + (static_cast<long long>(b / w_rep) * p.L + l0) * p.w_pitch;
+    const uint32_t wbytes = rows * p.w_pitch * 4;
+    const bool w_bulk = ((reinterpret_cast<uintptr_t>(wsrc) | wbytes) & 15) == 0;
+    if (lane == 0) {
+      mbar_arrive_expect_tx(qbar, TL::QS_BYTES + (w_tmap ? TL::WS_BYTES : w_bulk ? wbytes : 0));
+      tma_box_load(sQ, &tm_q, hg * (TL::GW / 2), l0, b, qbar, pol_stream);  // rows >= L arrive as zeros
+      if (w_tmap) tma_box_load(sW, &tm_w, 0, l0, b / w_rep, qbar, pol_stream);
+    }
+    if (!w_tmap) {
+      if (w_bulk) {
+        if (lane == 16) bulk_g2s_hint(sW, wsrc, wbytes, qbar, pol_stream);
+      } else {
+        float* wdst = const_cast<float*>(wsm);
+        for (int i = lane; i < rows * p.w_pitch; i += 32) wdst[i] = __ldg(wsrc + i);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- pass 1 on the resident slice
+  double dsum = 0.0, dsq = 0.0;
+  if (have_slice) {
+    mbar_wait(qbar, 0);
+    mbar_wait(kvbar, 0);
+    for (int h = 0; h < nheads; ++h) {
+      float acc[10][4];
+      qk_tile<T, D>(acc, sQ + h * D * 2, sK + h * D * 2, lane);
+      float fs = 0.f, fq = 0.f;  // rows >= L and keys >= S were zero-filled by the TMA: they add exact zeros
+#pragma unroll
+      for (int j = 0; j < 10; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          fs += acc[j][i];
+          fq = fmaf(acc[j][i], acc[j][i], fq);
+        }
+      dsum += static_cast<double>(fs);
+      dsq += static_cast<double>(fq);
+    }
+  }
+  publish_stats<TL::WARPS>(p, dsum, dsq, true);
+
+  // ---- grid barrier: wait until the last CTA has published the std
+  if (tid == 0) {
+    unsigned int spins = 0;
+    while (*epoch == s_epoch0 && ++spins < (1u << 24)) __nanosleep(40);  // bounded: a launch that is not co-resident must not hang
+    __threadfence();
+  }
+  __syncthreads();
+
+  // ---- pass 2 from shared memory
+  if (have_slice) {
+    const float sigma = p.sigma_dev ? __ldcg(p.sigma_dev) : p.sigma_host;
+    const float beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2e;
+    softmax_pv_slice<T, D>(nheads, p.S, beta_l2, p.scale * kLog2e, sQ, sK, sV, wsm, wp, qsm, nullptr, p.L, rows, lane);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane < rows) {
+      T* out = reinterpret_cast<T*>(p.out);
+      bulk_s2g(out + b * p.o_sb + static_cast<long long>(l0 + lane) * p.o_sl + hg * TL::GW, sQ + lane * PITCH, nheads * D * 2);
+      bulk_commit();
+      bulk_wait0();
+    }
+  }
 }
 
 // =============================================================================================
@@ -726,6 +873,22 @@ static bool make_map32(CUtensorMap* m, const void* base, int cols, int rows, int
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// fp32 [Bw, L, pitch] region map -> boxes of 80 columns x 16 rows, when the rows are 16-byte aligned (sets *flags |= 1)
+static bool make_map_w16(CUtensorMap* m, const XattnParams& p, int box_cols, int box_rows, unsigned* flags) {
+  if (p.w_pitch % 4 != 0 || (reinterpret_cast<uintptr_t>(p.W) & 15) != 0) return true;  // not eligible: plain copies
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.w_pitch), static_cast<cuuint64_t>(p.L), static_cast<cuuint64_t>(p.Bw)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(p.w_pitch) * 4, static_cast<cuuint64_t>(p.L) * p.w_pitch * 4};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.W), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  *flags |= 1u;
+  return true;
 }
 
 template <typename T, int D>
@@ -773,6 +936,59 @@ static cudaError_t launch_gram_stats(const XattnParams& p_in, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// slices per CTA <= 8 (one per warp) with whole CTAs per (batch, head-group) segment, all CTAs co-resident
+bool fused_plan(int B, int H, int L, int D, int S, int* cps_out) {
+  if (S > 80 || heads_per_group(D) == 0) return false;
+  const int G = heads_per_group(D);
+  const long long n_seg = static_cast<long long>(B) * ((H + G - 1) / G);
+  const int sms = sm_count_cached();
+  if (n_seg > sms) return false;
+  const int n_sl = (L + 15) / 16;
+  int cps = static_cast<int>(sms / n_seg);
+  if (cps > n_sl) cps = n_sl;
+  const int spc = (n_sl + cps - 1) / cps;  // slices per CTA with every SM in use
+  if (spc > 8) return false;
+  cps = (n_sl + spc - 1) / spc;            // fewest CTAs with that many slices each: a shorter barrier
+  if (cps_out) *cps_out = cps;
+  return true;
+}
+
+template <typename T, int D>
+static cudaError_t launch_fused(const XattnParams& p_in, cudaStream_t st) {
+  using TL = Tile<D>;
+  XattnParams p = p_in;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_fused_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TL::FWD_SMEM);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  int cps = 0;
+  if (!fused_plan(p.B, p.H, p.L, D, p.S, &cps)) return cudaErrorInvalidValue;
+  p.fused_cps = cps;
+  CUtensorMap tm_q, tm_k, tm_v;
+  if (!make_map32(&tm_q, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, TL::PITCH / 4, TL::ROWS) ||
+      !make_map32(&tm_k, p.k, p.H * D, p.S, p.B, p.k_ss, p.k_sb, TL::PITCH / 4, TL::KV_ROWS) ||
+      !make_map32(&tm_v, p.v, p.H * D, p.S, p.B, p.v_ss, p.v_sb, TL::PITCH / 4, TL::KV_ROWS))
+    return cudaErrorInvalidValue;
+  CUtensorMap tm_w = tm_q;
+  p.flags = 0;
+  if (!make_map_w16(&tm_w, p, TL::KV_ROWS, TL::ROWS, &p.flags)) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.B * p.n_hg * cps);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = TL::FWD_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // the grid barrier needs every CTA resident
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, xattn_fused_kernel<T, D>, p, tm_q, tm_k, tm_v, tm_w);
+}
+
 template <typename T, int D>
 static cudaError_t launch_forward(const XattnParams& p_in, cudaStream_t st) {
   XattnParams p = p_in;
@@ -793,19 +1009,7 @@ static cudaError_t launch_forward(const XattnParams& p_in, cudaStream_t st) {
     return cudaErrorInvalidValue;
   CUtensorMap tm_w = tm_q;
   p.flags = 0;
-  if (p.w_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0) {  // fp32 [Bw, L, pitch] -> boxes of 80 x 16
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return cudaErrorInvalidValue;
-    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.w_pitch), static_cast<cuuint64_t>(p.L), static_cast<cuuint64_t>(p.Bw)};
-    cuuint64_t gstr[2] = {static_cast<cuuint64_t>(p.w_pitch) * 4, static_cast<cuuint64_t>(p.L) * p.w_pitch * 4};
-    cuuint32_t box[3] = {static_cast<cuuint32_t>(TL::KV_ROWS), static_cast<cuuint32_t>(TL::ROWS), 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    if (enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.W), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return cudaErrorInvalidValue;
-    p.flags = 1;
-  }
+  if (!make_map_w16(&tm_w, p, TL::KV_ROWS, TL::ROWS, &p.flags)) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid_for(p.total));
   cfg.blockDim = dim3(256);
@@ -856,6 +1060,14 @@ bool gram_supports(int D, int S) { return D == 40 && S <= Tile<40>::KV_ROWS; }
 cudaError_t run_stats_gram(const XattnParams& p, int D, int dtype, cudaStream_t st) {
   if (!gram_supports(D, p.S)) return cudaErrorInvalidValue;
   return dtype == 0 ? launch_gram_stats<__half, 40>(p, st) : launch_gram_stats<__nv_bfloat16, 40>(p, st);
+}
+
+cudaError_t run_fused(const XattnParams& p, int D, int dtype, cudaStream_t st) {
+  if (dtype == 0) {
+    DSC_DISPATCH_D(launch_fused, __half)
+  } else {
+    DSC_DISPATCH_D(launch_fused, __nv_bfloat16)
+  }
 }
 
 cudaError_t run_forward(const XattnParams& p, int D, int dtype, cudaStream_t st) {

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSC_VERSION 102 /* major*10000 + minor*100 + patch */
+#define DSC_VERSION 103 /* major*10000 + minor*100 + patch */
 
 #define DSC_DTYPE_F16 0
 #define DSC_DTYPE_BF16 1
@@ -91,6 +91,21 @@ int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t
                       int w_pitch, const float* sigma_dev_or_null, float sigma_host, const void* workspace, void* out,
                       const int64_t o_str[3] /*HOST*/, int B, int H, int L, int D, int S, float scale, int dtype,
                       void* stream);
+
+/* One whole attention call: out = softmax(scale Q K^T + sigma * std(scale Q K^T) * W) V, i.e. dsc_xattn_stats followed
+ * by dsc_xattn_forward with the same arguments -- and, when every CTA's share of Q fits in shared memory (the small
+ * layers, small batches), ONE cooperative launch that reads Q once and keeps it on chip between the two passes.  This is
+ * what the processor calls (replaces attention_modify.py:90-103 including the weight_func of app.py:1004).  The
+ * statistics are left in the workspace exactly as by dsc_xattn_stats. */
+int dsc_xattn_call(const void* q, const void* k, const void* v, const int64_t q_str[4] /*HOST*/,
+                   const int64_t k_str[4] /*HOST*/, const int64_t v_str[4] /*HOST*/, const float* W, int Bw, int w_pitch,
+                   const float* sigma_dev_or_null, float sigma_host, void* workspace, void* out,
+                   const int64_t o_str[3] /*HOST*/, int B, int H, int L, int D, int S, float scale, int dtype,
+                   void* stream);
+
+/* Number of kernel launches dsc_xattn_call will issue for this shape on the current device: 1 (fused), 2 (pass 1 +
+ * pass 2) or 2 * chunks + 1 (long prompts); -1 for an unsupported shape.  Introspection only. */
+int dsc_xattn_call_launches(int B, int H, int L, int D, int S);
 
 /* Layout of the head of the workspace (read-only for callers). */
 typedef struct dsc_xattn_stats_t {
