@@ -115,6 +115,11 @@ class RegionAttnProcessor:
         region_prompt=None,
         ip_adapter_masks=None,
     ) -> torch.Tensor:
+        return self._forward(attn, hidden_states, encoder_hidden_states, attention_mask, temb, region_prompt)
+
+    def _forward(self, attn, hidden_states, encoder_hidden_states, attention_mask, temb, region_prompt, ip_branch=None):
+        """The processor body (reference attention_modify.py:425-503).  ``ip_branch(hidden, query, batch, head_dim)``,
+        when given, adds the IP-Adapter image-prompt terms before the output projection (:640-682)."""
         residual = hidden_states
         img_sequence_length = hidden_states.shape[1]
         if getattr(attn, "spatial_norm", None) is not None:
@@ -181,6 +186,8 @@ class RegionAttnProcessor:
 
         hidden_states = hidden_states.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim)
         hidden_states = hidden_states.to(query.dtype)
+        if ip_branch is not None:
+            hidden_states = ip_branch(hidden_states, query, batch_size, head_dim)
 
         hidden_states = attn.to_out[0](hidden_states, *args)
         hidden_states = attn.to_out[1](hidden_states)
@@ -199,3 +206,90 @@ class RegionAttnProcessorBaddbmm(RegionAttnProcessor):
     (source/app.py:479-481).  Its region branch (:164-175 via ``get_attention_scores`` :39-70) computes exactly the
     same scores, std, bias, softmax and PV as the SDPA-style function (bit-identical on CPU fp32), so
     the same two CUDA passes serve it; the class exists so either reference processor can be swapped by name."""
+
+
+def ip_mask_downsample(mask: torch.Tensor, batch_size: int, num_queries: int, value_embed_dim: int) -> torch.Tensor:
+    """Restatement of ``diffusers.image_processor.IPAdapterMaskProcessor.downsample`` (diffusers==0.27.2, third party,
+    not vendored by the reference; called at attention_modify.py:671-673): bicubic resize of the [1, H, W] mask to the
+    layer's latent grid (aspect ratio kept), flattened, repeated over the batch and the value channels."""
+    import math
+
+    o_h, o_w = mask.shape[1], mask.shape[2]
+    ratio = o_w / o_h
+    mask_h = int(math.sqrt(num_queries / ratio))
+    mask_h = int(mask_h) + int((num_queries % int(mask_h)) != 0)
+    mask_w = num_queries // mask_h
+    m = F.interpolate(mask.unsqueeze(0), size=(mask_h, mask_w), mode="bicubic").squeeze(0)
+    if m.shape[0] < batch_size:
+        m = m.repeat(batch_size, 1, 1)
+    m = m.view(m.shape[0], -1)
+    area = mask_h * mask_w
+    if area < num_queries:  # aspect ratios that do not tile the grid exactly: pad with zeros / truncate, as upstream
+        m = F.pad(m, (0, num_queries - m.shape[1]), value=0.0)
+    if area > num_queries:
+        m = m[:, :num_queries]
+    return m.view(m.shape[0], m.shape[1], 1).repeat(1, 1, value_embed_dim)
+
+
+class RegionIPAdapterAttnProcessor(torch.nn.Module):
+    """Drop-in for the reference's ``IPAdapterAttnProcessor2_0`` (source/modules/attention_modify.py:506-700; installed
+    by source/modules/ip_adapter.py:292): the text branch is the region-masked cross-attention of ``RegionAttnProcessor``
+    (same CUDA path), each image-prompt branch is a plain attention of the same queries over the adapter's
+    ``to_k_ip`` / ``to_v_ip`` projections, optionally gated by a spatial mask, added with its scale (:640-682).
+    Same constructor, parameter names (state dicts load unchanged) and call signature."""
+
+    def __init__(self, hidden_size, cross_attention_dim=None, num_tokens=(4,), scale=1.0, cache_kv: bool = False):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.cross_attention_dim = cross_attention_dim
+        if not isinstance(num_tokens, (tuple, list)):
+            num_tokens = [num_tokens]
+        self.num_tokens = num_tokens
+        if not isinstance(scale, list):
+            scale = [scale] * len(num_tokens)
+        if len(scale) != len(num_tokens):
+            raise ValueError("`scale` should be a list of integers with the same length as `num_tokens`.")
+        self.scale = scale
+        self.to_k_ip = torch.nn.ModuleList(
+            [torch.nn.Linear(cross_attention_dim, hidden_size, bias=False) for _ in range(len(num_tokens))])
+        self.to_v_ip = torch.nn.ModuleList(
+            [torch.nn.Linear(cross_attention_dim, hidden_size, bias=False) for _ in range(len(num_tokens))])
+        self._core = RegionAttnProcessor(cache_kv=cache_kv)
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+                 region_prompt=None, ip_adapter_masks=None):
+        ip_hidden_states = None
+        if encoder_hidden_states is not None:
+            if isinstance(encoder_hidden_states, tuple):
+                encoder_hidden_states, ip_hidden_states = encoder_hidden_states
+            else:  # deprecated single-tensor form (:575-585): the last num_tokens[0] rows are the image tokens
+                end_pos = encoder_hidden_states.shape[1] - self.num_tokens[0]
+                encoder_hidden_states, ip_hidden_states = (
+                    encoder_hidden_states[:, :end_pos, :], [encoder_hidden_states[:, end_pos:, :]])
+        if ip_hidden_states is None:  # self-attention call: nothing to add
+            return self._core._forward(attn, hidden_states, encoder_hidden_states, attention_mask, temb, region_prompt)
+
+        if ip_adapter_masks is not None:
+            if not isinstance(ip_adapter_masks, torch.Tensor) or ip_adapter_masks.ndim != 4:
+                raise ValueError(" ip_adapter_mask should be a tensor with shape [num_ip_adapter, 1, height, width]."
+                                 " Please use `IPAdapterMaskProcessor` to preprocess your mask")
+            if len(ip_adapter_masks) != len(self.scale):
+                raise ValueError(f"Number of ip_adapter_masks ({len(ip_adapter_masks)}) must match number of IP-Adapters "
+                                 f"({len(self.scale)})")
+        else:
+            ip_adapter_masks = [None] * len(self.scale)
+
+        def ip_branch(hidden, query, batch_size, head_dim):
+            for cur, sc, to_k_ip, to_v_ip, mask in zip(ip_hidden_states, self.scale, self.to_k_ip, self.to_v_ip,
+                                                       ip_adapter_masks):
+                ip_key = to_k_ip(cur).view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+                ip_value = to_v_ip(cur).view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+                cur = F.scaled_dot_product_attention(query, ip_key, ip_value, attn_mask=None, dropout_p=0.0, is_causal=False)
+                cur = cur.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
+                if mask is not None:
+                    m = ip_mask_downsample(mask, batch_size, cur.shape[1], cur.shape[2])
+                    cur = cur * m.to(dtype=query.dtype, device=query.device)
+                hidden = hidden + sc * cur
+            return hidden
+
+        return self._core._forward(attn, hidden_states, encoder_hidden_states, attention_mask, temb, region_prompt, ip_branch)

@@ -62,7 +62,7 @@ def score_std(query: torch.Tensor, key: torch.Tensor, scale: Optional[float] = N
     return (query @ key.transpose(-2, -1) * scale_factor).std()
 
 
-def processor_forward(attn, hidden_states, encoder_hidden_states=None, region_prompt=None):
+def processor_forward(attn, hidden_states, encoder_hidden_states=None, region_prompt=None, ip_branch=None):
     """attention_modify.py:414-503 for the SD-1.5 case (3-D input, no mask, no norms).
 
     ``attn`` is duck-typed: to_q/to_k/to_v/to_out, heads, residual_connection, rescale_output_factor.
@@ -85,6 +85,8 @@ def processor_forward(attn, hidden_states, encoder_hidden_states=None, region_pr
     else:
         out = F.scaled_dot_product_attention(query, key, value, dropout_p=0.0, is_causal=False)
     out = out.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
+    if ip_branch is not None:  # IP-Adapter image-prompt terms (attention_modify.py:640-682), see oracle/ip_adapter.py
+        out = ip_branch(out, query, batch_size, head_dim)
     out = attn.to_out[0](out)
     out = attn.to_out[1](out)
     if getattr(attn, "residual_connection", False):

@@ -328,3 +328,45 @@ def test_gram_identity_stats_kernel(monkeypatch, B, L, S):
     W = synthetic_w(B, L, S).cuda()
     out = dsc.region_attention(q, k, v, W, 8.0)
     assert rel_l2(out.float(), _oracle(q, k, v, W, 8.0)) <= TOL
+
+
+@pytest.mark.parametrize("n_adapters,with_masks", [(1, False), (2, True)])
+def test_ip_adapter_processor_matches_oracle(n_adapters, with_masks):
+    """Drop-in for the reference's IPAdapterAttnProcessor2_0 (attention_modify.py:506-700): region-masked text branch on
+    the CUDA path + image-prompt branches, against the oracle restatement (itself pinned to the reference class)."""
+    from diffusionspatialcontrol_b200 import RegionIPAdapterAttnProcessor
+    from oracle import ip_adapter as oip
+
+    torch.manual_seed(5)
+    C, D, L, B = 640, 80, 1024, 2
+    attn = _Attn(C, 8, D).cuda()
+    hs, ctx = torch.randn(B, L, C, device="cuda"), torch.randn(B, 77, 768, device="cuda")
+    ip = [torch.randn(B, 4 * (i + 1), 768, device="cuda") for i in range(n_adapters)]
+    tokens, scales = [t.shape[1] for t in ip], [0.7, 0.3][:n_adapters]
+    oracle = oip.OracleIPAdapterProcessor(C, 768, num_tokens=tokens, scale=scales).cuda()
+    ours = RegionIPAdapterAttnProcessor(C, 768, num_tokens=tokens, scale=scales).cuda().half()
+    ours.load_state_dict(oracle.state_dict())
+    masks = None
+    if with_masks:
+        masks = torch.zeros(n_adapters, 1, 64, 64, device="cuda")
+        masks[0, :, :, :32] = 1.0
+        masks[1, :, 20:, :] = 1.0
+    W = synthetic_w(B, L, 77)
+    rp = {"region_state": {L: W}, "sigma": torch.tensor(6.5), "weight_func": weight_func}
+    attn16 = _Attn(C, 8, D).cuda().half()
+    attn16.load_state_dict(attn.state_dict())
+    with torch.no_grad():
+        # fp16-representable inputs on both sides
+        hs16, ctx16, ip16 = hs.half(), ctx.half(), [t.half() for t in ip]
+        attn32 = _Attn(C, 8, D).cuda()
+        attn32.load_state_dict({k: v.float() for k, v in attn16.state_dict().items()})
+        oracle32 = oip.OracleIPAdapterProcessor(C, 768, num_tokens=tokens, scale=scales).cuda()
+        oracle32.load_state_dict({k: v.float() for k, v in ours.state_dict().items()})
+        torch.backends.cuda.matmul.allow_tf32 = False
+        want = oracle32(attn32, hs16.float(), encoder_hidden_states=(ctx16.float(), [t.float() for t in ip16]),
+                        region_prompt={**rp, "region_state": {L: W.cuda()}}, ip_adapter_masks=masks)
+        got = ours(attn16, hs16, encoder_hidden_states=(ctx16, ip16), region_prompt=rp,
+                   ip_adapter_masks=masks.half() if masks is not None else None)
+        plain = ours(attn16, hs16, encoder_hidden_states=(ctx16, [torch.zeros_like(t) for t in ip16]), region_prompt=rp)
+    assert rel_l2(got.float(), want) <= 4e-3
+    assert not torch.allclose(got, plain, atol=1e-3)  # the image prompt contributes
