@@ -205,7 +205,9 @@ static int forward_impl(const void* q, const void* k, const void* v, const int64
       p.n_total = static_cast<double>(B) * H * static_cast<double>(L) * S;
       p.fold_chunks = 1;
       e = run_fused(p, D, dtype, st);
-      return e == cudaSuccess ? DSC_OK : cuda_fail(e, who);
+      if (e != cudaErrorCooperativeLaunchTooLarge) return e == cudaSuccess ? DSC_OK : cuda_fail(e, who);
+      (void)cudaGetLastError();  // the device cannot hold the whole grid right now (e.g. shared with another context):
+      e = cudaSuccess;           // nothing was launched -- take the two-launch form below
     }
     rc = dsc_xattn_stats(q, k, q_str, k_str, nullptr, B, H, L, D, S, scale, dtype, const_cast<void*>(workspace), stream);
     if (rc) return rc;
