@@ -39,11 +39,13 @@ class RegionAttnProcessor:
     (numerically identical, the reference recomputes them on each of the 25 steps).
     """
 
-    def __init__(self, cache_kv: bool = False, max_cached_maps: int = 16):
+    def __init__(self, cache_kv: bool = False, max_cached_maps: int = 16, skip_zero_maps: bool = True):
         if not hasattr(F, "scaled_dot_product_attention"):
             raise ImportError("RegionAttnProcessor requires PyTorch 2.0")
         self.cache_kv = cache_kv
         self._w_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+        self._w_zero: dict = {}
+        self.skip_zero_maps = skip_zero_maps
         self._max_cached_maps = max_cached_maps
         self._checked_funcs: dict = {}
         self._sigma_cache: Optional[tuple] = None
@@ -57,10 +59,21 @@ class RegionAttnProcessor:
             self._w_cache.move_to_end(key)
             return hit[1]
         dev = padded_region_map(w.to(device=device, dtype=torch.float32, non_blocking=False))
+        # Regions switched off still reach this path with an all-zero map (reference encode_region_map_function.py:33-36,
+        # :74): beta * 0 adds nothing, so such a map is recognised ONCE here (one readback per map and
+        # generation, never inside a CUDA-graph capture) and its calls take plain SDPA -- no std pass at all.
+        zero = False
+        if self.skip_zero_maps and dev.is_cuda and not torch.cuda.is_current_stream_capturing():
+            zero = not bool(torch.count_nonzero(dev).item())
+        self._w_zero[key] = zero
         self._w_cache[key] = (w, dev)  # keeps `w` alive, so data_ptr cannot be recycled under the key
         while len(self._w_cache) > self._max_cached_maps:
-            self._w_cache.popitem(last=False)
+            old, _ = self._w_cache.popitem(last=False)
+            self._w_zero.pop(old, None)
         return dev
+
+    def _map_is_zero(self, w: torch.Tensor, device: torch.device) -> bool:
+        return self._w_zero.get((w.data_ptr(), w._version, tuple(w.shape), w.dtype, str(device)), False)
 
     def _check_weight_func(self, fn: Callable) -> None:
         ok = self._checked_funcs.get(id(fn))
@@ -100,6 +113,7 @@ class RegionAttnProcessor:
 
     def clear_caches(self) -> None:
         self._w_cache.clear()
+        self._w_zero.clear()
         self._kv_cache.clear()
         self._sigma_cache = None
 
@@ -172,13 +186,17 @@ class RegionAttnProcessor:
         if is_xattn and isinstance(region_state, dict):
             self._check_weight_func(weight_func)
             w = region_state[img_sequence_length]  # KeyError for an unknown resolution, like the reference (:481)
-            hidden_states = region_attention(
-                query, key, value,
-                self._device_map(w, query.device),
-                self._sigma_arg(sigma, query.device),
-                attn_mask=attention_mask,
-                scale=None,  # the reference always uses 1/sqrt(head_dim) here (:77), not attn.scale
-            )
+            w_dev = self._device_map(w, query.device)
+            if self._map_is_zero(w, query.device):
+                hidden_states = F.scaled_dot_product_attention(
+                    query, key, value, attn_mask=attention_mask, dropout_p=0.0, is_causal=False)
+            else:
+                hidden_states = region_attention(
+                    query, key, value, w_dev,
+                    self._sigma_arg(sigma, query.device),
+                    attn_mask=attention_mask,
+                    scale=None,  # the reference always uses 1/sqrt(head_dim) here (:77), not attn.scale
+                )
         else:
             hidden_states = F.scaled_dot_product_attention(
                 query, key, value, attn_mask=attention_mask, dropout_p=0.0, is_causal=False

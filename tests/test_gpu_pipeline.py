@@ -86,3 +86,30 @@ def test_device_resident_maps_are_not_reuploaded():
     assert proc._device_map(cpu, w.device) is a  # cached
     cpu[0, 0, 0] = 1.0  # in-place edit bumps _version: cache must not serve the stale copy
     assert proc._device_map(cpu, w.device)[0, 0, 0] == 1.0
+
+
+def test_all_zero_maps_take_plain_sdpa():
+    """Regions switched off still send a dict of all-zero maps down the region path: the processor
+    recognises such a map once, at upload, and its calls skip the std pass; the output is plain attention."""
+    from diffusionspatialcontrol_b200 import RegionAttnProcessor
+    from oracle import attention as oa
+
+    from .test_gpu_attention import _Attn
+
+    torch.manual_seed(2)
+    attn = _Attn(320, 8, 40).cuda().half()
+    hs, ctx = torch.randn(2, 256, 320, device="cuda").half(), torch.randn(2, 77, 768, device="cuda").half()
+    zero = torch.zeros(2, 256, 77)
+    rp = {"region_state": {256: zero}, "sigma": torch.tensor(9.0), "weight_func": oa.weight_func}
+    proc, always = RegionAttnProcessor(), RegionAttnProcessor(skip_zero_maps=False)
+    with torch.no_grad():
+        a = proc(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)
+        b = always(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)      # both CUDA passes, beta * 0
+        c = proc(attn, hs, encoder_hidden_states=ctx)                           # no region prompt at all
+    assert proc._map_is_zero(zero, hs.device) and not always._map_is_zero(zero, hs.device)
+    assert torch.equal(a, c)
+    assert torch.allclose(a.float(), b.float(), atol=2e-3, rtol=2e-3)
+    zero[0, 3, 1] = 0.5  # in-place edit: new version, no longer zero
+    with torch.no_grad():
+        d = proc(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)
+    assert not proc._map_is_zero(zero, hs.device) and not torch.equal(d, a)
