@@ -819,14 +819,16 @@ xattn_fused_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   if (tid == 0) {
     unsigned int spins = 0;
     while (*epoch == s_epoch0 && ++spins < (1u << 24)) __nanosleep(40);  // bounded: a launch that is not co-resident must not hang
+    s_epoch0 = (*epoch == s_epoch0) ? 1u : 0u;  // reused as "barrier timed out" flag
     __threadfence();
   }
   __syncthreads();
+  const bool timed_out = s_epoch0 != 0u;  // cannot happen under a cooperative launch; if it ever does, fail loudly (NaN output)
 
   // ---- pass 2 from shared memory
   if (have_slice) {
     const float sigma = p.sigma_dev ? __ldcg(p.sigma_dev) : p.sigma_host;
-    const float beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2e;
+    const float beta_l2 = timed_out ? __int_as_float(0x7fc00000) : sigma * __ldcg(&p.ws->std_unbiased) * kLog2e;
     softmax_pv_slice<T, D>(nheads, p.S, beta_l2, p.scale * kLog2e, sQ, sK, sV, wsm, wp, qsm, nullptr, p.L, rows, lane);
     fence_proxy_async();
     __syncwarp();
