@@ -20,6 +20,16 @@ __global__ void k(float* out, float s, long long* cyc) {
       if (MODE == 1) ffma2(x[i], x[i + 1], x[i], x[i + 1], s, s, 0.5f, 0.5f);
       if (MODE == 2) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i])); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i + 1])); }
       if (MODE == 3) { x[i] = fmaxf(fmaxf(x[i], x[i + 1]), s); x[i + 1] = fmaxf(fmaxf(x[i + 1], x[i]), -s); }
+      if (MODE == 4) {  // packed half exp2: one instruction for the pair
+        unsigned int h = __float_as_uint(x[i]);
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h));
+        x[i] = __uint_as_float(h);
+      }
+      if (MODE == 5) {  // bf16x2
+        unsigned int h = __float_as_uint(x[i]);
+        asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(h));
+        x[i] = __uint_as_float(h);
+      }
     }
   }
   long long t1 = clock64();
@@ -29,12 +39,13 @@ __global__ void k(float* out, float s, long long* cyc) {
 }
 int main() {
   float* out; long long* cyc; cudaMalloc(&out, 4 << 20); cudaMalloc(&cyc, 8);
-  const char* names[4] = {"FFMA (2 per pair)", "FFMA2 (1 per pair)", "MUFU.EX2 (2 per pair)", "FMNMX3-ish (2 per pair)"};
+  const char* names[6] = {"FFMA (2 per pair)", "FFMA2 (1 per pair)", "MUFU.EX2 (2 per pair)", "FMNMX3-ish (2 per pair)", "ex2.f16x2 (1 per pair)", "ex2.bf16x2 (1 per pair)"};
   for (int warps = 1; warps <= 8; warps *= 2) {  // warps per sub-partition (block = 4 SMSPs x warps)
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < 6; ++m) {
       long long h;
       if (m == 0) k<0><<<1, 128 * warps>>>(out, 1.0001f, cyc); if (m == 1) k<1><<<1, 128 * warps>>>(out, 1.0001f, cyc);
       if (m == 2) k<2><<<1, 128 * warps>>>(out, 1.0001f, cyc); if (m == 3) k<3><<<1, 128 * warps>>>(out, 1.0001f, cyc);
+      if (m == 4) k<4><<<1, 128 * warps>>>(out, 1.0001f, cyc); if (m == 5) k<5><<<1, 128 * warps>>>(out, 1.0001f, cyc);
       cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
       printf("{\"warps_per_smsp\": %d, \"op\": \"%s\", \"cycles_per_pair_per_warp\": %.3f, \"cycles_per_pair_per_smsp\": %.3f}\n", warps, names[m],
              (double)h / (ITER * 8), (double)h / (ITER * 8) / warps);
