@@ -3,7 +3,8 @@ duongve13112002/DiffusionSpatialControl), as a drop-in diffusers attention proce
 hand-written sm_100a CUDA behind a C ABI (libdsc_b200.so, include/dsc_b200.h)."""
 from .attention import padded_region_map, region_attention, score_stats  # noqa: F401
 from .attention_processor import (RegionAttnProcessor, RegionAttnProcessorBaddbmm,  # noqa: F401
-                                  RegionIPAdapterAttnProcessor, ip_mask_downsample)
+                                  RegionIPAdapterAttnProcessor, RegionIPAdapterAttnProcessorBaddbmm,
+                                  ip_mask_downsample)
 from .region_map import encode_region_map, encode_region_map_sp  # noqa: F401
 
 __all__ = ["RegionAttnProcessor", "RegionAttnProcessorBaddbmm", "region_attention", "score_stats", "encode_region_map", "encode_region_map_sp"]

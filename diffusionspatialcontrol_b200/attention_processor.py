@@ -311,3 +311,11 @@ class RegionIPAdapterAttnProcessor(torch.nn.Module):
             return hidden
 
         return self._core._forward(attn, hidden_states, encoder_hidden_states, attention_mask, temb, region_prompt, ip_branch)
+
+
+class RegionIPAdapterAttnProcessorBaddbmm(RegionIPAdapterAttnProcessor):
+    """Drop-in for the reference's ``IPAdapterAttnProcessor`` (source/modules/attention_modify.py:210-411), the
+    ``torch.baddbmm`` twin of ``IPAdapterAttnProcessor2_0`` used when ``F.scaled_dot_product_attention`` is missing
+    (source/modules/ip_adapter.py:292).  Same scores, std, bias, softmax and P V in the text branch and the same
+    image-prompt terms, so the same CUDA path serves it; the class exists so either reference class can be swapped
+    by name."""
