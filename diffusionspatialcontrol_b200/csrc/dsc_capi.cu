@@ -155,6 +155,22 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_stats");
 }
 
+// Which form dsc_xattn_call takes: 0 = two launches, 1 = single launch with Q resident in shared memory (mma.sync family,
+// small problems), 2 = single launch, two phases over the tile list (tcgen05 family, D = 40 / 80).
+static int call_form(int B, int H, int L, int D, int S) {
+  const char* nf = getenv("DSC_NO_FUSED");
+  if (n_chunks(S) > 1 || (nf && nf[0] == '1')) return 0;
+  const char* impl = getenv("DSC_XATTN_IMPL");
+  const bool want_mma = impl && strcmp(impl, "mma") == 0, want_tc5 = impl && strcmp(impl, "tc5") == 0;
+  if (!want_tc5 && fused_plan(B, H, L, D, S, nullptr)) return 1;
+  // Form 2 is opt-in (DSC_TC5_FUSED=1): measured on B200 it only ties the two-launch form at D = 40 (62.3 vs 62.5 us --
+  // programmatic dependent launch already hides pass 2's prologue behind the tail of pass 1) and loses at D = 80
+  // (45 vs 42 us, where pass 1 is faster on the mma.sync kernel).
+  const char* tf = getenv("DSC_TC5_FUSED");
+  if (!want_mma && tf && tf[0] == '1' && tc5_fused_supports(D)) return 2;
+  return 0;
+}
+
 static int forward_impl(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],
                         const int64_t v_str[4], const float* W, int Bw, int w_pitch, const float* sigma_dev_or_null,
                         float sigma_host, const void* workspace, void* out, const int64_t o_str[3], int B, int H, int L, int D,
@@ -201,10 +217,11 @@ static int forward_impl(const void* q, const void* k, const void* v, const int64
   cudaError_t e = cudaSuccess;
   if (with_stats) {
     // one attention call: a single cooperative launch when the problem fits on chip, else pass 1 then pass 2
-    if (dsc_xattn_call_launches(B, H, L, D, S) == 1) {
+    const int form = call_form(B, H, L, D, S);
+    if (form != 0) {
       p.n_total = static_cast<double>(B) * H * static_cast<double>(L) * S;
       p.fold_chunks = 1;
-      e = run_fused(p, D, dtype, st);
+      e = form == 1 ? run_fused(p, D, dtype, st) : run_fused_tc5(p, D, dtype, st);
       if (e != cudaErrorCooperativeLaunchTooLarge) return e == cudaSuccess ? DSC_OK : cuda_fail(e, who);
       (void)cudaGetLastError();  // the device cannot hold the whole grid right now (e.g. shared with another context):
       e = cudaSuccess;           // nothing was launched -- take the two-launch form below
@@ -242,10 +259,7 @@ int dsc_xattn_call_launches(int B, int H, int L, int D, int S) {
   if (B <= 0 || H <= 0 || L <= 0 || S <= 0 || heads_per_group(D) == 0 || S > DSC_MAX_KEYS_TOTAL) return -1;
   const int C = n_chunks(S);
   if (C > 1) return 2 * C + 1;
-  const char* nf = getenv("DSC_NO_FUSED");
-  const char* impl = getenv("DSC_XATTN_IMPL");
-  const bool fused_ok = !(nf && nf[0] == '1') && !(impl && strcmp(impl, "tc5") == 0) && fused_plan(B, H, L, D, S, nullptr);
-  return fused_ok ? 1 : 2;
+  return call_form(B, H, L, D, S) != 0 ? 1 : 2;
 }
 
 int dsc_xattn_forward(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],

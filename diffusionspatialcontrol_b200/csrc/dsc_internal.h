@@ -62,6 +62,8 @@ cudaError_t run_merge_chunks(const void* chunk_out, const float* lse, int n_chun
 bool tc5_supports(int D);
 cudaError_t run_stats_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st);
 cudaError_t run_forward_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st);
+bool tc5_fused_supports(int D);  // both passes in one cooperative launch
+cudaError_t run_fused_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st);
 
 cudaError_t run_region_downsample(const uint8_t* maps, int R, int Hpx, int Wpx, int w_r, int h_r, uint8_t* ds,
                                   uint32_t* any_set, cudaStream_t st);

@@ -595,10 +595,8 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_w) {
   using TL = Tile<D>;
   constexpr int PITCH = TL::PITCH;
-  constexpr int ND = TL::ND;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
   const uint32_t sK = smem_u32(smem);
   const uint32_t sV = sK + TL::KV_BYTES;
   const uint32_t sQ = sV + TL::KV_BYTES + warp * (TL::QS_BYTES + TL::WS_BYTES);

@@ -822,6 +822,7 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
 #ifndef DSC_POLY_PATTERN
 #define DSC_POLY_PATTERN 0x00  // bit i: key pairs with (pair & 7) == i take the polynomial 2^x below (0 = all on MUFU)
 #endif
+constexpr int kEpochOffsetT = 48;  // epoch word of the single-launch grid barrier, behind the public workspace header
 constexpr int kX4Consumers = 512;
 constexpr int kX4Threads = 640;
 // 640 threads -> 96 registers per thread from __launch_bounds__; the consumer path fits, so no setmaxnreg here (a
@@ -888,10 +889,12 @@ __device__ __forceinline__ void stage_vt40(unsigned char* sVt, const XattnParams
   fence_proxy_async();
 }
 
-template <typename T, int D, bool STATS>
-__global__ void __launch_bounds__(kX4Threads, 1)
-xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_o,
-                   const __grid_constant__ CUtensorMap tm_w) {
+// One pass (STATS: pass 1, else pass 2) as a device function, so that it can be a kernel of its own (MODE 0) or one of the
+// two phases of the single-launch kernel below (MODE 1: pass 1 followed by a grid barrier, keeps the TMEM allocation and
+// returns its base; MODE 2: pass 2 on that allocation, no programmatic-dependent-launch handshake).
+template <typename T, int D, bool STATS, int MODE>
+__device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_o,
+                                             const CUtensorMap& tm_w, uint32_t tmem_in, unsigned int epoch0 = 0u) {
   using C = TC<D>;
   using X = X4<D>;
   constexpr int HPT = X::HPT, PAR = X::PAR, NH = X::NH;
@@ -911,7 +914,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   const bool w_fast = !STATS && (p.flags & 4u) != 0;
   TRACE(1);
   CTA_TIME(0);
-  if constexpr (STATS) pdl_launch_dependents();  // let pass 2 start its prologue on SMs as they free up
+  if constexpr (STATS && MODE == 0) pdl_launch_dependents();  // let pass 2 start its prologue on SMs as they free up
   {  // first thing: start pulling this CTA's first K / V head group into L2
     const int begin0 = static_cast<int>(p.total * blockIdx.x / gridDim.x);
     if (tid < kX4Consumers && begin0 < p.total) prefetch_kv<T, D, STATS, kX4Consumers>(p, decode<D>(begin0, p), tid);
@@ -923,6 +926,8 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   // barrier map (8 B each): full[NST] | odone[NST] | qrdy[4] | srdy[4] | prdy[4] | ordy[4] ; tmem ptr after
   const uint32_t b_full = bars, b_odone = bars + 8 * NST, b_qrdy = bars + 16 * NST, b_srdy = b_qrdy + 32,
                  b_prdy = b_qrdy + 64, b_ordy = b_qrdy + 96;
+  const uint32_t b_beta = b_qrdy + 128;  // single-launch form: "the std of this call has been published" (grid barrier)
+  static_assert(16 * C::FWD_STAGES + 128 + 8 <= 240 && 16 * C::STATS_STAGES + 128 + 8 <= 240, "barrier area");
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV_BYTES + NST * STAGE_BYTES + 240);
 
   for (int i = tid; i < KV_BYTES / 16; i += kX4Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -963,6 +968,7 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
       mbar_init(b_full + 8 * s, 1);
       mbar_init(b_odone + 8 * s, warp_arrive ? STAGE_CONSUMERS / 32 : STAGE_CONSUMERS);
     }
+    if constexpr (MODE == 2) mbar_init(b_beta, 1);
     fence_mbar_init();
     for (int i = 0; i < min(NST, n_items); ++i) load_tile(i);
   }
@@ -975,24 +981,39 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
     }
     fence_mbar_init();
   }
-  if (warp == 16) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
-                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (MODE != 2) {
+    if (warp == 16) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                       smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   TRACE(52);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = MODE == 2 ? tmem_in : *tmem_ptr_smem;
   TRACE(2);
 
   if (warp >= 16) {
     const int wsvc = __shfl_sync(0xffffffffu, warp, 0) - 16;  // warp-uniform
     if (tid == kProducerTid) {
       // ============================== producer: TMA loads and stores ===============================
+      if constexpr (MODE == 2) {
+        // grid barrier of the single-launch form, waited for by ONE thread per CTA while everybody else already stages
+        // K / V^T, Q rows and the first Q K^T of pass 2: the last CTA to publish its pass-1 partial bumps the epoch word
+        volatile unsigned int* epoch =
+            reinterpret_cast<volatile unsigned int*>(reinterpret_cast<unsigned char*>(p.ws) + kEpochOffsetT);
+        unsigned int spins = 0;
+        while (*epoch == epoch0) {
+          __nanosleep(32);
+          if (++spins > (1u << 25)) __trap();  // unreachable under a cooperative launch; never hang, never use a stale std
+        }
+        __threadfence();
+        mbar_arrive(b_beta);
+      }
       auto store_tile = [&](int i) {
         if constexpr (!STATS) {
           const Item it = decode<D>(begin + i, p);
@@ -1173,7 +1194,8 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
           }
         } else {
           if (!have_beta) {
-            pdl_wait_prior_grid();  // pass 1 (same stream, launched just before) has published the std
+            if constexpr (MODE == 0) pdl_wait_prior_grid();  // pass 1 (same stream, launched just before) has published the std
+            if constexpr (MODE == 2) mbar_wait(b_beta, 0);         // ... or, in the single-launch form, the grid barrier
             const float sigma = p.sigma_dev ? __ldcg(p.sigma_dev) : p.sigma_host;
             beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2eT;
             have_beta = true;
@@ -1340,6 +1362,12 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         if (last) {  // last CTA: fold all partials (deterministic order)
           __threadfence();
           finalize_stats(p, partials, lane);
+          if constexpr (MODE == 1) {  // single-launch form: the publication is the grid barrier -- bump the epoch word
+            if (lane == 0) {
+              __threadfence();
+              atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(p.ws) + kEpochOffsetT), 1u);
+            }
+          }
         }
       }
     }
@@ -1351,10 +1379,41 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   tc_fence_after();
   TRACE(30);
   CTA_TIME(1);
-  if (warp == 16) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  if constexpr (MODE == 1) {
+    if (tid == 0)  // this phase's barrier words become ring-stage bytes of the next phase
+      for (int i = 0; i < 2 * NST + 16; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + 8 * i) : "memory");
+  } else {
+    if (warp == 16) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
   }
+  return tmem_base;
 }
+
+template <typename T, int D, bool STATS>
+__global__ void __launch_bounds__(kX4Threads, 1)
+xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_o,
+                   const __grid_constant__ CUtensorMap tm_w) {
+  x4_phase<T, D, STATS, 0>(p, tm_q, tm_o, tm_w, 0u);
+}
+
+// Both passes in ONE cooperative launch (grid <= SM count, one CTA per SM): pass 1 over the CTA's tile range, grid
+// barrier (the last CTA to publish its partial folds them all, writes the std and bumps an epoch word), pass 2 over the
+// same range.  K stays in place conceptually (it is restaged together with V^T while the slower CTAs still arrive), Q
+// is read again while much of it is still in L2 (pass 1 loads it evict-last), and there is no second launch, no second
+// TMEM allocation and no pass-2 prologue behind the end of pass 1.
+template <typename T, int D>
+__global__ void __launch_bounds__(kX4Threads, 1)
+xattn_tc5x4_fused_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_o,
+                         const __grid_constant__ CUtensorMap tm_w) {
+  volatile unsigned int* epoch = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<unsigned char*>(p.ws) + kEpochOffsetT);
+  unsigned int e0 = 0;
+  if (threadIdx.x == 19 * 32 + 16) e0 = *epoch;  // the producer thread, which waits for the bump in pass 2; read before
+                                                 // this CTA has arrived at the barrier: the bump cannot have happened yet
+  const uint32_t tmem_base = x4_phase<T, D, true, 1>(p, tm_q, tm_q, tm_q, 0u);
+  x4_phase<T, D, false, 2>(p, tm_q, tm_o, tm_w, tmem_base, e0);
+}
+
 
 // ---- host: tensor maps -------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1462,6 +1521,47 @@ extern "C" int dsc_debug_trace(long long* out /*HOST 4*512*2*/, int* counts /*HO
 }
 #endif
 
+template <typename T, int D>
+static cudaError_t launch_tc5x4_fused(XattnParams p, cudaStream_t st) {
+  using C = TC<D>;
+  constexpr int smem = X4<D>::FWD_SMEM > X4<D>::STATS_SMEM ? X4<D>::FWD_SMEM : X4<D>::STATS_SMEM;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_tc5x4_fused_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  CUtensorMap tm_q, tm_o;
+  if (!make_map(&tm_q, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb)) return cudaErrorInvalidValue;
+  if (!make_map(&tm_o, p.out, p.H * D, p.L, p.B, p.o_sl, p.o_sb)) return cudaErrorInvalidValue;
+  p.n_hg = (p.H + C::G - 1) / C::G;
+  p.n_sl = (p.L + C::ROWS - 1) / C::ROWS;
+  p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
+  if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
+  const int sms = sm_count_cached();
+  const int grid = static_cast<int>(p.total < sms ? p.total : sms);
+  static const unsigned env_flags = [] { const char* e = getenv("DSC_TC5_FLAGS"); return e ? static_cast<unsigned>(atoi(e)) : 0u; }();
+  p.flags = env_flags & 3u;
+  CUtensorMap tm_w = tm_q;
+  if (!(env_flags & 8u) && p.w_pitch == DSC_MAX_KEYS && p.S == 77 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0) {
+    if (!make_map_w(&tm_w, p.W, p.L, p.Bw)) return cudaErrorInvalidValue;
+    p.flags |= 4u;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kX4Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // the grid barrier between the passes needs every CTA resident
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, xattn_tc5x4_fused_kernel<T, D>, p, tm_q, tm_o, tm_w);
+}
+
 template <typename T, int D, bool STATS>
 static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   using C = TC<D>;
@@ -1525,6 +1625,14 @@ cudaError_t run_stats_tc5(const XattnParams& p, int D, int dtype, cudaStream_t s
   if (dtype == DSC_DTYPE_F16)
     return D == 40 ? launch_tc5<__half, 40, true>(p, st) : launch_tc5<__half, 80, true>(p, st);
   return D == 40 ? launch_tc5<__nv_bfloat16, 40, true>(p, st) : launch_tc5<__nv_bfloat16, 80, true>(p, st);
+}
+
+// both passes in one cooperative launch (4-warpgroup kernels, D = 40 / 80)
+bool tc5_fused_supports(int D) { return use_x4(D); }
+cudaError_t run_fused_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st) {
+  if (!use_x4(D)) return cudaErrorInvalidValue;
+  if (dtype == DSC_DTYPE_F16) return D == 40 ? launch_tc5x4_fused<__half, 40>(p, st) : launch_tc5x4_fused<__half, 80>(p, st);
+  return D == 40 ? launch_tc5x4_fused<__nv_bfloat16, 40>(p, st) : launch_tc5x4_fused<__nv_bfloat16, 80>(p, st);
 }
 
 cudaError_t run_forward_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st) {

@@ -20,17 +20,19 @@ from .helpers import make_qkv, rel_l2, synthetic_w, weight_func
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tc5", "tc5-padded", "mma", "mma-padded", "fused", "fused-padded"])
+@pytest.fixture(autouse=True, params=["tc5", "tc5-padded", "mma", "mma-padded", "fused", "fused-padded", "tc5fused", "tc5fused-padded"])
 def impl(request, monkeypatch):
     """Every test runs against both kernel families: tcgen05/TMEM (default where implemented: D=40, 80)
     and the legacy mma.sync path (all head dims; also the cross-check of the first) -- and with the region map in
     both device layouts: dense [B', L, 77] as the reference builds it, and the padded fast layout (rows 80 floats
     apart) that the processor's cache and encode_region_map produce."""
     family, _, layout = request.param.partition("-")
-    # "fused": the single-launch kernel (both passes, Q resident on chip) wherever the problem fits, two-pass mma.sync
-    # elsewhere; "mma" / "tc5": always two launches
-    monkeypatch.setenv("DSC_XATTN_IMPL", "mma" if family == "fused" else family)
-    monkeypatch.setenv("DSC_NO_FUSED", "0" if family == "fused" else "1")
+    # "fused": the single-launch mma.sync kernel (both passes, Q resident on chip) wherever the problem fits, two-pass
+    # mma.sync elsewhere; "tc5fused": the single-launch two-phase tcgen05 kernel (D = 40 / 80), two-pass elsewhere;
+    # "mma" / "tc5": always two launches
+    monkeypatch.setenv("DSC_XATTN_IMPL", {"fused": "mma", "tc5fused": "tc5"}.get(family, family))
+    monkeypatch.setenv("DSC_NO_FUSED", "0" if family in ("fused", "tc5fused") else "1")
+    monkeypatch.setenv("DSC_TC5_FUSED", "1" if family == "tc5fused" else "0")
     if layout == "padded":
         from diffusionspatialcontrol_b200 import attention as att
 
