@@ -30,7 +30,7 @@ def eager_reference_sequence(q, k, v, W, sigma):
     B, H = a.shape[:2]
     a = a.reshape(B * H, L, S)
     cw = W * sigma * a.std()
-    a = a + torch.repeat_interleave(cw, a.shape[0] // cw.shape[0], dim=0)
+    a += torch.repeat_interleave(cw, a.shape[0] // cw.shape[0], dim=0)  # in place, like the reference: keeps a's dtype
     a = a.reshape(B, H, L, S)
     return torch.softmax(a, dim=-1) @ v
 
