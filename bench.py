@@ -164,23 +164,27 @@ def attention_roofline(device):
             W = torch.zeros(B, L, S, device=device)
             W[:, : L // 2, 1:3] = 0.5
             W = att.padded_region_map(W)  # the device layout encode_region_map produces (rows 80 floats apart)
-            sets.append((q, k, v, W, torch.empty_like(q)))
+            Wc, cols = att.compact_region_map(W)  # + the compact form the processor derives once per map (2 weighted columns)
+            sets.append((q, k, v, W, torch.empty_like(q), Wc))
         qs, ks, vs = I4(*vw(sets[0][0]).stride()), I4(*vw(sets[0][1]).stride()), I4(*vw(sets[0][2]).stride())
         os_ = I3(*sets[0][4].stride())
 
+        cols_arr = (ctypes.c_int32 * len(cols))(*cols)
+
         def k1(t):
-            q, k, v, W, out = t
+            q, k, v, W, out, Wc = t
             check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), qs, ks, None, B, H, L, D, S, sc, 0, ws.data_ptr(), st))
 
         def k2(t):
-            q, k, v, W, out = t
+            q, k, v, W, out, Wc = t
             check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, W.stride(1), None, 7.0,
                                         ws.data_ptr(), out.data_ptr(), os_, B, H, L, D, S, sc, 0, st))
 
         def call(t):  # one attention call through the C ABI: pass 1 + pass 2 (pass 2 a programmatic dependent launch of
-            q, k, v, W, out = t  # pass 1), or ONE fused cooperative launch where the problem fits on chip (small layers)
-            check(lib.dsc_xattn_call(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, W.stride(1), None, 7.0,
-                                     ws.data_ptr(), out.data_ptr(), os_, B, H, L, D, S, sc, 0, st))
+            q, k, v, W, out, Wc = t  # pass 1), or ONE fused cooperative launch where the problem fits on chip (small layers)
+            check(lib.dsc_xattn_call_cw(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, W.stride(1),
+                                        Wc.data_ptr(), len(cols), cols_arr, None, 7.0, ws.data_ptr(), out.data_ptr(), os_,
+                                        B, H, L, D, S, sc, 0, st))
 
         for i in range(10):
             call(sets[i % 2])
@@ -212,8 +216,8 @@ def attention_roofline(device):
     return {
         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
         "peak_source": how,
-        "kernel": "one attention call = dsc_xattn_call (at this shape: dsc_xattn_stats + dsc_xattn_forward, two tcgen05 kernels, pass 2 "
-                  "a programmatic dependent launch of pass 1), one CUDA-event pair around the call, as in the pipeline",
+        "kernel": "one attention call = dsc_xattn_call_cw, the call the processor makes (at this shape: two tcgen05 kernels, pass 2 a "
+                  "programmatic dependent launch of pass 1 and fed with the compact region map), one CUDA-event pair around it",
         "shape": {"B": B, "H": H, "L": L0, "D": D0, "S": S, "dtype": "f16"},
         "algorithmic_bytes_per_call": d["bytes"], "avg_ms_call": d["ms_call"], "median_ms_call": d["ms_call_median"],
         "timed_calls": d["n_calls"],

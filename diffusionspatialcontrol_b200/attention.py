@@ -127,6 +127,27 @@ def padded_region_map(W: torch.Tensor) -> torch.Tensor:
     return buf[:, :, :S]
 
 
+MAX_COMPACT_COLS = 16  # DSC_MAX_COMPACT_COLS
+COMPACT_PITCH = 20     # DSC_COMPACT_PITCH
+AUTO_COMPACT = False   # tests: derive the compact form inside region_attention (costs a device->host readback per call)
+
+
+def compact_region_map(W: torch.Tensor):
+    """Compact form of a region map: with region prompts only the few tokens of the region phrases carry weights
+    (reference encode_region_map_function.py:57-63), so W[B', L, S] is non-zero in a handful of key columns.  Returns
+    ``(Wc, cols)`` -- fp32 [B', L, 20] holding those columns (ascending, zero-padded to 16 + 4) and their indices -- or
+    ``None`` when more than 16 columns are in use.  One device->host readback: call it once per map (the processor
+    does, at upload), never per attention call."""
+    Bw, L, S = W.shape
+    cols = torch.nonzero((W != 0).reshape(-1, S).any(dim=0)).flatten().tolist()
+    if len(cols) > MAX_COMPACT_COLS:
+        return None
+    Wc = torch.zeros((Bw, L, COMPACT_PITCH), dtype=torch.float32, device=W.device)
+    if cols:
+        Wc[:, :, : len(cols)] = W[:, :, cols]
+    return Wc, cols
+
+
 def region_attention(
     query: torch.Tensor,  # [B, H, L, D]
     key: torch.Tensor,  # [B, H, S, D]
@@ -136,6 +157,7 @@ def region_attention(
     attn_mask: Optional[torch.Tensor] = None,
     scale: Optional[float] = None,
     workspace: Optional[torch.Tensor] = None,
+    compact=None,  # optional (Wc, cols) from compact_region_map(region_state)
 ) -> torch.Tensor:
     """softmax(scale*QK^T + sigma*std(scale*QK^T)*W) V  ->  [B, H, L, D] (a view of a fresh [B, L, H*D])."""
     _check_inputs(query, key)
@@ -177,7 +199,17 @@ def region_attention(
     st = _stream_ptr(q.device)
     qs, ks, vs = _I64x4(*q.stride()), _I64x4(*k.stride()), _I64x4(*v.stride())
     with torch.cuda.device(q.device):
-        check(lib.dsc_xattn_call(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), W.shape[0],
-                                 W.stride(1), sigma_ptr, sigma_host, ws.data_ptr(), out.data_ptr(), _I64x3(*out.stride()),
-                                 B, H, L, D, S, scale, dt, st))
+        if compact is None and AUTO_COMPACT:
+            compact = compact_region_map(W)
+        wc_ptr, n_act, cols_arr = None, 0, None
+        if compact is not None and len(compact[1]) > 0:
+            Wc, cols = compact
+            if Wc.shape != (W.shape[0], L, COMPACT_PITCH) or Wc.dtype != torch.float32 or not Wc.is_contiguous() \
+                    or Wc.device != q.device:
+                raise ValueError("compact region map must be a contiguous fp32 [B', L, 20] tensor on the query's device")
+            wc_ptr, n_act = Wc.data_ptr(), len(cols)
+            cols_arr = (ctypes.c_int32 * n_act)(*cols)
+        check(lib.dsc_xattn_call_cw(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), W.shape[0],
+                                    W.stride(1), wc_ptr, n_act, cols_arr, sigma_ptr, sigma_host, ws.data_ptr(),
+                                    out.data_ptr(), _I64x3(*out.stride()), B, H, L, D, S, scale, dt, st))
     return out.view(B, L, H, D).transpose(1, 2)

@@ -17,7 +17,7 @@ from typing import Callable, Optional
 import torch
 import torch.nn.functional as F
 
-from .attention import padded_region_map, region_attention
+from .attention import compact_region_map, padded_region_map, region_attention
 
 
 def _is_reference_weight_func(fn: Callable) -> bool:
@@ -45,6 +45,7 @@ class RegionAttnProcessor:
         self.cache_kv = cache_kv
         self._w_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
         self._w_zero: dict = {}
+        self._w_compact: dict = {}
         self.skip_zero_maps = skip_zero_maps
         self._max_cached_maps = max_cached_maps
         self._checked_funcs: dict = {}
@@ -62,15 +63,23 @@ class RegionAttnProcessor:
         # Regions switched off still reach this path with an all-zero map (reference encode_region_map_function.py:33-36,
         # :74): beta * 0 adds nothing, so such a map is recognised ONCE here (one readback per map and
         # generation, never inside a CUDA-graph capture) and its calls take plain SDPA -- no std pass at all.
-        zero = False
-        if self.skip_zero_maps and dev.is_cuda and not torch.cuda.is_current_stream_capturing():
-            zero = not bool(torch.count_nonzero(dev).item())
+        # The same readback yields the compact form (only the key columns that carry weights: the tokens of the region
+        # phrases), which the tcgen05 pass 2 streams instead of the dense map (80 instead of 308 bytes per query row).
+        zero, compact = False, None
+        if dev.is_cuda and not torch.cuda.is_current_stream_capturing():
+            compact = compact_region_map(dev)
+            zero = self.skip_zero_maps and compact is not None and len(compact[1]) == 0
         self._w_zero[key] = zero
+        self._w_compact[key] = compact
         self._w_cache[key] = (w, dev)  # keeps `w` alive, so data_ptr cannot be recycled under the key
         while len(self._w_cache) > self._max_cached_maps:
             old, _ = self._w_cache.popitem(last=False)
             self._w_zero.pop(old, None)
+            self._w_compact.pop(old, None)
         return dev
+
+    def _map_compact(self, w: torch.Tensor, device: torch.device):
+        return self._w_compact.get((w.data_ptr(), w._version, tuple(w.shape), w.dtype, str(device)))
 
     def _map_is_zero(self, w: torch.Tensor, device: torch.device) -> bool:
         return self._w_zero.get((w.data_ptr(), w._version, tuple(w.shape), w.dtype, str(device)), False)
@@ -114,6 +123,7 @@ class RegionAttnProcessor:
     def clear_caches(self) -> None:
         self._w_cache.clear()
         self._w_zero.clear()
+        self._w_compact.clear()
         self._kv_cache.clear()
         self._sigma_cache = None
 
@@ -196,6 +206,7 @@ class RegionAttnProcessor:
                     self._sigma_arg(sigma, query.device),
                     attn_mask=attention_mask,
                     scale=None,  # the reference always uses 1/sqrt(head_dim) here (:77), not attn.scale
+                    compact=self._map_compact(w, query.device),
                 )
         else:
             hidden_states = F.scaled_dot_product_attention(

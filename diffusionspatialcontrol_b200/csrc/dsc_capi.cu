@@ -171,11 +171,25 @@ static int call_form(int B, int H, int L, int D, int S) {
   return 0;
 }
 
+struct CompactW {
+  const float* wc = nullptr;
+  int n = 0;
+  const int32_t* cols = nullptr;
+};
+
 static int forward_impl(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],
                         const int64_t v_str[4], const float* W, int Bw, int w_pitch, const float* sigma_dev_or_null,
                         float sigma_host, const void* workspace, void* out, const int64_t o_str[3], int B, int H, int L, int D,
-                        int S, float scale, int dtype, void* stream, bool with_stats, const char* who) {
+                        int S, float scale, int dtype, void* stream, bool with_stats, const char* who,
+                        const CompactW& cw = CompactW()) {
   int rc = check_dims(B, H, L, D, S, dtype);
+  if (cw.wc != nullptr && cw.n > 0) {
+    if (cw.n > DSC_MAX_COMPACT_COLS || !cw.cols || !aligned16(cw.wc))
+      return fail(DSC_ERR_INVALID_ARGUMENT, "compact map: need 1..%d columns, a column list and a 16-byte aligned base", DSC_MAX_COMPACT_COLS);
+    for (int j = 0; j < cw.n; ++j)
+      if (cw.cols[j] < 0 || cw.cols[j] >= S || (j > 0 && cw.cols[j] <= cw.cols[j - 1]))
+        return fail(DSC_ERR_INVALID_ARGUMENT, "compact map: column list must be ascending and inside [0, S)");
+  }
   if (rc) return rc;
   if (!workspace || !W || !out || !o_str) return fail(DSC_ERR_INVALID_ARGUMENT, "null pointer");
   if (Bw <= 0 || B % Bw != 0)
@@ -213,6 +227,11 @@ static int forward_impl(const void* q, const void* k, const void* v, const int64
   p.o_sb = o_str[0];
   p.o_sl = o_str[1];
   p.ws = const_cast<Workspace*>(static_cast<const Workspace*>(workspace));
+  if (cw.wc != nullptr && cw.n > 0) {
+    p.wc = cw.wc;
+    p.n_active = cw.n;
+    for (int j = 0; j < cw.n; ++j) p.active_cols[j] = cw.cols[j];
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
   if (with_stats) {
@@ -276,6 +295,18 @@ int dsc_xattn_call(const void* q, const void* k, const void* v, const int64_t q_
                    void* stream) {
   return forward_impl(q, k, v, q_str, k_str, v_str, W, Bw, w_pitch, sigma_dev_or_null, sigma_host, workspace, out, o_str, B, H,
                       L, D, S, scale, dtype, stream, true, "dsc_xattn_call");
+}
+
+int dsc_xattn_call_cw(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],
+                      const int64_t v_str[4], const float* W, int Bw, int w_pitch, const float* Wc, int n_active,
+                      const int32_t* active_cols, const float* sigma_dev_or_null, float sigma_host, void* workspace, void* out,
+                      const int64_t o_str[3], int B, int H, int L, int D, int S, float scale, int dtype, void* stream) {
+  CompactW cw;
+  cw.wc = Wc;
+  cw.n = n_active;
+  cw.cols = active_cols;
+  return forward_impl(q, k, v, q_str, k_str, v_str, W, Bw, w_pitch, sigma_dev_or_null, sigma_host, workspace, out, o_str, B, H,
+                      L, D, S, scale, dtype, stream, true, "dsc_xattn_call_cw", cw);
 }
 
 int dsc_region_downsample(const uint8_t* maps, int R, int Hpx, int Wpx, int w_r, int h_r, uint8_t* ds,

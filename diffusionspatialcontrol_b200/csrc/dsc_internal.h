@@ -40,6 +40,11 @@ struct XattnParams {
   int w_col0;           // pass 2: first W column of this chunk
   float* lse;           // pass 2: optional [B, H, L] log2-sum-exp of each row's logits (nullptr = not wanted)
   int fused_cps;        // fused single-launch kernel: CTAs per (batch, head-group) segment
+  // compact region map (optional; tcgen05 pass 2): only the n_active <= 16 key columns that are non-zero anywhere,
+  // fp32 [Bw, L, 20] (16 values + 4 pad floats per row); the kernel permutes the keys so that these columns come first
+  const float* wc;
+  int n_active;
+  int active_cols[16];  // ascending key indices of the compact columns
   unsigned flags;       // 4-warpgroup tcgen05 kernel: launcher-set mode bits (see launch_tc5x4)
 };
 

@@ -314,7 +314,8 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #define KV_TRACE(tag) do {} while (0)
 #endif
 template <typename T, int D, bool STATS, int NTHR = 256>
-__device__ __forceinline__ void stage_kv(unsigned char* smem, const XattnParams& p, const Item& it, int ctid) {
+__device__ __forceinline__ void stage_kv(unsigned char* smem, const XattnParams& p, const Item& it, int ctid,
+                                         const unsigned char* perm = nullptr) {
   using C = TC<D>;
   constexpr int MAXK = (C::G * DSC_MAX_KEYS * C::DCH + NTHR - 1) / NTHR;
   constexpr int NPAIR = D / 2 + 1;  // column pairs of V incl. the (ones, zero) pair that forms row D
@@ -333,7 +334,8 @@ __device__ __forceinline__ void stage_kv(unsigned char* smem, const XattnParams&
     const int hc = e / p.S, key = e - hc * p.S;       // one runtime division per piece
     const int h = hc / C::DCH, c = hc - h * C::DCH;   // constant divisor
     ksoff[u] = h * C::K_HEAD_BYTES + c * C::K_CH_BYTES + key * 16;
-    kv[u] = __ldg(reinterpret_cast<const uint4*>(kg + (key * kss + h * D + c * 8)));
+    const int krow = perm ? perm[key] : key;  // key slot -> row of K (compact region map: weighted columns first)
+    kv[u] = __ldg(reinterpret_cast<const uint4*>(kg + (krow * kss + h * D + c * 8)));
   }
   uint32_t ve[STATS ? 1 : MAXV][8];  // ve[u][j] = V[key 8*kc+j][d, d+1] (two 16-bit values)
   int vsoff[STATS ? 1 : MAXV];
@@ -845,13 +847,22 @@ struct X4 {
   static constexpr int WT_BYTES = C::ROWS * W_SMEM_PITCH * 4;
   static_assert(WT_BYTES % 1024 == 0, "stage alignment");
   static constexpr int FWD_SMEM = KV_FWD + C::FWD_STAGES * (C::QT_BYTES + WT_BYTES) + C::BAR_BYTES;
+  // compact region map (only the <= 16 key columns that carry weights; keys permuted so that they come first): the W tile
+  // shrinks from 42 KB to 10 KB (128 rows x 20 floats: 16 values + 4 pad, pitch 80 B = 5 x 16 B, conflict-free for
+  // 128-bit reads) and a THIRD ring stage fits
+  static constexpr int CW_PITCH = DSC_COMPACT_PITCH;
+  static constexpr int CWT_BYTES = C::ROWS * CW_PITCH * 4;
+  static constexpr int CW_STAGES = 3;
+  static constexpr int CW_PERM_OFF = KV_FWD + CW_STAGES * (C::QT_BYTES + CWT_BYTES) + C::BAR_BYTES;  // 80-byte slot -> key table
+  static constexpr int CW_SMEM = CW_PERM_OFF + 128;
+  static_assert((C::QT_BYTES + CWT_BYTES) % 1024 == 0 && CW_SMEM <= 227 * 1024, "compact-W stage");
   static constexpr int STATS_SMEM = C::K_BYTES_PAD + C::STATS_STAGES * C::QT_BYTES + C::BAR_BYTES;
 };
 
 // V (160 columns of the head group = n_vh virtual heads of 40) -> V^T canonical [key chunk][row d][8 keys], row 40 = ones
 template <typename T, int NTHR>
 __device__ __forceinline__ void stage_vt40(unsigned char* sVt, const XattnParams& p, const Item& it, int gw, int n_vh,
-                                           int ctid) {
+                                           int ctid, const unsigned char* perm = nullptr) {
   constexpr int NPAIR = 21;  // 20 column pairs + the (ones, zero) pair
   constexpr int MAXV = (4 * 10 * NPAIR + NTHR - 1) / NTHR;
   const T* __restrict__ vg = reinterpret_cast<const T*>(p.v) + it.b * p.v_sb + it.hg * gw;
@@ -870,7 +881,9 @@ __device__ __forceinline__ void stage_vt40(unsigned char* sVt, const XattnParams
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int key = kc * 8 + j;
-      const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(vg + (min(key, p.S - 1) * vss + col)));
+      const int slot = min(key, p.S - 1);
+      const int vrow = perm ? perm[slot] : slot;
+      const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(vg + (vrow * vss + col)));
       ve[u][j] = key >= p.S ? 0u : (dp == 20 ? one : x);
     }
   }
@@ -892,14 +905,15 @@ __device__ __forceinline__ void stage_vt40(unsigned char* sVt, const XattnParams
 // One pass (STATS: pass 1, else pass 2) as a device function, so that it can be a kernel of its own (MODE 0) or one of the
 // two phases of the single-launch kernel below (MODE 1: pass 1 followed by a grid barrier, keeps the TMEM allocation and
 // returns its base; MODE 2: pass 2 on that allocation, no programmatic-dependent-launch handshake).
-template <typename T, int D, bool STATS, int MODE>
+template <typename T, int D, bool STATS, int MODE, bool CW = false>
 __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_o,
                                              const CUtensorMap& tm_w, uint32_t tmem_in, unsigned int epoch0 = 0u) {
   using C = TC<D>;
   using X = X4<D>;
   constexpr int HPT = X::HPT, PAR = X::PAR, NH = X::NH;
-  constexpr int NST = STATS ? C::STATS_STAGES : C::FWD_STAGES;
-  constexpr int STAGE_BYTES = STATS ? C::QT_BYTES : (C::QT_BYTES + X::WT_BYTES);
+  static_assert(!(CW && STATS), "the compact region map only concerns pass 2");
+  constexpr int NST = STATS ? C::STATS_STAGES : (CW ? X::CW_STAGES : C::FWD_STAGES);
+  constexpr int STAGE_BYTES = STATS ? C::QT_BYTES : (C::QT_BYTES + (CW ? X::CWT_BYTES : X::WT_BYTES));
   constexpr int KV_BYTES = STATS ? C::K_BYTES_PAD : X::KV_FWD;
   constexpr int S_COL = 0, O_COL = 80, WG_COLS = 128;  // P aliases S, the Q operand aliases O
   constexpr int STAGE_CONSUMERS = HPT * 128;           // threads that hand a ring stage back
@@ -927,10 +941,28 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
   const uint32_t b_full = bars, b_odone = bars + 8 * NST, b_qrdy = bars + 16 * NST, b_srdy = b_qrdy + 32,
                  b_prdy = b_qrdy + 64, b_ordy = b_qrdy + 96;
   const uint32_t b_beta = b_qrdy + 128;  // single-launch form: "the std of this call has been published" (grid barrier)
-  static_assert(16 * C::FWD_STAGES + 128 + 8 <= 240 && 16 * C::STATS_STAGES + 128 + 8 <= 240, "barrier area");
+  static_assert(16 * NST + 128 + 8 <= 240, "barrier area");
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV_BYTES + NST * STAGE_BYTES + 240);
 
   for (int i = tid; i < KV_BYTES / 16; i += kX4Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  const unsigned char* perm = nullptr;
+  if constexpr (CW) {
+    // key slot -> key: the n_active weighted columns first (ascending), then every other key in order
+    unsigned char* pt = smem + X::CW_PERM_OFF;
+    if (tid < DSC_MAX_KEYS) {
+      int key = tid;
+      if (tid < p.n_active) {
+#pragma unroll
+        for (int j = 0; j < DSC_MAX_COMPACT_COLS; ++j) key = (j == tid) ? p.active_cols[j] : key;
+      } else {
+        key = tid - p.n_active;
+#pragma unroll
+        for (int j = 0; j < DSC_MAX_COMPACT_COLS; ++j) key += (j < p.n_active && p.active_cols[j] <= key) ? 1 : 0;
+      }
+      pt[tid] = static_cast<unsigned char>(min(key, DSC_MAX_KEYS - 1));
+    }
+    perm = pt;  // visible to everybody after the start-up barrier below
+  }
   TRACE(51);
   const int begin = static_cast<int>(p.total * blockIdx.x / gridDim.x);
   const int n_items = static_cast<int>(p.total * (blockIdx.x + 1) / gridDim.x) - begin;
@@ -943,7 +975,9 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
     uint32_t tx = C::QT_BYTES;
     const float* wsrc = nullptr;
     uint32_t wbytes = 0;
-    if constexpr (!STATS) {
+    if constexpr (CW) {
+      tx += X::CWT_BYTES;
+    } else if constexpr (!STATS) {
       if (w_fast) {
         tx += X::WT_BYTES;  // the whole box is counted, zero-filled parts included
       } else {
@@ -956,7 +990,9 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
 #pragma unroll
     for (int j = 0; j < C::NBOX; ++j)
       tma_load_3d(sQ + j * C::BOX_BYTES, &tm_q, it.hg * C::GW + j * C::BOX_COLS, it.l0, it.b, b_full + 8 * s, pol);
-    if constexpr (!STATS) {
+    if constexpr (CW) {
+      tma_load_3d(sQ + C::QT_BYTES, &tm_w, 0, it.l0, it.b / (p.B / p.Bw), b_full + 8 * s, pol);  // 20 x 128 box of Wc
+    } else if constexpr (!STATS) {
       if (w_fast) tma_load_3d(sQ + C::QT_BYTES, &tm_w, 0, it.l0, it.b / (p.B / p.Bw), b_full + 8 * s, pol);
       else if (wbytes != 0) bulk_g2s_hint(sQ + C::QT_BYTES, wsrc, wbytes, b_full + 8 * s, pol);
     }
@@ -1104,8 +1140,8 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
       const int r1 = min(n_items, r0 + p.n_sl - it0.tile);
       TRACE(3);
       asm volatile("bar.sync 1, 512;" ::: "memory");
-      stage_kv<T, D, true, kX4Consumers>(smem, p, it0, tid);  // K of the head group
-      if constexpr (!STATS) stage_vt40<T, kX4Consumers>(smem + X::VT_OFF, p, it0, C::GW, it0.nheads * NH, tid);
+      stage_kv<T, D, true, kX4Consumers>(smem, p, it0, tid, perm);  // K of the head group
+      if constexpr (!STATS) stage_vt40<T, kX4Consumers>(smem + X::VT_OFF, p, it0, C::GW, it0.nheads * NH, tid, perm);
       asm volatile("bar.sync 1, 512;" ::: "memory");
       TRACE(4);
       if (r1 < n_items) prefetch_kv<T, D, STATS, kX4Consumers>(p, decode<D>(begin + r1, p), tid);
@@ -1202,7 +1238,36 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
           }
           // logits in the log2 domain: s*scale*log2e + beta*log2e*W, W streamed from the shared tile
           uint32_t pw[40];
-          if (w_fast && beta_l2 > 1e-20f) {
+          if constexpr (CW) {
+            // compact region map: the weighted key columns are slots 0..15 (keys permuted at staging), one 80-byte row
+            // of W per query.  y = s * a + w * bw, 2^(e * y - e * max(y)): a = scale / beta, bw = 1, e = beta -- or, for a
+            // vanishing beta, a = scale, bw = beta, e = 1
+            const bool bpos = beta_l2 > 1e-20f;
+            const float ca = bpos ? scale_l2 / beta_l2 : scale_l2, cbw = bpos ? 1.f : beta_l2, ce = bpos ? beta_l2 : 1.f;
+            const float4* wt4 = reinterpret_cast<const float4*>(qtile + C::QT_BYTES + row * (X::CW_PITCH * 4));
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 w = wt4[j];
+              fmul2(w.x, w.y, w.x, w.y, cbw, cbw);
+              fmul2(w.z, w.w, w.z, w.w, cbw, cbw);
+              ffma2(sc[4 * j], sc[4 * j + 1], sc[4 * j], sc[4 * j + 1], ca, ca, w.x, w.y);
+              ffma2(sc[4 * j + 2], sc[4 * j + 3], sc[4 * j + 2], sc[4 * j + 3], ca, ca, w.z, w.w);
+            }
+#pragma unroll
+            for (int j = 8; j < 40; ++j) fmul2(sc[2 * j], sc[2 * j + 1], sc[2 * j], sc[2 * j + 1], ca, ca);
+            sc[77] = sc[78] = sc[79] = -INFINITY;  // pad keys (the launcher takes this path only for S == 77)
+#pragma unroll
+            for (int j = 0; j < 80; ++j) mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
+            const float nb = -ce * fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+#pragma unroll
+            for (int j = 0; j < 39; ++j) {
+              float e0, e1;
+              ffma2(e0, e1, sc[2 * j], sc[2 * j + 1], ce, ce, nb, nb);
+              pw[j] = j < 38 ? Mma<T>::pack(ex2_approx(e0), ex2_approx(e1)) : Mma<T>::pack(ex2_approx(e0), 0.f);
+            }
+            pw[39] = 0u;
+          } else if (w_fast && beta_l2 > 1e-20f) {
             // x = beta * y with y = s * (scale/beta) + W: the row max is taken on y, 2^(x - max) = 2^(beta*y - beta*ymax)
             const float4* wt4 = reinterpret_cast<const float4*>(qtile + C::QT_BYTES + row * (X::W_SMEM_PITCH * 4));
             const float cy = scale_l2 / beta_l2;
@@ -1397,6 +1462,14 @@ xattn_tc5x4_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
   x4_phase<T, D, STATS, 0>(p, tm_q, tm_o, tm_w, 0u);
 }
 
+// pass 2 with the compact region map (3-stage ring, 80-byte W rows, keys permuted)
+template <typename T, int D>
+__global__ void __launch_bounds__(kX4Threads, 1)
+xattn_tc5x4_cw_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_o,
+                      const __grid_constant__ CUtensorMap tm_w) {
+  x4_phase<T, D, false, 0, true>(p, tm_q, tm_o, tm_w, 0u);
+}
+
 // Both passes in ONE cooperative launch (grid <= SM count, one CTA per SM): pass 1 over the CTA's tile range, grid
 // barrier (the last CTA to publish its partial folds them all, writes the std and bumps an epoch word), pass 2 over the
 // same range.  K stays in place conceptually (it is restaged together with V^T while the slower CTAs still arrive), Q
@@ -1448,6 +1521,19 @@ static bool make_map_w(CUtensorMap* m, const float* base, int L, int Bw) {
   cuuint64_t gdim[3] = {DSC_MAX_KEYS, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(Bw)};
   cuuint64_t gstr[2] = {DSC_MAX_KEYS * 4ull, static_cast<cuuint64_t>(L) * DSC_MAX_KEYS * 4ull};
   cuuint32_t box[3] = {84, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// compact region map fp32 [Bw, L, 20] -> boxes of 20 columns x 128 rows
+static bool make_map_wc(CUtensorMap* m, const float* base, int L, int Bw) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {DSC_COMPACT_PITCH, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(Bw)};
+  cuuint64_t gstr[2] = {DSC_COMPACT_PITCH * 4ull, static_cast<cuuint64_t>(L) * DSC_COMPACT_PITCH * 4ull};
+  cuuint32_t box[3] = {DSC_COMPACT_PITCH, 128, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1589,9 +1675,15 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   static const unsigned env_flags = [] { const char* e = getenv("DSC_TC5_FLAGS"); return e ? static_cast<unsigned>(atoi(e)) : 0u; }();
   p.flags = env_flags & 3u;
   CUtensorMap tm_w = tm_q;
-  if (!STATS && !(env_flags & 8u) && p.w_pitch == DSC_MAX_KEYS && p.S == 77 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0) {
-    if (!make_map_w(&tm_w, p.W, p.L, p.Bw)) return cudaErrorInvalidValue;
-    p.flags |= 4u;  // W tiles arrive as TMA boxes at a pitch of 84 floats
+  bool compact = false;
+  if constexpr (!STATS) {
+    compact = p.wc != nullptr && p.n_active > 0 && p.S == 77 && !(env_flags & 16u);  // bit 4: ignore the compact map
+    if (compact) {
+      if (!make_map_wc(&tm_w, p.wc, p.L, p.Bw)) return cudaErrorInvalidValue;
+    } else if (!(env_flags & 8u) && p.w_pitch == DSC_MAX_KEYS && p.S == 77 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0) {
+      if (!make_map_w(&tm_w, p.W, p.L, p.Bw)) return cudaErrorInvalidValue;
+      p.flags |= 4u;  // W tiles arrive as TMA boxes at a pitch of 84 floats
+    }
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -1604,6 +1696,18 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   const char* nopdl = getenv("DSC_NO_PDL");
   cfg.attrs = attr;
   cfg.numAttrs = (!STATS && !(nopdl && nopdl[0] == '1')) ? 1 : 0;  // pass 2 may overlap the tail of pass 1
+  if constexpr (!STATS) {
+    if (compact) {
+      static thread_local int cw_dev = -1;
+      if (cw_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(xattn_tc5x4_cw_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, X4<D>::CW_SMEM);
+        if (e != cudaSuccess) return e;
+        cw_dev = dev;
+      }
+      cfg.dynamicSmemBytes = X4<D>::CW_SMEM;
+      return cudaLaunchKernelEx(&cfg, xattn_tc5x4_cw_kernel<T, D>, p, tm_q, tm_o, tm_w);
+    }
+  }
   return cudaLaunchKernelEx(&cfg, xattn_tc5x4_kernel<T, D, STATS>, p, tm_q, tm_o, tm_w);
 }
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSC_VERSION 103 /* major*10000 + minor*100 + patch */
+#define DSC_VERSION 104 /* major*10000 + minor*100 + patch */
 
 #define DSC_DTYPE_F16 0
 #define DSC_DTYPE_BF16 1
@@ -102,6 +102,21 @@ int dsc_xattn_call(const void* q, const void* k, const void* v, const int64_t q_
                    const float* sigma_dev_or_null, float sigma_host, void* workspace, void* out,
                    const int64_t o_str[3] /*HOST*/, int B, int H, int L, int D, int S, float scale, int dtype,
                    void* stream);
+
+/* dsc_xattn_call with the region map ALSO given in compact form: Wc is fp32 [Bw, L, DSC_COMPACT_PITCH] holding, for every
+ * query row, the values of the n_active <= DSC_MAX_COMPACT_COLS key columns of W that are non-zero anywhere (column
+ * active_cols[j], ascending, in slot j; remaining slots zero) -- with region prompts only the few tokens of the region
+ * phrases carry weights (encode_region_map_function.py:57-63).  Where it applies (tcgen05 pass 2, S == 77) the kernels
+ * then read 80 instead of 308 bytes of W per query row: the keys are permuted so that the active columns come first
+ * (softmax and P V do not depend on the key order).  W itself must still be valid (other paths use it); Wc == NULL or
+ * n_active == 0 means "no compact form".  Same result as dsc_xattn_call. */
+#define DSC_MAX_COMPACT_COLS 16
+#define DSC_COMPACT_PITCH 20
+int dsc_xattn_call_cw(const void* q, const void* k, const void* v, const int64_t q_str[4] /*HOST*/,
+                      const int64_t k_str[4] /*HOST*/, const int64_t v_str[4] /*HOST*/, const float* W, int Bw, int w_pitch,
+                      const float* Wc, int n_active, const int32_t* active_cols /*HOST*/, const float* sigma_dev_or_null,
+                      float sigma_host, void* workspace, void* out, const int64_t o_str[3] /*HOST*/, int B, int H, int L,
+                      int D, int S, float scale, int dtype, void* stream);
 
 /* Number of kernel launches dsc_xattn_call will issue for this shape on the current device: 1 (fused), 2 (pass 1 +
  * pass 2) or 2 * chunks + 1 (long prompts); -1 for an unsupported shape.  Introspection only. */

@@ -85,8 +85,13 @@ def bench_shape(B, H, L, D, S, dtype, flush, iters=30, ref=True):
     W = torch.zeros(B, L, S, device=dev)
     W[:, : L // 2, 1:3] = 0.5
     W[:, L // 3 :, 6] = 0.7
-    if os.environ.get("DSC_W_LAYOUT", "padded") == "padded":  # the layout encode_region_map / the processor cache produce
+    layout = os.environ.get("DSC_W_LAYOUT", "compact")  # compact: what the processor passes (padded dense map + compact form)
+    if layout in ("padded", "compact"):
         W = att.padded_region_map(W)
+    wc_ptr, n_act, cols_arr = None, 0, None
+    if layout == "compact":
+        Wc, cols = att.compact_region_map(W)
+        wc_ptr, n_act, cols_arr = Wc.data_ptr(), len(cols), (ctypes.c_int32 * len(cols))(*cols)
     view = lambda t: t.view(B, -1, H, D).transpose(1, 2)
     q4, k4, v4 = view(q), view(k), view(v)
     out = torch.empty(B, L, H * D, device=dev, dtype=dtype)
@@ -108,8 +113,8 @@ def bench_shape(B, H, L, D, S, dtype, flush, iters=30, ref=True):
         k2()
 
     def onecall():  # the product path: one C-ABI call (a single fused launch where the problem fits on chip)
-        check(lib.dsc_xattn_call(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, W.stride(1), None, 7.0,
-                                 ws.data_ptr(), out.data_ptr(), os_, B, H, L, D, S, scale, dt, st))
+        check(lib.dsc_xattn_call_cw(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, W.stride(1), wc_ptr,
+                                    n_act, cols_arr, None, 7.0, ws.data_ptr(), out.data_ptr(), os_, B, H, L, D, S, scale, dt, st))
 
     sig = torch.tensor(7.0, device=dev, dtype=dtype)
 
@@ -124,12 +129,14 @@ def bench_shape(B, H, L, D, S, dtype, flush, iters=30, ref=True):
     for i in range(nset):
         qi, ki, vi, oi = torch.randn_like(q), torch.randn_like(k), torch.randn_like(v), torch.empty_like(out)
         Wi = att.padded_region_map(W.clone()) if W.stride(1) == 80 else W.clone()
-        sets.append((qi, ki, vi, Wi, oi))
+        Wci = att.compact_region_map(Wi)[0] if layout == "compact" else None
+        sets.append((qi, ki, vi, Wi, oi, Wci))
 
     def call_set(t):
-        qi, ki, vi, Wi, oi = t
-        check(lib.dsc_xattn_call(qi.data_ptr(), ki.data_ptr(), vi.data_ptr(), qs, ks, vs, Wi.data_ptr(), B, Wi.stride(1), None, 7.0,
-                                 ws.data_ptr(), oi.data_ptr(), os_, B, H, L, D, S, scale, dt, st))
+        qi, ki, vi, Wi, oi, Wci = t
+        check(lib.dsc_xattn_call_cw(qi.data_ptr(), ki.data_ptr(), vi.data_ptr(), qs, ks, vs, Wi.data_ptr(), B, Wi.stride(1),
+                                    Wci.data_ptr() if Wci is not None else None, n_act, cols_arr, None, 7.0,
+                                    ws.data_ptr(), oi.data_ptr(), os_, B, H, L, D, S, scale, dt, st))
 
     for t in sets:
         call_set(t)

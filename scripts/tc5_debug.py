@@ -40,10 +40,11 @@ if mode == "stats":
     print("ratio sumsq", st["sumsq"] / float((a * a).sum()), "ratio sum", st["sum"] / float(a.sum()))
 else:
     W = torch.zeros(B, L, S); W[:, : L // 2, 1:3] = 0.5; W[:, L // 3:, 6 % S] += 0.7; W = W.cuda()
-    if os.environ.get("DSC_W_LAYOUT", "padded") == "padded":
+    if os.environ.get("DSC_W_LAYOUT", "compact") in ("padded", "compact"):
         from diffusionspatialcontrol_b200.attention import padded_region_map
         W = padded_region_map(W)
-    out = dsc.region_attention(q4, k4, v4, W, 5.0)
+    from diffusionspatialcontrol_b200.attention import compact_region_map
+    out = dsc.region_attention(q4, k4, v4, W, 5.0, compact=compact_region_map(W) if os.environ.get("DSC_W_LAYOUT", "compact") == "compact" else None)
     torch.cuda.synchronize()
     # fp32 check written out here (dev tool; the parity tests proper live in tests/ and use oracle/)
     _a = (q4.float() @ k4.float().transpose(-2, -1)) * (D ** -0.5)

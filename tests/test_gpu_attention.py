@@ -20,7 +20,8 @@ from .helpers import make_qkv, rel_l2, synthetic_w, weight_func
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tc5", "tc5-padded", "mma", "mma-padded", "fused", "fused-padded", "tc5fused", "tc5fused-padded"])
+@pytest.fixture(autouse=True, params=["tc5", "tc5-padded", "mma", "mma-padded", "fused", "fused-padded", "tc5fused", "tc5fused-padded",
+                                      "tc5-compact"])
 def impl(request, monkeypatch):
     """Every test runs against both kernel families: tcgen05/TMEM (default where implemented: D=40, 80)
     and the legacy mma.sync path (all head dims; also the cross-check of the first) -- and with the region map in
@@ -33,6 +34,10 @@ def impl(request, monkeypatch):
     monkeypatch.setenv("DSC_XATTN_IMPL", {"fused": "mma", "tc5fused": "tc5"}.get(family, family))
     monkeypatch.setenv("DSC_NO_FUSED", "0" if family in ("fused", "tc5fused") else "1")
     monkeypatch.setenv("DSC_TC5_FUSED", "1" if family == "tc5fused" else "0")
+    if layout == "compact":  # tcgen05 pass 2 fed with the compact region map (weighted key columns only, keys permuted)
+        from diffusionspatialcontrol_b200 import attention as att
+
+        monkeypatch.setattr(att, "AUTO_COMPACT", True)
     if layout == "padded":
         from diffusionspatialcontrol_b200 import attention as att
 
