@@ -11,13 +11,15 @@ q = torch.randn(B, L, H * D, device="cuda", dtype=dtype)
 k = torch.randn(B, S, H * D, device="cuda", dtype=dtype)
 v = torch.randn(B, S, H * D, device="cuda", dtype=dtype)
 W = torch.zeros(B, L, S, device="cuda"); W[:, : L // 2, 1:3] = 0.5
-if os.environ.get("DSC_W_LAYOUT", "padded") == "padded":
+if os.environ.get("DSC_W_LAYOUT", "compact") in ("padded", "compact"):
     from diffusionspatialcontrol_b200.attention import padded_region_map
     W = padded_region_map(W)
+from diffusionspatialcontrol_b200.attention import compact_region_map
+COMPACT = compact_region_map(W) if os.environ.get("DSC_W_LAYOUT", "compact") == "compact" else None
 view = lambda t: t.view(B, -1, H, D).transpose(1, 2)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 for _ in range(iters):
     flush.zero_()
-    o = dsc.region_attention(view(q), view(k), view(v), W, 7.0)
+    o = dsc.region_attention(view(q), view(k), view(v), W, 7.0, compact=COMPACT)
 torch.cuda.synchronize()
 print("ok", float(o.float().abs().mean()))
