@@ -1245,25 +1245,32 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
             const bool bpos = beta_l2 > 1e-20f;
             const float ca = bpos ? scale_l2 / beta_l2 : scale_l2, cbw = bpos ? 1.f : beta_l2, ce = bpos ? beta_l2 : 1.f;
             const float4* wt4 = reinterpret_cast<const float4*>(qtile + C::QT_BYTES + row * (X::CW_PITCH * 4));
-            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            // slots 0..15: y formed explicitly; slots 16..79 carry no weight: their y is a * s, so the row max is taken on
+            // the raw scores (a > 0) and the scaling folds into the single FFMA that forms the exponent
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float4 w = wt4[j];
-              fmul2(w.x, w.y, w.x, w.y, cbw, cbw);
-              fmul2(w.z, w.w, w.z, w.w, cbw, cbw);
+              if (!bpos) {
+                fmul2(w.x, w.y, w.x, w.y, cbw, cbw);
+                fmul2(w.z, w.w, w.z, w.w, cbw, cbw);
+              }
               ffma2(sc[4 * j], sc[4 * j + 1], sc[4 * j], sc[4 * j + 1], ca, ca, w.x, w.y);
               ffma2(sc[4 * j + 2], sc[4 * j + 3], sc[4 * j + 2], sc[4 * j + 3], ca, ca, w.z, w.w);
             }
-#pragma unroll
-            for (int j = 8; j < 40; ++j) fmul2(sc[2 * j], sc[2 * j + 1], sc[2 * j], sc[2 * j + 1], ca, ca);
             sc[77] = sc[78] = sc[79] = -INFINITY;  // pad keys (the launcher takes this path only for S == 77)
+            float my[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mr[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int j = 0; j < 80; ++j) mx[j & 3] = fmaxf(mx[j & 3], sc[j]);
-            const float nb = -ce * fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            for (int j = 0; j < 16; ++j) my[j & 3] = fmaxf(my[j & 3], sc[j]);
+#pragma unroll
+            for (int j = 16; j < 80; ++j) mr[j & 3] = fmaxf(mr[j & 3], sc[j]);
+            const float m = fmaxf(fmaxf(fmaxf(my[0], my[1]), fmaxf(my[2], my[3])),
+                                  ca * fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])));
+            const float nb = -ce * m, k2 = ce * ca;
 #pragma unroll
             for (int j = 0; j < 39; ++j) {
               float e0, e1;
-              ffma2(e0, e1, sc[2 * j], sc[2 * j + 1], ce, ce, nb, nb);
+              if (j < 8) ffma2(e0, e1, sc[2 * j], sc[2 * j + 1], ce, ce, nb, nb);
+              else ffma2(e0, e1, sc[2 * j], sc[2 * j + 1], k2, k2, nb, nb);
               pw[j] = j < 38 ? Mma<T>::pack(ex2_approx(e0), ex2_approx(e1)) : Mma<T>::pack(ex2_approx(e0), 0.f);
             }
             pw[39] = 0u;
@@ -1677,7 +1684,7 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   CUtensorMap tm_w = tm_q;
   bool compact = false;
   if constexpr (!STATS) {
-    compact = p.wc != nullptr && p.n_active > 0 && p.S == 77 && !(env_flags & 16u);  // bit 4: ignore the compact map
+    compact = p.wc != nullptr && p.n_active > 0 && p.S == 77 && p.scale > 0.f && !(env_flags & 16u);  // bit 4: ignore the compact map
     if (compact) {
       if (!make_map_wc(&tm_w, p.wc, p.L, p.Bw)) return cudaErrorInvalidValue;
     } else if (!(env_flags & 8u) && p.w_pitch == DSC_MAX_KEYS && p.S == 77 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0) {
