@@ -377,3 +377,34 @@ def test_ip_adapter_processor_matches_oracle(n_adapters, with_masks):
         plain = ours(attn16, hs16, encoder_hidden_states=(ctx16, [torch.zeros_like(t) for t in ip16]), region_prompt=rp)
     assert rel_l2(got.float(), want) <= 4e-3
     assert not torch.allclose(got, plain, atol=1e-3)  # the image prompt contributes
+
+
+@pytest.mark.parametrize("D,L", [(40, 1024), (80, 512)])
+def test_compact_region_map_edge_cases(D, L, monkeypatch):
+    """The compact form (weighted key columns only) with the maximum of 16 columns incl. the first and the last key,
+    in arbitrary positions; 17 columns have no compact form and take the dense map."""
+    dsc, att = _dsc()
+    monkeypatch.setenv("DSC_XATTN_IMPL", "tc5")
+    monkeypatch.setenv("DSC_NO_FUSED", "1")
+    B, S = 2, 77
+    q, k, v = make_qkv(B, 8, L, D, S, seed=D + L, device="cuda")
+    g = torch.Generator().manual_seed(5)
+    cols = sorted({0, 76} | set(torch.randperm(75, generator=g)[:14].add(1).tolist()))
+    assert len(cols) == 16
+    W = torch.zeros(B, L, S)
+    for j, c in enumerate(cols):
+        W[:, (j * 37) % L :: 3, c] = 0.1 * (j + 1) * (-1) ** j
+    W = W.cuda()
+    comp = att.compact_region_map(W)
+    assert comp is not None and comp[1] == cols and comp[0].shape == (B, L, 20)
+    for sigma in (11.0, 0.0):
+        out = dsc.region_attention(q, k, v, W, sigma, compact=comp)
+        ref = _oracle(q, k, v, W, sigma)
+        assert rel_l2(out.float(), ref) <= TOL
+        dense = dsc.region_attention(q, k, v, W, sigma)
+        assert rel_l2(out.float(), dense.float()) <= 3e-4  # same math, keys visited in another order
+    W17 = W.clone()
+    W17[:, 5, [c for c in range(77) if c not in cols][0]] = 1.0
+    assert att.compact_region_map(W17) is None
+    with pytest.raises(ValueError):
+        dsc.region_attention(q, k, v, W, 1.0, compact=(comp[0][:, :, :16].contiguous(), cols))
