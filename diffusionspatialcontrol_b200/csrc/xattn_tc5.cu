@@ -285,14 +285,13 @@ template <typename T, int D, bool STATS, int NTHR>
 __device__ __forceinline__ void prefetch_kv(const XattnParams& p, const Item& it, int ctid) {
   using C = TC<D>;
   const int row_bytes = it.nheads * D * 2;
-  const int lines_per_row = (row_bytes + 127) / 128;
-  const int n_lines = p.S * lines_per_row;
   const char* kb = reinterpret_cast<const char*>(reinterpret_cast<const T*>(p.k) + it.b * p.k_sb + it.hg * C::GW);
   const char* vb = reinterpret_cast<const char*>(reinterpret_cast<const T*>(p.v) + it.b * p.v_sb + it.hg * C::GW);
-  for (int e = ctid; e < n_lines; e += NTHR) {
-    const int key = e / lines_per_row, l = e - key * lines_per_row;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + static_cast<long long>(key) * p.k_ss * 2 + l * 128));
-    if constexpr (!STATS) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + static_cast<long long>(key) * p.v_ss * 2 + l * 128));
+  for (int key = ctid; key < p.S; key += NTHR) {  // one thread per key row (<= 3 lines of 128 B), no divisions
+    for (int l = 0; l < row_bytes; l += 128) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + static_cast<long long>(key) * p.k_ss * 2 + l));
+      if constexpr (!STATS) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + static_cast<long long>(key) * p.v_ss * 2 + l));
+    }
   }
 }
 
@@ -317,7 +316,7 @@ template <typename T, int D, bool STATS, int NTHR = 256>
 __device__ __forceinline__ void stage_kv(unsigned char* smem, const XattnParams& p, const Item& it, int ctid,
                                          const unsigned char* perm = nullptr) {
   using C = TC<D>;
-  constexpr int MAXK = (C::G * DSC_MAX_KEYS * C::DCH + NTHR - 1) / NTHR;
+  constexpr int MAXK = (C::G * DSC_MAX_KEYS * C::DCH + NTHR - 1) / NTHR;  // pieces incl. the pad keys (stored as zeros)
   constexpr int NPAIR = D / 2 + 1;  // column pairs of V incl. the (ones, zero) pair that forms row D
   constexpr int MAXV = (C::G * 10 * NPAIR + NTHR - 1) / NTHR;
   KV_TRACE(31);
@@ -325,17 +324,19 @@ __device__ __forceinline__ void stage_kv(unsigned char* smem, const XattnParams&
   // thread for every piece (64-bit multiplies here cost more issue slots than the loads themselves)
   const T* __restrict__ kg = reinterpret_cast<const T*>(p.k) + it.b * p.k_sb + it.hg * C::GW;
   const int kss = static_cast<int>(p.k_ss), vss = static_cast<int>(p.v_ss);
-  const int n_k = it.nheads * C::DCH * p.S;
+  const int n_k = it.nheads * C::DCH * DSC_MAX_KEYS;  // pieces (head, chunk, key slot 0..79), key fastest
   uint4 kv[MAXK];
   int ksoff[MAXK];
 #pragma unroll
   for (int u = 0; u < MAXK; ++u) {
     const int e = min(ctid + u * NTHR, n_k - 1);
-    const int hc = e / p.S, key = e - hc * p.S;       // one runtime division per piece
-    const int h = hc / C::DCH, c = hc - h * C::DCH;   // constant divisor
+    const int hc = e / DSC_MAX_KEYS, key = e - hc * DSC_MAX_KEYS;  // constant divisors only
+    const int h = hc / C::DCH, c = hc - h * C::DCH;
     ksoff[u] = h * C::K_HEAD_BYTES + c * C::K_CH_BYTES + key * 16;
-    const int krow = perm ? perm[key] : key;  // key slot -> row of K (compact region map: weighted columns first)
+    const int slot = min(key, p.S - 1);
+    const int krow = perm ? perm[slot] : slot;  // key slot -> row of K (compact region map: weighted columns first)
     kv[u] = __ldg(reinterpret_cast<const uint4*>(kg + (krow * kss + h * D + c * 8)));
+    if (key >= p.S) kv[u] = make_uint4(0, 0, 0, 0);  // pad keys: exact zero scores
   }
   uint32_t ve[STATS ? 1 : MAXV][8];  // ve[u][j] = V[key 8*kc+j][d, d+1] (two 16-bit values)
   int vsoff[STATS ? 1 : MAXV];
@@ -944,7 +945,16 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
   static_assert(16 * NST + 128 + 8 <= 240, "barrier area");
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV_BYTES + NST * STAGE_BYTES + 240);
 
-  for (int i = tid; i < KV_BYTES / 16; i += kX4Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  // Only the zero chunk that pads K's contraction dim (D = 40: the odd half k-step) has to be cleared: staging writes
+  // every other byte the tensor core reads (pad keys as explicit zeros), and the V^T rows 42..47 it never writes only
+  // feed the O columns 42..47 that nobody reads.
+  if constexpr (C::KCH > C::DCH) {
+    constexpr int ZCH = (C::KCH - C::DCH) * C::K_CH_BYTES / 16;  // uint4 per head
+    for (int i = tid; i < C::G * ZCH; i += kX4Threads) {
+      const int h = i / ZCH, r = i - h * ZCH;
+      reinterpret_cast<uint4*>(smem + h * C::K_HEAD_BYTES + C::DCH * C::K_CH_BYTES)[r] = make_uint4(0, 0, 0, 0);
+    }
+  }
   const unsigned char* perm = nullptr;
   if constexpr (CW) {
     // key slot -> key: the n_active weighted columns first (ascending), then every other key in order
