@@ -929,7 +929,13 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
   const bool w_fast = !STATS && (p.flags & 4u) != 0;
   TRACE(1);
   CTA_TIME(0);
-  if constexpr (STATS && MODE == 0) pdl_launch_dependents();  // let pass 2 start its prologue on SMs as they free up
+  if constexpr (STATS && MODE == 0) {
+    // pass 1 is itself launched as a programmatic dependent of whatever precedes it in the stream: its CTAs may be
+    // placed while that kernel drains; nothing of its inputs is touched before the predecessor has completed
+    pdl_wait_prior_grid();
+    pdl_launch_dependents();  // let pass 2 start its prologue on SMs as they free up
+  }
+  if constexpr (!STATS && MODE == 0) pdl_launch_dependents();  // a following pass 1 (next call) may be placed as SMs free up
   {  // first thing: start pulling this CTA's first K / V head group into L2
     const int begin0 = static_cast<int>(p.total * blockIdx.x / gridDim.x);
     if (tid < kX4Consumers && begin0 < p.total) prefetch_kv<T, D, STATS, kX4Consumers>(p, decode<D>(begin0, p), tid);
@@ -1712,7 +1718,7 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   const char* nopdl = getenv("DSC_NO_PDL");
   cfg.attrs = attr;
-  cfg.numAttrs = (!STATS && !(nopdl && nopdl[0] == '1')) ? 1 : 0;  // pass 2 may overlap the tail of pass 1
+  cfg.numAttrs = !(nopdl && nopdl[0] == '1') ? 1 : 0;  // pass 2 may overlap the tail of pass 1 (and pass 1 its predecessor's)
   if constexpr (!STATS) {
     if (compact) {
       static thread_local int cw_dev = -1;
