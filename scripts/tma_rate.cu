@@ -99,7 +99,7 @@ int main() {
   EncodeFn encode = nullptr; cudaDriverEntryPointQueryResult qres;
   cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres);
   if (!encode) { printf("{\"bench\":\"tensor_2d\",\"err\":\"no cuTensorMapEncodeTiled\"}\n"); return 0; }
-  int boxcols[] = {160, 168, 320, 64};
+  int boxcols[] = {160, 168, 320, 64, 32, 16, 8};
   for (int bc : boxcols) {
     cuuint64_t rows_total = bufsz / 640;
     cuuint64_t gdim[2] = {320, rows_total}; cuuint64_t gstr[1] = {640};
