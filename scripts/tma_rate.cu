@@ -69,6 +69,34 @@ __global__ void k_tensor(const __grid_constant__ CUtensorMap map, int box_rows, 
   if (acc == 0xdeadbeef) sink[0] = acc;
 }
 
+// NB boxes of box_cols x box_rows (adjacent column ranges of the same rows) per tile, all on one barrier, NST tiles in
+// flight: what staging K / V into 16-byte-row UMMA layouts by TMA would look like (NB = 20, box_cols = 8, box_rows = 80)
+__global__ void k_tensor_multi(const __grid_constant__ CUtensorMap map, int box_rows, int box_bytes_row, int nb, int tiles, unsigned* sink) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bars[NST];
+  const int lane = threadIdx.x;
+  const uint32_t box_bytes = box_rows * box_bytes_row, stage_bytes = nb * box_bytes;
+  if (lane == 0) { for (int s = 0; s < NST; ++s) mbar_init(s32(&bars[s]), 1); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  __syncwarp();
+  auto issue = [&](int t) {
+    const int s = t % NST;
+    if (lane == 0) {
+      expect(s32(&bars[s]), stage_bytes);
+      for (int j = 0; j < nb; ++j)
+        tma2d(s32(smem) + s * stage_bytes + j * box_bytes, &map, j * (box_bytes_row / 2), (blockIdx.x * tiles + t) * box_rows, s32(&bars[s]));
+    }
+  };
+  for (int t = 0; t < NST && t < tiles; ++t) issue(t);
+  unsigned acc = 0;
+  for (int t = 0; t < tiles; ++t) {
+    wait(s32(&bars[t % NST]), (t / NST) & 1);
+    acc += smem[(t % NST) * stage_bytes + lane];
+    __syncwarp();
+    if (t + NST < tiles) issue(t + NST);
+  }
+  if (acc == 0xdeadbeef) sink[0] = acc;
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int main() {
@@ -115,6 +143,25 @@ int main() {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     double bytes = (double)ctas * tiles * 128 * bc * 2;
     printf("{\"bench\":\"tensor_2d\",\"box_cols\":%d,\"box_rows\":128,\"tiles\":%d,\"ms\":%.4f,\"gbs\":%.1f,\"err\":\"%s\"}\n", bc, tiles, ms, bytes / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+  }
+  // many narrow boxes per tile
+  struct { int bc, rows, nb; } multi[] = {{8, 80, 20}, {8, 80, 40}, {8, 128, 20}, {32, 128, 5}, {16, 80, 10}};
+  for (auto m : multi) {
+    cuuint64_t rows_total = bufsz / 640;
+    cuuint64_t gdim[2] = {320, rows_total}; cuuint64_t gstr[1] = {640};
+    cuuint32_t box[2] = {(cuuint32_t)m.bc, (cuuint32_t)m.rows}; cuuint32_t estr[2] = {1, 1};
+    CUtensorMap map;
+    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) continue;
+    int tiles = 64; int smem = NST * m.nb * m.rows * m.bc * 2;
+    cudaFuncSetAttribute(k_tensor_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_tensor_multi<<<ctas, 32, smem>>>(map, m.rows, m.bc * 2, m.nb, tiles, sink);
+    cudaEventRecord(e0);
+    k_tensor_multi<<<ctas, 32, smem>>>(map, m.rows, m.bc * 2, m.nb, tiles, sink);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double bytes = (double)ctas * tiles * m.nb * m.rows * m.bc * 2;
+    printf("{\"bench\":\"tensor_2d_multi\",\"box_cols\":%d,\"box_rows\":%d,\"boxes_per_tile\":%d,\"tiles\":%d,\"ms\":%.4f,\"us_per_tile\":%.3f,\"ns_per_box_row\":%.2f,\"gbs\":%.1f,\"err\":\"%s\"}\n",
+           m.bc, m.rows, m.nb, tiles, ms, ms * 1e3 / tiles, ms * 1e6 / tiles / (m.nb * m.rows), bytes / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
   }
   return 0;
 }
