@@ -38,15 +38,15 @@ int sm_count_cached() {
 
 // Kernel family per call.  DSC_XATTN_IMPL=mma forces the legacy mma.sync kernels, =tc5 forces tcgen05/TMEM
 // wherever it is implemented (D = 40, 80); default "auto" = whichever measured faster on B200 for the head dim
-// (profiles/): tcgen05 at D = 40 (both passes) and D = 80 (pass 2; its pass 1 is 2 us faster on mma.sync), mma.sync
-// elsewhere.  The two passes only share the std in the workspace, so the families mix freely.
+// (profiles/): tcgen05 at D = 40 and D = 80 (both passes; since pass 1 stages K by TMA it is level with mma.sync at
+// D = 80 too), mma.sync elsewhere.  The two passes only share the std in the workspace, so the families mix freely.
 static bool use_tc5(int D, bool stats) {
   const char* e = getenv("DSC_XATTN_IMPL");
   const char* es = getenv("DSC_XATTN_STATS_IMPL");  // pass 1 alone (A/B runs)
   if (stats && es) e = es;
   if (e && strcmp(e, "mma") == 0) return false;
   if (e && strcmp(e, "tc5") == 0) return tc5_supports(D);
-  return D == 40 || (D == 80 && !stats);
+  return D == 40 || D == 80;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

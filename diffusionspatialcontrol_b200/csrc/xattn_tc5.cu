@@ -948,7 +948,20 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
   const uint32_t b_full = bars, b_odone = bars + 8 * NST, b_qrdy = bars + 16 * NST, b_srdy = b_qrdy + 32,
                  b_prdy = b_qrdy + 64, b_ordy = b_qrdy + 96;
   const uint32_t b_beta = b_qrdy + 128;  // single-launch form: "the std of this call has been published" (grid barrier)
-  static_assert(16 * NST + 128 + 8 <= 240, "barrier area");
+  const uint32_t b_kfull = b_qrdy + 136;  // pass 1: the K head group has landed (staged by TMA, see issue_k)
+  static_assert(16 * NST + 128 + 16 <= 240, "barrier area");
+  // Pass 1 stages K with the TMA itself: one box of 8 columns x 80 keys per (head, 16-byte chunk) IS the UMMA K-major
+  // layout [chunk][key][16 B] (keys >= S arrive as zeros); 20 such boxes on one barrier stream at about a row per clock
+  // (profiles/r1_tma_copy_rate.jsonl) with no thread work.  (Pass 2 cannot: V must be transposed and, with the compact
+  // region map, the keys permuted.)  For pass 1 the tensor map of K travels in the tm_o slot.
+  auto issue_k = [&](const Item& it) {
+    const uint64_t pol_k = policy_evict_last();
+    mbar_arrive_expect_tx(b_kfull, it.nheads * C::DCH * C::K_CH_BYTES);
+    for (int h = 0; h < it.nheads; ++h)
+#pragma unroll
+      for (int c = 0; c < C::DCH; ++c)
+        tma_load_3d(s0 + h * C::K_HEAD_BYTES + c * C::K_CH_BYTES, &tm_o, it.hg * C::GW + h * D + c * 8, 0, it.b, b_kfull, pol_k);
+  };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV_BYTES + NST * STAGE_BYTES + 240);
 
   // Only the zero chunk that pads K's contraction dim (D = 40: the odd half k-step) has to be cleared: staging writes
@@ -1031,7 +1044,14 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
       mbar_init(b_prdy + 8 * g, warp_arrive ? 4 : 128);
       mbar_init(b_ordy + 8 * g, 1);
     }
+    if constexpr (STATS) mbar_init(b_kfull, 1);
     fence_mbar_init();
+    if constexpr (STATS) {
+      if (n_items > 0) {
+        fence_proxy_async();  // the zero chunk cleared above (generic proxy) before the async-proxy writes next to it
+        issue_k(decode<D>(begin, p));
+      }
+    }
   }
   if constexpr (MODE != 2) {
     if (warp == 16) {
@@ -1150,15 +1170,24 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
     bool have_beta = STATS;
     const float scale_l2 = p.scale * kLog2eT;
     double dsum = 0.0, dsq = 0.0;
-    uint32_t n_s = 0, n_o = 0, n_q = 0;
+    uint32_t n_s = 0, n_o = 0, n_q = 0, n_run = 0;
     for (int r0 = 0; r0 < n_items;) {
       const Item it0 = decode<D>(begin + r0, p);
       const int r1 = min(n_items, r0 + p.n_sl - it0.tile);
       TRACE(3);
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      stage_kv<T, D, true, kX4Consumers>(smem, p, it0, tid, perm);  // K of the head group
-      if constexpr (!STATS) stage_vt40<T, kX4Consumers>(smem + X::VT_OFF, p, it0, C::GW, it0.nheads * NH, tid, perm);
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if constexpr (STATS) {
+        if (r0 > 0) {  // every warpgroup is done with the previous K: its successor may land
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          if (tid == 0) issue_k(it0);
+        }
+        MBAR_WAIT(b_kfull, n_run & 1, 4);
+        ++n_run;
+      } else {
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        stage_kv<T, D, true, kX4Consumers>(smem, p, it0, tid, perm);  // K of the head group
+        stage_vt40<T, kX4Consumers>(smem + X::VT_OFF, p, it0, C::GW, it0.nheads * NH, tid, perm);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+      }
       TRACE(4);
       if (r1 < n_items) prefetch_kv<T, D, STATS, kX4Consumers>(p, decode<D>(begin + r1, p), tid);
       const bool active = h < it0.nheads;
@@ -1469,7 +1498,7 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
   CTA_TIME(1);
   if constexpr (MODE == 1) {
     if (tid == 0)  // this phase's barrier words become ring-stage bytes of the next phase
-      for (int i = 0; i < 2 * NST + 16; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + 8 * i) : "memory");
+      for (int i = 0; i < 2 * NST + 18; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + 8 * i) : "memory");
   } else {
     if (warp == 16) {
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -1501,12 +1530,12 @@ xattn_tc5x4_cw_kernel(const XattnParams p, const __grid_constant__ CUtensorMap t
 template <typename T, int D>
 __global__ void __launch_bounds__(kX4Threads, 1)
 xattn_tc5x4_fused_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_o,
-                         const __grid_constant__ CUtensorMap tm_w) {
+                         const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_k) {
   volatile unsigned int* epoch = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<unsigned char*>(p.ws) + kEpochOffsetT);
   unsigned int e0 = 0;
   if (threadIdx.x == 19 * 32 + 16) e0 = *epoch;  // the producer thread, which waits for the bump in pass 2; read before
                                                  // this CTA has arrived at the barrier: the bump cannot have happened yet
-  const uint32_t tmem_base = x4_phase<T, D, true, 1>(p, tm_q, tm_q, tm_q, 0u);
+  const uint32_t tmem_base = x4_phase<T, D, true, 1>(p, tm_q, tm_k, tm_q, 0u);
   x4_phase<T, D, false, 2>(p, tm_q, tm_o, tm_w, tmem_base, e0);
 }
 
@@ -1546,6 +1575,19 @@ static bool make_map_w(CUtensorMap* m, const float* base, int L, int Bw) {
   cuuint32_t box[3] = {84, 128, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// K [B, S, cols] 16-bit (element strides sb, ss, 1) -> boxes of 8 columns (16 B) x 80 keys: one UMMA K-major chunk column
+static bool make_map_k(CUtensorMap* m, const void* base, int cols, int S, int B, long long ss, long long sb) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(ss) * 2, static_cast<cuuint64_t>(B > 1 ? sb : ss * S) * 2};
+  cuuint32_t box[3] = {8, DSC_MAX_KEYS, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1668,7 +1710,9 @@ static cudaError_t launch_tc5x4_fused(XattnParams p, cudaStream_t st) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, xattn_tc5x4_fused_kernel<T, D>, p, tm_q, tm_o, tm_w);
+  CUtensorMap tm_k;
+  if (!make_map_k(&tm_k, p.k, p.H * D, p.S, p.B, p.k_ss, p.k_sb)) return cudaErrorInvalidValue;
+  return cudaLaunchKernelEx(&cfg, xattn_tc5x4_fused_kernel<T, D>, p, tm_q, tm_o, tm_w, tm_k);
 }
 
 template <typename T, int D, bool STATS>
@@ -1685,8 +1729,9 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   }
   CUtensorMap tm_q, tm_o;
   if (!make_map(&tm_q, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb)) return cudaErrorInvalidValue;
-  if (STATS) tm_o = tm_q;
-  else if (!make_map(&tm_o, p.out, p.H * D, p.L, p.B, p.o_sl, p.o_sb)) return cudaErrorInvalidValue;
+  if (STATS) {
+    if (!make_map_k(&tm_o, p.k, p.H * D, p.S, p.B, p.k_ss, p.k_sb)) return cudaErrorInvalidValue;  // pass 1: K's map
+  } else if (!make_map(&tm_o, p.out, p.H * D, p.L, p.B, p.o_sl, p.o_sb)) return cudaErrorInvalidValue;
   p.n_hg = (p.H + C::G - 1) / C::G;
   p.n_sl = (p.L + C::ROWS - 1) / C::ROWS;
   p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
