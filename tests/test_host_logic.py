@@ -108,3 +108,29 @@ def test_sampler_and_region_entry_points_refuse_cpu():
         encode_region_map_sp(None, None, SimpleNamespace(down_blocks=[0]), 64, 64, text_ids=[np.array([1]), np.array([1])],
                              device="cpu")
     assert encode_region_map_sp(None, None, None, 64, 64, text_ids=None).numel() == 0  # reference :22-23
+
+
+def test_region_map_layouts_keep_the_reference_values():
+    """padded_region_map / compact_region_map are pure re-layouts of the reference's [B', L, n_tok] tensor (no GPU needed)."""
+    import torch
+
+    from diffusionspatialcontrol_b200 import compact_region_map, padded_region_map
+    from diffusionspatialcontrol_b200.attention import _region_layout_ok
+
+    from .helpers import synthetic_w
+
+    W = synthetic_w(2, 96, 77)
+    P = padded_region_map(W)
+    assert P.shape == W.shape and P.stride() == (96 * 80, 80, 1) and torch.equal(P, W) and _region_layout_ok(P)
+    assert padded_region_map(P) is P  # already in the fast layout: returned as is
+    Wc, cols = compact_region_map(W)
+    assert cols == [1, 2, 3, 6] and Wc.shape == (2, 96, 20) and Wc.is_contiguous()
+    assert torch.equal(Wc[:, :, :4], W[:, :, cols]) and not Wc[:, :, 4:].any()
+    zc, zcols = compact_region_map(torch.zeros(1, 8, 77))
+    assert zcols == [] and not zc.any()  # regions off: nothing weighted
+    many = torch.zeros(1, 8, 77)
+    many[0, 0, :17] = 1.0
+    assert compact_region_map(many) is None  # more than 16 weighted columns: no compact form
+    long = synthetic_w(1, 32, 154)
+    PL = padded_region_map(long)
+    assert PL.stride(1) == 160 and torch.equal(PL, long) and _region_layout_ok(PL)
