@@ -1193,17 +1193,19 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
       const bool active = h < it0.nheads;
       const int first = r0 + ((par - (r0 % PAR)) + PAR) % PAR;  // first tile of this warpgroup's parity in the run
       // Q row of head h of tile i -> TMEM (first D/2 (+4 zero) columns of the O region)
-      auto store_q = [&](int i) {  // smem -> registers -> tcgen05.st (not yet waited for)
+      constexpr int QWN = D == 40 ? 24 : 40;
+      auto load_q = [&](int i, uint32_t (&qw)[QWN]) {  // Q row of head h of tile i: shared memory -> registers
         const int s = i % NST;
         const unsigned char* qtile = smem + KV_BYTES + s * STAGE_BYTES;
         MBAR_WAIT(b_full + 8 * s, (i / NST) & 1, 6);
         TRACE(5);
-        uint32_t qw[D == 40 ? 24 : 40];
 #pragma unroll
         for (int c = 0; c < C::DCH; ++c) {
           const uint4 v = *reinterpret_cast<const uint4*>(qtile + chunk_off(h * C::DCH + c));
           qw[4 * c] = v.x; qw[4 * c + 1] = v.y; qw[4 * c + 2] = v.z; qw[4 * c + 3] = v.w;
         }
+      };
+      auto put_q = [&](uint32_t (&qw)[QWN]) {  // registers -> tcgen05.st (not yet waited for)
         if constexpr (D == 40) {
           qw[20] = qw[21] = qw[22] = qw[23] = 0u;  // zero K padding of the odd half k-step
           const uint32_t qa = tw + O_COL + (QDB ? (n_q & 1) * 24 : 0);
@@ -1221,6 +1223,11 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
         arrive(b_qrdy + 8 * g);
         TRACE(6);
         if constexpr (STATS) arrive(b_odone + 8 * (i % NST));  // pass 1 only reads Q
+      };
+      auto store_q = [&](int i) {
+        uint32_t qw[QWN];
+        load_q(i, qw);
+        put_q(qw);
       };
       auto stage_q = [&](int i) {
         store_q(i);
@@ -1406,7 +1413,50 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
           tc_fence_before();
           arrive(b_prdy + 8 * g);
           TRACE(16);
-          // ---- O row, one 40-column half at a time
+          auto o_chunk = [&](const float* oc8, float inv_, int chunk) {  // 8 O columns -> 16 bytes of the row in smem
+            float t[8];
+            fmul2(t[0], t[1], oc8[0], oc8[1], inv_, inv_);
+            fmul2(t[2], t[3], oc8[2], oc8[3], inv_, inv_);
+            fmul2(t[4], t[5], oc8[4], oc8[5], inv_, inv_);
+            fmul2(t[6], t[7], oc8[6], oc8[7], inv_, inv_);
+            uint4 v;
+            v.x = Mma<T>::pack(t[0], t[1]);
+            v.y = Mma<T>::pack(t[2], t[3]);
+            v.z = Mma<T>::pack(t[4], t[5]);
+            v.w = Mma<T>::pack(t[6], t[7]);
+            *reinterpret_cast<uint4*>(qtile + chunk_off(chunk)) = v;
+          };
+          if constexpr (PAR == 1) {
+            // D = 40.  The next tile's Q row leaves shared memory while the tensor core multiplies P V (the scores and P
+            // are dead: registers are free).  O is read in pieces: columns 0..23 (where the Q operand lives) and the ones
+            // column first, then the Q row goes to TMEM -- its Q K^T starts -- and only then columns 24..39.
+            uint32_t qnext[QWN];
+            load_q(has_next ? i + 1 : i, qnext);  // (unconditional: this tile's own stage when there is no next tile)
+            MBAR_WAIT(b_ordy + 8 * g, n_o & 1, 5);
+            ++n_o;
+            TRACE(17);
+            tc_fence_after();
+            float oa[24], oz[4];
+            tmem_ld_x16(tw + O_COL, reinterpret_cast<uint32_t*>(oa));
+            tmem_ld_x8(tw + O_COL + 16, reinterpret_cast<uint32_t*>(oa) + 16);
+            tmem_ld_x4(tw + O_COL + 40, reinterpret_cast<uint32_t*>(oz));
+            tc_wait_ld();
+            const float inv1 = 1.f / oz[0];  // the ones column: softmax row sum of the rounded P
+            tc_fence_before();
+            if (has_next) {
+              put_q(qnext);
+              publish_q(i + 1);
+            }
+            o_chunk(oa, inv1, h * C::DCH);
+            o_chunk(oa + 8, inv1, h * C::DCH + 1);
+            o_chunk(oa + 16, inv1, h * C::DCH + 2);
+            float ob[16];
+            tmem_ld_x16(tw + O_COL + 24, reinterpret_cast<uint32_t*>(ob));
+            tc_wait_ld();
+            tc_fence_before();
+            o_chunk(ob, inv1, h * C::DCH + 3);
+            o_chunk(ob + 8, inv1, h * C::DCH + 4);
+          } else {
           float inv = 0.f;
 #pragma unroll
           for (int j = 0; j < NH; ++j) {
@@ -1439,6 +1489,7 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
               v.w = Mma<T>::pack(oc[6], oc[7]);
               *reinterpret_cast<uint4*>(qtile + chunk_off(h * C::DCH + j * 5 + c)) = v;
             }
+          }
           }
           TRACE(18);
           fence_proxy_async();
