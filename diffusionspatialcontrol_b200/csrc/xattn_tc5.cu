@@ -949,7 +949,8 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
                  b_prdy = b_qrdy + 64, b_ordy = b_qrdy + 96;
   const uint32_t b_beta = b_qrdy + 128;  // single-launch form: "the std of this call has been published" (grid barrier)
   const uint32_t b_kfull = b_qrdy + 136;  // pass 1: the K head group has landed (staged by TMA, see issue_k)
-  static_assert(16 * NST + 128 + 16 <= 240, "barrier area");
+  const uint32_t b_prdy2 = b_qrdy + 144;  // pass 2: second part of P (keys 48..79) is in TMEM, one barrier per warpgroup
+  static_assert(16 * NST + 128 + 16 + 32 <= 240, "barrier area");
   // Pass 1 stages K with the TMA itself: one box of 8 columns x 80 keys per (head, 16-byte chunk) IS the UMMA K-major
   // layout [chunk][key][16 B] (keys >= S arrive as zeros); 20 such boxes on one barrier stream at about a row per clock
   // (profiles/r1_tma_copy_rate.jsonl) with no thread work.  (Pass 2 cannot: V must be transposed and, with the compact
@@ -1042,6 +1043,7 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
       mbar_init(b_qrdy + 8 * g, warp_arrive ? 4 : 128);
       mbar_init(b_srdy + 8 * g, 1);
       mbar_init(b_prdy + 8 * g, warp_arrive ? 4 : 128);
+      mbar_init(b_prdy2 + 8 * g, warp_arrive ? 4 : 128);
       mbar_init(b_ordy + 8 * g, 1);
     }
     if constexpr (STATS) mbar_init(b_kfull, 1);
@@ -1116,7 +1118,7 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
       constexpr uint32_t idesc_pv = idesc_f16<T>(48);
       const uint32_t tw = tmem_base + g * WG_COLS;
       const uint64_t kdesc = smem_desc(s0 + h * C::K_HEAD_BYTES, C::K_CH_BYTES, 128);
-      uint32_t nq = 0, np = 0;
+      uint32_t nq = 0, np = 0, np2 = 0;
       for (int i = 0; i < n_items; ++i) {
         if (PAR > 1 && (i % PAR) != par) continue;
         const Item it = decode<D>(begin + i, p);
@@ -1139,8 +1141,18 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
             ++np;
             TRACE(24);
             tc_fence_after();
+            // P arrives in two parts (keys 0..47, then 48..79): the first three k-steps are multiplied while the consumers
+            // still exponentiate the rest.  (The second V half of D = 80 finds all of P in place.)
 #pragma unroll
-            for (int kk = 0; kk < 5; ++kk)
+            for (int kk = 0; kk < 3; ++kk)
+              umma_ts(tw + O_COL, tw + S_COL + kk * 8, vdesc + static_cast<uint64_t>((kk * 2 * TC<40>::VT_CH_BYTES) >> 4), idesc_pv, kk);
+            if (j == 0) {
+              if (issuer_spin) mbar_wait(b_prdy2 + 8 * g, np2 & 1); else mbar_wait_relaxed(b_prdy2 + 8 * g, np2 & 1);
+              ++np2;
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int kk = 3; kk < 5; ++kk)
               umma_ts(tw + O_COL, tw + S_COL + kk * 8, vdesc + static_cast<uint64_t>((kk * 2 * TC<40>::VT_CH_BYTES) >> 4), idesc_pv, kk);
             tc_commit(b_ordy + 8 * g);
             TRACE(25);
@@ -1324,8 +1336,21 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
               if (j < 8) ffma2(e0, e1, sc[2 * j], sc[2 * j + 1], ce, ce, nb, nb);
               else ffma2(e0, e1, sc[2 * j], sc[2 * j + 1], k2, k2, nb, nb);
               pw[j] = j < 38 ? Mma<T>::pack(ex2_approx(e0), ex2_approx(e1)) : Mma<T>::pack(ex2_approx(e0), 0.f);
+              if (j == 23) {  // keys 0..47 are done: publish them, the tensor core starts on P V
+                TRACE(14);
+                tmem_st_x16(tw + S_COL, pw);
+                tmem_st_x8(tw + S_COL + 16, pw + 16);
+                tc_wait_st();
+                tc_fence_before();
+                arrive(b_prdy + 8 * g);
+              }
             }
             pw[39] = 0u;
+            tmem_st_x16(tw + S_COL + 24, pw + 24);
+            tc_wait_st();
+            tc_fence_before();
+            arrive(b_prdy2 + 8 * g);
+            TRACE(16);
           } else if (w_fast && beta_l2 > 1e-20f) {
             // x = beta * y with y = s * (scale/beta) + W: the row max is taken on y, 2^(x - max) = 2^(beta*y - beta*ymax)
             const float4* wt4 = reinterpret_cast<const float4*>(qtile + C::QT_BYTES + row * (X::W_SMEM_PITCH * 4));
@@ -1406,13 +1431,16 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
           }
           // (ex2.approx.f16x2 was tried to halve the MUFU work: on sm_100a it lowers to two MUFU.EX2.F16 plus
           //  repacking, i.e. more issue slots for the same MUFU count -- measured slower)
-          TRACE(14);
-          tmem_st_x32(tw + S_COL, pw);  // P over the first 40 columns of S (the whole S row is in registers)
-          tmem_st_x8(tw + S_COL + 32, pw + 32);
-          tc_wait_st();
-          tc_fence_before();
-          arrive(b_prdy + 8 * g);
-          TRACE(16);
+          if constexpr (!CW) {
+            TRACE(14);
+            tmem_st_x32(tw + S_COL, pw);  // P over the first 40 columns of S (the whole S row is in registers)
+            tmem_st_x8(tw + S_COL + 32, pw + 32);
+            tc_wait_st();
+            tc_fence_before();
+            arrive(b_prdy + 8 * g);
+            arrive(b_prdy2 + 8 * g);
+            TRACE(16);
+          }
           auto o_chunk = [&](const float* oc8, float inv_, int chunk) {  // 8 O columns -> 16 bytes of the row in smem
             float t[8];
             fmul2(t[0], t[1], oc8[0], oc8[1], inv_, inv_);
@@ -1549,7 +1577,7 @@ __device__ __forceinline__ uint32_t x4_phase(const XattnParams& p, const CUtenso
   CTA_TIME(1);
   if constexpr (MODE == 1) {
     if (tid == 0)  // this phase's barrier words become ring-stage bytes of the next phase
-      for (int i = 0; i < 2 * NST + 18; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + 8 * i) : "memory");
+      for (int i = 0; i < 2 * NST + 22; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + 8 * i) : "memory");
   } else {
     if (warp == 16) {
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
