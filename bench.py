@@ -224,6 +224,9 @@ def attention_roofline(device):
         "avg_ms_stats_alone": d["ms_stats"], "avg_ms_forward_alone": d["ms_forward"],
         "all_16_layers": {"bytes_per_unet_step": tot_b, "ms_per_unet_step": tot_t,
                           "achieved": tot_b / (tot_t * 1e-3) / 1e9, "frac": tot_b / (tot_t * 1e-3) / 1e9 / peak},
+        "per_shape": {f"{L}x{D}": {"ms_call": v["ms_call"], "bytes": v["bytes"], "launches": lib_launches(B, H, L, D, S),
+                                   "frac": v["bytes"] / (v["ms_call"] * 1e-3) / 1e9 / peak}
+                      for (L, D), v in sorted(per_shape.items(), reverse=True)},
         "l2": "flushed before every timed call (512 MiB write, then a 256 MiB read so that L2 holds clean lines); two input "
               "sets alternate, so no timed call reads buffers the previous one touched; 10 warm-up calls",
     }
