@@ -8,20 +8,28 @@
 //
 // Work unit = tile of 128 query rows x one head group (G*D = 160 columns: 4 heads at D=40, 2 at D=80).
 // One persistent CTA per SM owns a contiguous range of the (batch, head-group)-major tile list.
-//   warp 8        producer : TMA tensor-map loads (cp.async.bulk.tensor, 64B-swizzled 32-column boxes) of the Q
-//                            tile + one bulk copy of the W tile into a 2/3-stage smem ring, tensor-map stores of
-//                            finished O tiles.  (Measured, profiles/r1_tma_copy_rate.jsonl: a 1-D bulk copy costs
-//                            ~30 ns of TMA issue per SM whatever its size, so per-row copies cap at 1.6-3 TB/s;
-//                            one box instruction per 8 KB streams at > 5.5 TB/s.)
-//   warp 9        MMA      : one elected thread issues tcgen05.mma (M=128, N=80 for S=QK^T; N=48/80 for O=PV),
-//                            tcgen05.commit -> mbarrier
-//   warps 0-3/4-7 two consumer warpgroups, ONE THREAD PER QUERY ROW (TMEM lane = row); warpgroup g takes the
-//                 heads h = g (mod 2) of the tile, so QK^T/PV of one head overlaps the softmax of the other:
-//                   Q_h row: smem -> registers -> tcgen05.st (A operand lives in TMEM)
-//                   S row  : tcgen05.ld 80 fp32 -> + beta*W row (registers, shared by the heads) -> max / exp2 /
-//                            sum entirely in-thread (no shuffles) -> P (fp16/bf16) -> tcgen05.st over S (A of PV)
-//                   O row  : tcgen05.ld -> * 1/sum -> overwrite the Q_h columns of the row in smem
-// K_h and V_h^T of the head group stay resident in shared memory in the UMMA canonical K-major no-swizzle
+//
+// Two kernel organisations live in this file:
+//   * xattn_tc5x4_* (default): FOUR consumer warpgroups, one head each, 640 threads -- see the block comment above
+//     x4_phase() for the roles, the TMEM column budget, the compact region map (keys permuted so that the weighted
+//     columns come first, 80-byte W rows, 3-stage ring), K staged by TMA in pass 1, the two-part publication of P, the
+//     piecewise O read, programmatic dependent launch, and the opt-in single-launch form of both passes.
+//   * xattn_tc5_kernel (DSC_TC5_VARIANT=x2, kept for A/B runs): TWO consumer warpgroups that alternate heads with
+//     software pipelining:
+//       warp 8        producer : TMA tensor-map loads (cp.async.bulk.tensor, 64B-swizzled 32-column boxes) of the Q
+//                                tile + one bulk copy of the W tile into a 2/3-stage smem ring, tensor-map stores of
+//                                finished O tiles.  (Measured, profiles/r1_tma_copy_rate.jsonl: a 1-D bulk copy costs
+//                                ~30 ns of TMA issue per SM whatever its size, so per-row copies cap at 1.6-3 TB/s;
+//                                boxes stream at > 5 TB/s.)
+//       warps 9, 10   MMA      : one elected thread per warpgroup issues tcgen05.mma (M=128, N=80 for S=QK^T; N=48/96
+//                                for O=PV), tcgen05.commit -> mbarrier
+//       warps 0-3/4-7 consumers: ONE THREAD PER QUERY ROW (TMEM lane = row); warpgroup g takes the heads h = g (mod 2)
+//                     of the tile, so QK^T/PV of one head overlaps the softmax of the other:
+//                       Q_h row: smem -> registers -> tcgen05.st (A operand lives in TMEM)
+//                       S row  : tcgen05.ld 80 fp32 -> + beta*W row (registers, shared by the heads) -> max / exp2 /
+//                                sum entirely in-thread (no shuffles) -> P (fp16/bf16) -> tcgen05.st (A of PV)
+//                       O row  : tcgen05.ld -> * 1/sum -> overwrite the Q_h columns of the row in smem
+// In both, K_h and V_h^T of the head group stay resident in shared memory in the UMMA canonical K-major no-swizzle
 // layout (8-row x 16-byte core matrices; chunk pitch = LBO, 128 B between 8-row groups = SBO); the odd half
 // k-step of D=40 multiplies an explicit zero chunk.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
