@@ -830,6 +830,13 @@ xattn_tc5_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, 
 // (A fifth service warp does not fit: 21 warps x 96 registers cannot be launched -- registers are handed out per
 //  4-warp group -- and tensor-core issue from the consumer warps themselves measured 10 % slower: five tcgen05.mma
 //  plus the commit keep the issuing warp busy for 400-600 cycles per batch.)
+// Region map W, three forms: compact (CW = true; what the processor passes: only the <= 16 weighted key columns, 80 B
+// per query row, keys permuted at K / V^T staging so that they are slots 0..15, 3-stage ring), padded dense (rows 80
+// floats apart, one 84 x 128 TMA box per tile, 128-bit reads), dense (the reference's pitch-77 tensor: bulk copy, scalar
+// reads).  Pass 1 stages K by TMA (one 8-column x 80-key box per UMMA chunk column); pass 2 stages K and V^T with the
+// consumer threads (transpose + key permutation).  P is published in two parts (keys 0..47 | 48..79) so that P V starts
+// under the last exponentials; at D = 40 the next tile's Q row is fetched into registers during P V and goes to TMEM
+// after a partial O read.  Pass 1 -> pass 2 (and predecessor -> pass 1) are programmatic dependent launches.
 #ifndef DSC_POLY_PATTERN
 #define DSC_POLY_PATTERN 0x00  // bit i: key pairs with (pair & 7) == i take the polynomial 2^x below (0 = all on MUFU)
 #endif
