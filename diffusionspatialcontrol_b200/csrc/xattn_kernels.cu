@@ -219,12 +219,10 @@ __device__ __forceinline__ void publish_stats(const XattnParams& p, double dsum,
       p.ws->sumsq = sumsq;
       p.ws->n = n;
       p.ws->n_partials = n_fold;
-      __threadfence();
-      p.ws->ticket = 0u;  // reusable without a memset
-      if (signal_epoch) {
-        __threadfence();
+      p.ws->ticket = 0u;  // reusable without a memset (its next use is in a later kernel: no ordering needed here)
+      __threadfence();    // the statistics above are visible before ...
+      if (signal_epoch)   // ... the barrier of the single-launch kernel opens
         atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(p.ws) + kEpochOffset), 1u);
-      }
     }
   }
 }
