@@ -46,6 +46,7 @@ class RegionAttnProcessor:
         self._w_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
         self._w_zero: dict = {}
         self._w_compact: dict = {}
+        self._static_maps: dict = {}
         self.skip_zero_maps = skip_zero_maps
         self._max_cached_maps = max_cached_maps
         self._checked_funcs: dict = {}
@@ -53,7 +54,22 @@ class RegionAttnProcessor:
         self._kv_cache: dict = {}
 
     # -- small caches (all keyed so that a changed tensor is never served stale) ----------------
+    def register_static_map(self, w: torch.Tensor, compact=None, zero: bool = False) -> None:
+        """A region map that lives in a STATIC device buffer whose contents are rewritten in place between calls (CUDA-graph
+        replay): it is used exactly as given -- no re-layout copy, no content inspection -- together with the compact
+        form ``(Wc, cols)`` (also a static buffer; the column list is baked into a captured graph) and the "all zero" verdict
+        stated here.  ``w`` must already be in the padded device layout (``padded_region_map``)."""
+        if not w.is_cuda or w.dtype != torch.float32 or padded_region_map(w) is not w:
+            raise ValueError("a static region map must be a padded fp32 device tensor (see padded_region_map)")
+        self._static_maps[w.data_ptr()] = (w, compact, bool(zero))
+
+    def _static_entry(self, w: torch.Tensor):
+        hit = self._static_maps.get(w.data_ptr()) if self._static_maps else None
+        return hit if hit is not None and hit[0] is w else None
+
     def _device_map(self, w: torch.Tensor, device: torch.device) -> torch.Tensor:
+        if self._static_entry(w) is not None:
+            return w
         key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype, str(device))
         hit = self._w_cache.get(key)
         if hit is not None and hit[0] is w:
@@ -79,9 +95,15 @@ class RegionAttnProcessor:
         return dev
 
     def _map_compact(self, w: torch.Tensor, device: torch.device):
+        st = self._static_entry(w)
+        if st is not None:
+            return st[1]
         return self._w_compact.get((w.data_ptr(), w._version, tuple(w.shape), w.dtype, str(device)))
 
     def _map_is_zero(self, w: torch.Tensor, device: torch.device) -> bool:
+        st = self._static_entry(w)
+        if st is not None:
+            return st[2]
         return self._w_zero.get((w.data_ptr(), w._version, tuple(w.shape), w.dtype, str(device)), False)
 
     def _check_weight_func(self, fn: Callable) -> None:

@@ -12,6 +12,7 @@ from typing import Dict, List, Optional
 
 import torch
 
+from .attention import compact_region_map, padded_region_map
 from .attention_processor import RegionAttnProcessor
 from .region_map import encode_region_map
 from .sampler import KarrasSchedule, dpmpp2m_step
@@ -63,9 +64,16 @@ class RegionTxt2ImgPipeline:
         per cross-attention layer included) for a given batch shape.  Launch-bound glue (hundreds of small PyTorch
         kernels per step) is replayed with one graph launch; our kernels are capture-safe (no host sync, workspace
         pre-allocated, tensor maps passed by value)."""
-        key = (n, height, width, self.dtype, tuple(sorted(region_state.keys())))
+        # The region maps live in static buffers in the layout the kernels read (padded rows + compact form); what a
+        # captured graph bakes in -- which key columns carry weights, or that a map is all zero (plain SDPA) -- is part
+        # of the graph's key, so another prompt layout captures another graph instead of replaying a wrong one.
+        compacts = {L: compact_region_map(w) for L, w in region_state.items()}
+        sig = tuple((L, tuple(w.shape), None if compacts[L] is None else tuple(compacts[L][1]))
+                    for L, w in sorted(region_state.items()))
+        key = (n, height, width, self.dtype, sig)
         st = self._graphs.get(key)
         if st is not None:
+            st["compacts"] = compacts
             return st
         dev, dt = self.device, self.dtype
         st = {
@@ -73,8 +81,16 @@ class RegionTxt2ImgPipeline:
             "t": torch.zeros((), device=dev, dtype=torch.float32),
             "sigma": torch.zeros((), device=dev, dtype=torch.float32),
             "ctx": torch.zeros((2 * n, 77, self.unet_ctx_dim()), device=dev, dtype=dt),
-            "rs": {L: torch.zeros_like(w, device=dev, dtype=torch.float32) for L, w in region_state.items()},
+            "rs": {L: padded_region_map(torch.zeros(tuple(w.shape), device=dev, dtype=torch.float32))
+                   for L, w in region_state.items()},
+            "rsc": {L: (None if c is None else torch.zeros_like(c[0])) for L, c in compacts.items()},
+            "compacts": compacts,
         }
+        for L in region_state:
+            c = compacts[L]
+            self.processor.register_static_map(
+                st["rs"][L], compact=None if c is None else (st["rsc"][L], list(c[1])),
+                zero=c is not None and len(c[1]) == 0)
         rp = {"region_state": st["rs"], "sigma": st["sigma"], "weight_func": weight_func}
         kw = {"region_prompt": rp}
         side = torch.cuda.Stream(device=dev)
@@ -121,6 +137,8 @@ class RegionTxt2ImgPipeline:
             st["ctx"].copy_(ctx)
             for L, w in region_state.items():
                 st["rs"][L].copy_(w)
+                if st["rsc"][L] is not None:
+                    st["rsc"][L].copy_(st["compacts"][L][0])
             unet_in = st["x"]
             unet_in.copy_(torch.cat([x, x]).mul_(sched.c_in(0)))
             for i in range(num_inference_steps):
