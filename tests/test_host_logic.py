@@ -134,3 +134,13 @@ def test_region_map_layouts_keep_the_reference_values():
     long = synthetic_w(1, 32, 154)
     PL = padded_region_map(long)
     assert PL.stride(1) == 160 and torch.equal(PL, long) and _region_layout_ok(PL)
+
+
+def test_static_region_maps_must_be_padded_device_tensors():
+    import torch
+
+    from diffusionspatialcontrol_b200 import RegionAttnProcessor
+
+    proc = RegionAttnProcessor()
+    with pytest.raises(ValueError):
+        proc.register_static_map(torch.zeros(1, 8, 77))  # CPU / dense: would be copied at first use, i.e. frozen in a graph
