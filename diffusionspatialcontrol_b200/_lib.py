@@ -15,6 +15,8 @@ MAX_KEYS = 80
 ERR_INVALID_ARGUMENT, ERR_UNSUPPORTED, ERR_LAYOUT, ERR_SHAPE = -1, -2, -3, -4
 
 # symbol -> (restype, argtypes); kept in the order of include/dsc_b200.h
+PASS_STATS, PASS_FORWARD, PASS_BOTH = 1, 2, 3
+
 SIGNATURES = {
     "dsc_version": (c_int, []),
     "dsc_last_error": (c_char_p, []),
@@ -43,6 +45,18 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), c_void_p, c_int,
          c_int, c_void_p, c_float, c_void_p, c_void_p, POINTER(c_int64)]
         + [c_int] * 5 + [c_float, c_int, c_void_p],
+    ),
+    "dsc_xattn_prepared_supported": (c_int, [c_int] * 3),
+    "dsc_xattn_kv_image_bytes": (c_int, [c_int] * 4 + [POINTER(c_size_t)]),
+    "dsc_xattn_prepare_kv": (
+        c_int,
+        [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int, POINTER(ctypes.c_int32)]
+        + [c_int] * 5 + [c_void_p, c_void_p],
+    ),
+    "dsc_xattn_call_prepared": (
+        c_int,
+        [c_void_p, POINTER(c_int64), c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,
+         POINTER(c_int64)] + [c_int] * 5 + [c_float, c_int, c_int, c_void_p],
     ),
     "dsc_region_downsample": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]),
     "dsc_region_accumulate": (

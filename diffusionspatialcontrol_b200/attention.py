@@ -42,6 +42,36 @@ def get_workspace(device: torch.device, nbytes: int = 0) -> torch.Tensor:
     return ws
 
 
+def _checked_workspace(workspace: Optional[torch.Tensor], device: torch.device, need: int) -> torch.Tensor:
+    """The kernels always write the 64-byte header and their per-CTA partials: a caller-supplied workspace is checked
+    against ``dsc_xattn_workspace_bytes`` for EVERY call (not only long prompts), plus dtype / device / alignment.  It
+    must have been zero-filled once after allocation (the ticket word returns to 0 after each call)."""
+    if workspace is None:
+        return get_workspace(device, need)
+    if workspace.dtype != torch.uint8 or not workspace.is_cuda or workspace.device != device or not workspace.is_contiguous():
+        raise ValueError(f"workspace must be a contiguous uint8 tensor on {device}")
+    if workspace.numel() < need:
+        raise ValueError(f"workspace too small: {workspace.numel()} < {need} bytes (dsc_xattn_workspace_bytes)")
+    if workspace.data_ptr() % 16 != 0:
+        raise ValueError("workspace must be 16-byte aligned")
+    return workspace
+
+
+def _sigma_args(sigma, device: torch.device):
+    """(device pointer | None, host value, keep-alive).  A device sigma is passed by address (no host sync).  A host
+    sigma is passed by value -- which a CUDA-graph capture would freeze into the kernel parameters, so every replay
+    would reuse the capture-time sigma: refused while the stream is capturing."""
+    if isinstance(sigma, torch.Tensor) and sigma.is_cuda:
+        if sigma.dtype != torch.float32 or sigma.device != device:
+            sigma = sigma.to(device=device, dtype=torch.float32)
+        keep = sigma.reshape(-1)
+        return keep.data_ptr(), 0.0, keep
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("sigma must be a CUDA tensor while a CUDA graph is being captured: a host value would be "
+                           "frozen into the captured kernel parameters and every replay would reuse it")
+    return None, float(sigma), None
+
+
 def _as_bhxd(x: torch.Tensor, name: str) -> torch.Tensor:
     """Return x ([B,H,rows,D]) in the layout the kernels stream: a view of [B, rows, H*D]."""
     if x.dim() != 4:
@@ -76,7 +106,7 @@ def score_stats(query: torch.Tensor, key: torch.Tensor, scale: Optional[float] =
     B, H, L, D = q.shape
     S = k.shape[2]
     scale = 1.0 / math.sqrt(D) if scale is None else float(scale)
-    ws = get_workspace(q.device) if workspace is None else workspace
+    ws = _checked_workspace(workspace, q.device, workspace_bytes(B, H, L, D, S))
     with torch.cuda.device(q.device):
         check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), _I64x4(*q.stride()), _I64x4(*k.stride()), None,
                                   B, H, L, D, S, scale, _DTYPES[q.dtype], ws.data_ptr(), _stream_ptr(q.device)))
@@ -177,23 +207,9 @@ def region_attention(
     if W.dtype != torch.float32 or W.device != q.device or not _region_layout_ok(W):
         W = padded_region_map(W.to(device=q.device, dtype=torch.float32))
     scale = 1.0 / math.sqrt(D) if scale is None else float(scale)
-    need = workspace_bytes(B, H, L, D, S) if S > MAX_KEYS else 0
-    ws = get_workspace(q.device, need) if workspace is None else workspace
-    if ws.numel() < need:
-        raise ValueError(f"workspace too small for S={S} keys: {ws.numel()} < {need} bytes")
+    ws = _checked_workspace(workspace, q.device, workspace_bytes(B, H, L, D, S))
     out = torch.empty((B, L, H * D), dtype=q.dtype, device=q.device)
-
-    sigma_ptr, sigma_host = None, 0.0
-    if isinstance(sigma, torch.Tensor):
-        if sigma.is_cuda:  # never .item() a device sigma: pass its address
-            if sigma.dtype != torch.float32 or sigma.device != q.device:
-                sigma = sigma.to(device=q.device, dtype=torch.float32)
-            sigma_keepalive = sigma.reshape(-1)
-            sigma_ptr = sigma_keepalive.data_ptr()
-        else:
-            sigma_host = float(sigma)
-    else:
-        sigma_host = float(sigma)
+    sigma_ptr, sigma_host, _sigma_keepalive = _sigma_args(sigma, q.device)  # never .item() a device sigma
 
     dt = _DTYPES[q.dtype]
     st = _stream_ptr(q.device)
@@ -212,4 +228,83 @@ def region_attention(
         check(lib.dsc_xattn_call_cw(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), W.shape[0],
                                     W.stride(1), wc_ptr, n_act, cols_arr, sigma_ptr, sigma_host, ws.data_ptr(),
                                     out.data_ptr(), _I64x3(*out.stride()), B, H, L, D, S, scale, dt, st))
+    return out.view(B, L, H, D).transpose(1, 2)
+
+
+# ---- prepared K / V (the fast form for the SD-1.5 shapes) ---------------------------------------------------------------
+class PreparedKV:
+    """K and V of one cross-attention layer laid out ONCE as the shared-memory image the tcgen05 kernels multiply from
+    (``dsc_xattn_prepare_kv``).  They are projections of the text embeddings and do not change during a generation
+    (reference attention_modify.py:465-466 recomputes the same ``to_k`` / ``to_v`` on each of the 25 steps).  The image
+    bakes in the active-column list of the compact region map it is used with."""
+
+    __slots__ = ("image", "cols", "B", "H", "D", "S", "dtype")
+
+    def __init__(self, image, cols, B, H, D, S, dtype):
+        self.image, self.cols, self.B, self.H, self.D, self.S, self.dtype = image, tuple(cols), B, H, D, S, dtype
+
+
+def prepared_supported(H: int, D: int, S: int, n_active: int) -> bool:
+    return 1 <= n_active <= MAX_COMPACT_COLS and bool(lib.dsc_xattn_prepared_supported(H, D, S))
+
+
+def kv_image_bytes(B: int, H: int, D: int, S: int) -> int:
+    n = ctypes.c_size_t(0)
+    check(lib.dsc_xattn_kv_image_bytes(B, H, D, S, ctypes.byref(n)))
+    return int(n.value)
+
+
+def prepare_kv(key: torch.Tensor, value: torch.Tensor, cols, out: Optional[torch.Tensor] = None) -> PreparedKV:
+    """key, value: [B, H, S, D] (views of the [B, S, H*D] projections); cols: ascending active key columns of the compact
+    region map (``compact_region_map(W)[1]``).  ``out``: optional uint8 device buffer to (re)fill in place (static buffers
+    of a captured CUDA graph).  Asynchronous on the current stream."""
+    _check_inputs(key, value)
+    k, v = _as_bhxd(key, "key"), _as_bhxd(value, "value")
+    B, H, S, D = k.shape
+    cols = [int(c) for c in cols]
+    nbytes = kv_image_bytes(B, H, D, S)
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=k.device)
+    elif out.dtype != torch.uint8 or out.device != k.device or out.numel() < nbytes or not out.is_contiguous():
+        raise ValueError(f"kv image buffer must be a contiguous uint8 tensor of >= {nbytes} bytes on {k.device}")
+    cols_arr = (ctypes.c_int32 * max(1, len(cols)))(*cols)
+    with torch.cuda.device(k.device):
+        check(lib.dsc_xattn_prepare_kv(k.data_ptr(), v.data_ptr(), _I64x4(*k.stride()), _I64x4(*v.stride()), len(cols),
+                                       cols_arr, B, H, D, S, _DTYPES[k.dtype], out.data_ptr(), _stream_ptr(k.device)))
+    return PreparedKV(out, cols, B, H, D, S, k.dtype)
+
+
+def region_attention_prepared(
+    query: torch.Tensor,  # [B, H, L, D]
+    kv: PreparedKV,
+    compact,  # (Wc fp32 [B', L, 20], cols) from compact_region_map; cols must equal kv.cols
+    sigma: Union[float, torch.Tensor],
+    scale: Optional[float] = None,
+    workspace: Optional[torch.Tensor] = None,
+    passes: int = _lib.PASS_BOTH,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """``region_attention`` on a prepared K / V image: same result, K / V^T fetched with one bulk copy per CTA."""
+    if not query.is_cuda or query.dtype not in _DTYPES:
+        raise TypeError("query must be a float16 / bfloat16 CUDA tensor")
+    q = _as_bhxd(query, "query")
+    B, H, L, D = q.shape
+    Wc, cols = compact
+    if tuple(int(c) for c in cols) != kv.cols:
+        raise ValueError("the K/V image was prepared for another active-column list")
+    if (B, H, D) != (kv.B, kv.H, kv.D) or q.dtype != kv.dtype or kv.image.device != q.device:
+        raise ValueError("query does not match the prepared K/V image (batch / heads / head dim / dtype / device)")
+    if Wc.dim() != 3 or Wc.shape[1:] != (L, COMPACT_PITCH) or Wc.dtype != torch.float32 or not Wc.is_contiguous() \
+            or Wc.device != q.device or B % Wc.shape[0] != 0:
+        raise ValueError("compact region map must be a contiguous fp32 [B', L, 20] tensor on the query's device, B' | B")
+    scale = 1.0 / math.sqrt(D) if scale is None else float(scale)
+    ws = _checked_workspace(workspace, q.device, workspace_bytes(B, H, L, D, kv.S))
+    if out is None:
+        out = torch.empty((B, L, H * D), dtype=q.dtype, device=q.device)
+    sigma_ptr, sigma_host, _keep = _sigma_args(sigma, q.device)
+    with torch.cuda.device(q.device):
+        check(lib.dsc_xattn_call_prepared(q.data_ptr(), _I64x4(*q.stride()), kv.image.data_ptr(), Wc.data_ptr(), Wc.shape[0],
+                                          len(kv.cols), sigma_ptr, sigma_host, ws.data_ptr(), out.data_ptr(),
+                                          _I64x3(*out.stride()), B, H, L, D, kv.S, scale, _DTYPES[q.dtype], passes,
+                                          _stream_ptr(q.device)))
     return out.view(B, L, H, D).transpose(1, 2)

@@ -17,7 +17,8 @@ from typing import Callable, Optional
 import torch
 import torch.nn.functional as F
 
-from .attention import compact_region_map, padded_region_map, region_attention
+from .attention import (PreparedKV, compact_region_map, padded_region_map, prepare_kv, prepared_supported, region_attention,
+                        region_attention_prepared)
 
 
 def _is_reference_weight_func(fn: Callable) -> bool:
@@ -35,11 +36,15 @@ def _is_reference_weight_func(fn: Callable) -> bool:
 class RegionAttnProcessor:
     r"""B200-native replacement for the reference's ``AttnProcessor2_0``.
 
-    cache_kv: reuse ``to_k/to_v(encoder_hidden_states)`` while the same text-embedding tensor is passed
-    (numerically identical, the reference recomputes them on each of the 25 steps).
+    cache_kv: reuse ``to_k/to_v(encoder_hidden_states)`` -- and the K / V^T image the tcgen05 kernels multiply from
+    (``prepare_kv``) -- while the same text-embedding tensor (same object, same ``_version``) is passed (SURVEY 8f-1;
+    numerically identical: the reference recomputes the same projections on each of the 25 steps,
+    attention_modify.py:465-466).  With ``cache_kv=False`` the projections and the image are rebuilt on every call.
+    ``register_static_kv`` is the same for a captured CUDA graph: projections computed outside the graph into static
+    buffers that the replays read.
     """
 
-    def __init__(self, cache_kv: bool = False, max_cached_maps: int = 16, skip_zero_maps: bool = True):
+    def __init__(self, cache_kv: bool = True, max_cached_maps: int = 16, skip_zero_maps: bool = True):
         if not hasattr(F, "scaled_dot_product_attention"):
             raise ImportError("RegionAttnProcessor requires PyTorch 2.0")
         self.cache_kv = cache_kv
@@ -52,6 +57,13 @@ class RegionAttnProcessor:
         self._checked_funcs: dict = {}
         self._sigma_cache: Optional[tuple] = None
         self._kv_cache: dict = {}
+        self._kv_static: dict = {}
+        self._img_cache: dict = {}
+        # Statistics workspace handed to every region call (None: one zero-filled buffer per (device, stream), allocated
+        # on first use).  A CUDA-graph capture must set it to a buffer allocated OUTSIDE the capture: the per-stream
+        # lookup would allocate inside the capture (graph-private pool, a memset node in every replay, and one buffer
+        # shared by every graph captured on that stream).
+        self.workspace: Optional[torch.Tensor] = None
 
     # -- small caches (all keyed so that a changed tensor is never served stale) ----------------
     def register_static_map(self, w: torch.Tensor, compact=None, zero: bool = False) -> None:
@@ -131,7 +143,18 @@ class RegionAttnProcessor:
             return conv
         return float(sigma)
 
+    def register_static_kv(self, attn, ehs: torch.Tensor, key: torch.Tensor, value: torch.Tensor, images=None) -> None:
+        """K / V projections of ``attn`` for the text embeddings that live in the STATIC buffer ``ehs`` (rewritten in
+        place between CUDA-graph replays), themselves in static buffers the caller refreshes whenever it rewrites
+        ``ehs``: calls with exactly this ``ehs`` use them instead of running ``to_k`` / ``to_v`` (so a captured graph
+        holds no K/V GEMMs).  ``images``: optional ``{cols tuple: PreparedKV}`` of static K / V^T images, one per
+        active-column list of the region maps the layer is used with."""
+        self._kv_static[id(attn)] = (attn, ehs, key, value, dict(images or {}))
+
     def _project_kv(self, attn, ehs: torch.Tensor, args):
+        st = self._kv_static.get(id(attn)) if self._kv_static else None
+        if st is not None and st[0] is attn and st[1] is ehs:
+            return st[2], st[3]
         if not self.cache_kv:
             return attn.to_k(ehs, *args), attn.to_v(ehs, *args)
         key = id(attn)
@@ -142,11 +165,32 @@ class RegionAttnProcessor:
         self._kv_cache[key] = (ehs, ehs._version, k, v)
         return k, v
 
+    def _kv_image(self, attn, ehs: torch.Tensor, key: torch.Tensor, value: torch.Tensor, cols) -> PreparedKV:
+        """The K / V^T image of this layer for the active-column list ``cols``: static (CUDA graph), cached (same text
+        embeddings as last time) or rebuilt.  ``key`` / ``value`` are the [B, H, S, D] views of the projections."""
+        cols = tuple(int(c) for c in cols)
+        st = self._kv_static.get(id(attn)) if self._kv_static else None
+        if st is not None and st[0] is attn and st[1] is ehs and cols in st[4]:
+            return st[4][cols]
+        if not self.cache_kv:
+            return prepare_kv(key, value, cols)
+        ck = (id(attn), cols)
+        hit = self._img_cache.get(ck)
+        if hit is not None and hit[0] is ehs and hit[1] == ehs._version and hit[2].B == key.shape[0] and hit[2].dtype == key.dtype:
+            return hit[2]
+        img = prepare_kv(key, value, cols, out=None if hit is None or hit[2].B != key.shape[0] or hit[2].dtype != key.dtype
+                         else hit[2].image)
+        if len(self._img_cache) > 256:
+            self._img_cache.clear()
+        self._img_cache[ck] = (ehs, ehs._version, img)
+        return img
+
     def clear_caches(self) -> None:
         self._w_cache.clear()
         self._w_zero.clear()
         self._w_compact.clear()
         self._kv_cache.clear()
+        self._img_cache.clear()
         self._sigma_cache = None
 
     # -- processor protocol ---------------------------------------------------------------------
@@ -223,13 +267,24 @@ class RegionAttnProcessor:
                 hidden_states = F.scaled_dot_product_attention(
                     query, key, value, attn_mask=attention_mask, dropout_p=0.0, is_causal=False)
             else:
-                hidden_states = region_attention(
-                    query, key, value, w_dev,
-                    self._sigma_arg(sigma, query.device),
-                    attn_mask=attention_mask,
-                    scale=None,  # the reference always uses 1/sqrt(head_dim) here (:77), not attn.scale
-                    compact=self._map_compact(w, query.device),
-                )
+                compact = self._map_compact(w, query.device)
+                if (attention_mask is None and compact is not None and query.dtype in (torch.float16, torch.bfloat16)
+                        and prepared_supported(attn.heads, head_dim, key.shape[2], len(compact[1]))):
+                    # SD-1.5 layers with 40-wide heads: tcgen05 kernels over a K / V^T image that is laid out once per
+                    # generation (K, V are projections of the text embeddings: constant over the 25 steps)
+                    kv = self._kv_image(attn, encoder_hidden_states, key, value, compact[1])
+                    hidden_states = region_attention_prepared(
+                        query, kv, compact, self._sigma_arg(sigma, query.device), workspace=self.workspace,
+                        scale=None)  # the reference always uses 1/sqrt(head_dim) here (:77), not attn.scale
+                else:
+                    hidden_states = region_attention(
+                        query, key, value, w_dev,
+                        self._sigma_arg(sigma, query.device),
+                        attn_mask=attention_mask,
+                        scale=None,
+                        workspace=self.workspace,
+                        compact=compact,
+                    )
         else:
             hidden_states = F.scaled_dot_product_attention(
                 query, key, value, attn_mask=attention_mask, dropout_p=0.0, is_causal=False

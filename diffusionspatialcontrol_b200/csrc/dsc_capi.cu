@@ -309,6 +309,88 @@ int dsc_xattn_call_cw(const void* q, const void* k, const void* v, const int64_t
                       L, D, S, scale, dtype, stream, true, "dsc_xattn_call_cw", cw);
 }
 
+int dsc_xattn_prepared_supported(int H, int D, int S) { return x3_supports(H, D, S) ? 1 : 0; }
+
+int dsc_xattn_kv_image_bytes(int B, int H, int D, int S, size_t* out) {
+  if (!out) return fail(DSC_ERR_INVALID_ARGUMENT, "out is null");
+  if (B <= 0) return fail(DSC_ERR_INVALID_ARGUMENT, "non-positive batch");
+  if (!x3_supports(H, D, S)) return fail(DSC_ERR_UNSUPPORTED, "prepared K/V: need D == 40, S == 77, H %% 4 == 0 (H=%d D=%d S=%d)", H, D, S);
+  *out = x3_image_bytes(B, H);
+  return DSC_OK;
+}
+
+static int check_cols(int n_active, const int32_t* cols, int S) {
+  if (n_active < 0 || n_active > DSC_MAX_COMPACT_COLS || (n_active > 0 && !cols))
+    return fail(DSC_ERR_INVALID_ARGUMENT, "compact map: need 0..%d columns and a column list", DSC_MAX_COMPACT_COLS);
+  for (int j = 0; j < n_active; ++j)
+    if (cols[j] < 0 || cols[j] >= S || (j > 0 && cols[j] <= cols[j - 1]))
+      return fail(DSC_ERR_INVALID_ARGUMENT, "compact map: column list must be ascending and inside [0, S)");
+  return DSC_OK;
+}
+
+int dsc_xattn_prepare_kv(const void* k, const void* v, const int64_t k_str[4], const int64_t v_str[4], int n_active,
+                         const int32_t* active_cols, int B, int H, int D, int S, int dtype, void* kv_image, void* stream) {
+  int rc = check_dims(B, H, 1, D, S, dtype);
+  if (rc) return rc;
+  if (!x3_supports(H, D, S)) return fail(DSC_ERR_UNSUPPORTED, "prepared K/V: need D == 40, S == 77, H %% 4 == 0 (H=%d D=%d S=%d)", H, D, S);
+  if (!kv_image || !aligned16(kv_image)) return fail(DSC_ERR_INVALID_ARGUMENT, "kv_image must be a 16-byte aligned device buffer");
+  if ((rc = check_bhxd("k", k, k_str, D))) return rc;
+  if ((rc = check_bhxd("v", v, v_str, D))) return rc;
+  if ((rc = check_cols(n_active, active_cols, S))) return rc;
+  cudaError_t e = run_prepare_kv_x3(k, v, k_str[0], k_str[2], v_str[0], v_str[2], B, H, S, n_active, active_cols, dtype, kv_image,
+                                    static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_prepare_kv");
+}
+
+int dsc_xattn_call_prepared(const void* q, const int64_t q_str[4], const void* kv_image, const float* Wc, int Bw, int n_active,
+                            const float* sigma_dev_or_null, float sigma_host, void* workspace, void* out, const int64_t o_str[3],
+                            int B, int H, int L, int D, int S, float scale, int dtype, int passes, void* stream) {
+  int rc = check_dims(B, H, L, D, S, dtype);
+  if (rc) return rc;
+  if (!x3_supports(H, D, S)) return fail(DSC_ERR_UNSUPPORTED, "prepared K/V: need D == 40, S == 77, H %% 4 == 0 (H=%d D=%d S=%d)", H, D, S);
+  if (passes < 1 || passes > 3) return fail(DSC_ERR_INVALID_ARGUMENT, "passes must be 1, 2 or 3");
+  if (!workspace || !kv_image || !aligned16(kv_image)) return fail(DSC_ERR_INVALID_ARGUMENT, "null / misaligned workspace or kv_image");
+  if ((rc = check_bhxd("q", q, q_str, D))) return rc;
+  if (!(scale > 0.f)) return fail(DSC_ERR_UNSUPPORTED, "prepared K/V path needs scale > 0");
+  XattnParams p{};
+  p.B = B;
+  p.H = H;
+  p.L = L;
+  p.S = S;
+  p.q = q;
+  p.q_sb = q_str[0];
+  p.q_sl = q_str[2];
+  p.scale = scale;
+  p.kv_image = kv_image;
+  p.ws = static_cast<Workspace*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaSuccess;
+  if (passes & DSC_PASS_STATS) {
+    if (stats_grid(static_cast<long long>(B) * (H / 4) * ((L + 127) / 128)) > kMaxPartials)
+      return fail(DSC_ERR_UNSUPPORTED, "grid exceeds the workspace's partial slots");
+    e = run_stats_x3(p, dtype, st);
+    if (e != cudaSuccess) return cuda_fail(e, "dsc_xattn_call_prepared (pass 1)");
+  }
+  if (passes & DSC_PASS_FORWARD) {
+    if (!Wc || !aligned16(Wc) || !out || !o_str) return fail(DSC_ERR_INVALID_ARGUMENT, "pass 2 needs Wc (16-byte aligned) and out");
+    if (n_active < 1 || n_active > DSC_MAX_COMPACT_COLS) return fail(DSC_ERR_INVALID_ARGUMENT, "n_active must be in 1..%d", DSC_MAX_COMPACT_COLS);
+    if (Bw <= 0 || B % Bw != 0) return fail(DSC_ERR_SHAPE, "region map batch Bw=%d must divide the attention batch B=%d", Bw, B);
+    if (!aligned16(out) || o_str[2] != 1 || o_str[1] % 8 != 0 || o_str[0] % 8 != 0)
+      return fail(DSC_ERR_LAYOUT, "out: need 16-byte base, unit inner stride, row/batch strides multiple of 8");
+    p.out = out;
+    p.o_sb = o_str[0];
+    p.o_sl = o_str[1];
+    p.wc = Wc;
+    p.n_active = n_active;
+    p.Bw = Bw;
+    p.sigma_dev = sigma_dev_or_null;
+    p.sigma_host = sigma_host;
+    e = run_forward_x3(p, dtype, st);
+    if (e != cudaSuccess) return cuda_fail(e, "dsc_xattn_call_prepared (pass 2)");
+  }
+  return DSC_OK;
+}
+
 int dsc_region_downsample(const uint8_t* maps, int R, int Hpx, int Wpx, int w_r, int h_r, uint8_t* ds,
                           uint32_t* any_set, void* stream) {
   if (R < 0 || Hpx <= 0 || Wpx <= 0 || w_r <= 0 || h_r <= 0) return fail(DSC_ERR_INVALID_ARGUMENT, "bad size");

@@ -1,0 +1,904 @@
+// Region-masked cross-attention, tcgen05 + TMEM, THREE decoupled consumer warpgroups ("x3"), D = 40, S = 77.
+//
+// Same two passes as xattn_tc5.cu (pass 1: std of scale*QK^T over the whole call; pass 2: softmax(scale*QK^T + beta*W) V;
+// reference source/modules/attention_modify.py:74-103 with the weight_func of source/app.py:1004), reorganised so that no
+// thread ever waits for a tensor-core round trip it has just started:
+//
+//   * Work item = (128-row tile, head).  Items of a CTA's tile range are dealt round-robin to 3 consumer warpgroups
+//     (one thread per query row; TMEM lane = row).  A warpgroup owns 168 TMEM columns: S (80 fp32) | P (40, 16-bit pairs)
+//     | O (48 fp32) -- S, P and O are SEPARATE regions (3 x 168 = 504 <= 512 columns), so
+//         Q K^T of item n+1 is issued the moment S(n) has been read into registers,
+//         P V   of item n   runs while the warpgroup already exponentiates item n+1,
+//         O(n) is drained (x 1/rowsum -> shared memory) in the middle of item n+1's softmax, when P V(n) has long
+//         finished.
+//     The x4 kernel (xattn_tc5.cu) aliases P on S and the Q operand on O: its four warpgroups sit through the serial chain
+//     O -> Q rows to TMEM -> QK^T -> S -> softmax -> P -> PV together (2.8k of 5.7k cycles per tile idle, profiles/r1_*).
+//   * Q is the A operand STRAIGHT FROM SHARED MEMORY (no smem -> registers -> TMEM hop, no consumer thread involved).
+//     The TMA engine costs about one cycle per box ROW whatever its width (profiles/r1_tma_copy_rate.jsonl,
+//     profiles/r2_x3_trace_*.txt), so the 160-column tile arrives as just three boxes: columns [0,64) and [64,128) with
+//     SWIZZLE_128B and [128,160) with SWIZZLE_64B (384 rows) -- the UMMA K-major canonical layouts.  A k16 step must lie
+//     inside one swizzle row, and head h starts at column 40h, so the contraction of head h runs over the three
+//     16-column blocks (32-byte aligned in the row) that cover its 40 columns, and the K image holds ZEROS where a block's
+//     columns belong to a neighbouring head (h = 0: blocks 0-2, h = 1: 2-4, h = 2: 5-7, h = 3: 7-9): 3 MMAs per head,
+//     as many as 40 columns need anyway.  Finished O rows overwrite their own columns in the same boxes and leave through
+//     the same three box shapes; the compact W tile (128 rows x 80 B, contiguous in global memory) is ONE bulk copy.
+//   * K and V^T|1 of a (batch, 4-head group) arrive as ONE bulk copy of a prepared 60 KB image (dsc_xattn_prepare_kv:
+//     UMMA K-major chunks, keys permuted so that the weighted columns of the compact region map are slots 0..15, ones
+//     row appended to V^T so that column 40 of O is the softmax row sum).  K/V never change during a generation
+//     (attention_modify.py:465-466 recomputes the same projections on each of the 25 steps), so the image is built once.
+//   * 512 threads: warps 0-11 consumers, warp 12 lane 0 = TMA producer, lane 0 of warps 13-15 = tensor-core issuers of
+//     warpgroups 0-2 -> 128 registers per thread (the 640-thread x4 kernel has 96).
+//   * pass 1 (STATS): same skeleton, S double-buffered in TMEM (2 x 80 columns per warpgroup), 4-stage Q ring, every
+//     thread accumulates sum / sum of squares of its S rows; fold as in xattn_tc5.cu (deterministic).
+// Pass 2 is a programmatic dependent launch of pass 1, as before.
+#include "tc5_common.cuh"
+#include "tc5_tmem.cuh"
+
+#include <stdio.h>
+
+namespace dsc {
+
+namespace x3 {
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int D = 40, HPT = 4, GW = 160, ROWS = 128, NWG = 3;
+constexpr int THREADS = 512, CONSUMERS = NWG * 128;
+// TMEM columns of one warpgroup
+constexpr int WG_COLS = 168, S_COL = 0, P_COL = 80, O_COL = 120, S1_COL = 80;
+// ring stage: Q / O tile = boxes [0,64) | [64,128) (SW128, 16 KB each) | [128,160) (SW64, 8 KB), then the compact W tile
+constexpr int BOX128_BYTES = ROWS * 128, BOX64_BYTES = ROWS * 64;
+constexpr int QT_BYTES = 2 * BOX128_BYTES + BOX64_BYTES;               // 40960
+constexpr int CW_BYTES = ROWS * DSC_COMPACT_PITCH * 4;                 // 10240
+constexpr int FWD_STAGE = QT_BYTES + CW_BYTES, FWD_NST = 3;            // 51200
+constexpr int STATS_STAGE = QT_BYTES, STATS_NST = 4;
+// prepared K / V^T image of one (batch, head group): see dsc_xattn_prepare_kv
+constexpr int K_CH = DSC_MAX_KEYS * 16, K_HEAD = 6 * K_CH, K_BYTES = HPT * K_HEAD;         // 1280, 7680, 30720
+constexpr int VT_CH = 48 * 16, VT_HEAD = 10 * VT_CH, VT_BYTES = HPT * VT_HEAD;             // 768, 7680, 30720
+constexpr int IMG_BYTES = K_BYTES + VT_BYTES;                                              // 61440
+constexpr int BAR_BYTES = 256;
+constexpr int FWD_SMEM = IMG_BYTES + FWD_NST * FWD_STAGE + BAR_BYTES;                      // 215296
+constexpr int STATS_SMEM = K_BYTES + STATS_NST * STATS_STAGE + BAR_BYTES;                  // 194816
+static_assert(IMG_BYTES % 1024 == 0 && K_BYTES % 1024 == 0 && FWD_STAGE % 1024 == 0 && STATS_STAGE % 1024 == 0, "alignment");
+static_assert(FWD_SMEM <= 227 * 1024 && STATS_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(NWG * WG_COLS <= 512, "TMEM budget");
+constexpr int kProducerTid = 12 * 32;
+
+struct Tile {
+  int b, hg, tile, l0;
+};
+__device__ __forceinline__ Tile decode(int idx, const XattnParams& p) {
+  Tile t;
+  const int seg = idx / p.n_sl;
+  t.tile = idx - seg * p.n_sl;
+  t.b = seg / p.n_hg;
+  t.hg = seg - t.b * p.n_hg;
+  t.l0 = t.tile * ROWS;
+  return t;
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major SWIZZLE_64B descriptor: rows 64 B apart, 8-row groups 512 B apart (LBO unused: both chunks of a k-step lie in the row)
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
+  return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(512 >> 4) << 32) | (1ull << 46) |
+         (4ull << 61);
+}
+
+// K-major SWIZZLE_128B descriptor: rows 128 B apart, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+#ifdef DSC_WATCHDOG
+__device__ unsigned int g_x3_abort = 0;
+__device__ unsigned int g_x3_info[4] = {0, 0, 0, 0};
+#endif
+// Every barrier wait is bounded: a protocol error must end in a trap (an error the host sees), never in a hung GPU.
+// (-DDSC_WATCHDOG: record who waited on what, let the kernel drain; read back with dsc_debug_x3_watchdog.)
+__device__ __forceinline__ bool test_bar(uint32_t bar, uint32_t parity) {  // non-blocking probe of a barrier phase
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+template <bool RELAXED>
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t tag) {
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (RELAXED) __nanosleep(40);
+    if (++spins == 64) t0 = clock64();
+    if (spins > 64) {
+#ifdef DSC_WATCHDOG
+      if (*reinterpret_cast<volatile unsigned int*>(&g_x3_abort)) return;
+      if (clock64() - t0 > (1ll << 30)) {
+        if (atomicCAS(&g_x3_abort, 0u, 1u) == 0u) {
+          g_x3_info[0] = tag;
+          g_x3_info[1] = blockIdx.x;
+          g_x3_info[2] = threadIdx.x;
+          g_x3_info[3] = parity;
+        }
+        return;
+      }
+#else
+      if (clock64() - t0 > (1ll << 32)) __trap();  // ~2 s: unreachable unless the barrier protocol is broken
+#endif
+    }
+  }
+}
+
+#ifdef DSC_TRACE
+// Debug build only: clock64 timeline of block 0 -- thread 0 of each consumer warpgroup, the producer, the three issuers
+// -> g_x3_trace[pass][who][slot] = {tag, clock}; globaltimer at start / end of every CTA.
+__device__ long long g_x3_trace[2][7][1024][2];
+__device__ int g_x3_trace_n[2][7];
+__device__ unsigned long long g_x3_cta[2][160][2];
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define X3_TRACE_DECL                                                                                   \
+  int tr_n = 0;                                                                                         \
+  const int tr_k = blockIdx.x != 0 ? -1                                                                 \
+                   : (threadIdx.x & 127) == 0 && threadIdx.x < 384 ? (int)(threadIdx.x >> 7)            \
+                   : threadIdx.x == 384 ? 3 : (threadIdx.x >= 416 && (threadIdx.x & 31) == 0) ? 4 + (int)((threadIdx.x - 416) >> 5) : -1;
+#define X3_TRACE(tag)                                            \
+  do {                                                           \
+    if (tr_k >= 0 && tr_n < 1024) {                              \
+      g_x3_trace[STATS ? 0 : 1][tr_k][tr_n][0] = (tag);          \
+      g_x3_trace[STATS ? 0 : 1][tr_k][tr_n][1] = clock64();      \
+      g_x3_trace_n[STATS ? 0 : 1][tr_k] = ++tr_n;                \
+    }                                                            \
+  } while (0)
+#define X3_CTA_TIME(k) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_x3_cta[STATS ? 0 : 1][blockIdx.x][k] = gtimer_ns(); } while (0)
+#else
+#define X3_TRACE_DECL
+#define X3_TRACE(tag) do {} while (0)
+#define X3_CTA_TIME(k) do {} while (0)
+#endif
+
+#ifndef X3_DRAIN_AT
+#define X3_DRAIN_AT 23  // key pair of the current item after which the previous item's O row is taken out of TMEM
+#endif
+#ifndef X3_PREPASS
+#define X3_PREPASS 0    // row max of the NEXT item taken from TMEM while the current item is still being exponentiated
+#endif
+#ifndef X3_TURNS
+#define X3_TURNS 2      // pass 2: at most this many of the three warps that share an SM sub-partition exponentiate at a time (0 = off)
+#endif
+#ifndef X3_L2_PREFETCH
+#define X3_L2_PREFETCH 1  // tile i + NST is pulled towards L2 when tile i is loaded
+#endif
+
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(THREADS, 1)
+xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, const __grid_constant__ CUtensorMap tm_qb,
+                const __grid_constant__ CUtensorMap tm_qp, const __grid_constant__ CUtensorMap tm_oa,
+                const __grid_constant__ CUtensorMap tm_ob) {
+  constexpr int NST = STATS ? STATS_NST : FWD_NST;
+  constexpr int STAGE = STATS ? STATS_STAGE : FWD_STAGE;
+  constexpr int KV = STATS ? K_BYTES : IMG_BYTES;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  X3_TRACE_DECL
+  X3_CTA_TIME(0);
+  X3_TRACE(1);
+  if (warp == 15 && lane < 5) {  // hide the descriptor fetches behind the rest of the prologue
+    const CUtensorMap* m = lane == 0 ? &tm_qa : lane == 1 ? &tm_qb : lane == 2 ? &tm_qp : lane == 3 ? &tm_oa : &tm_ob;
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+  }
+  if constexpr (STATS) {
+    // pass 1 is itself a programmatic dependent of whatever precedes it in the stream: nothing of its inputs is touched
+    // before that kernel has completed; pass 2 may be placed as SMs free up
+    pdl_wait_prior_grid();
+    pdl_launch_dependents();
+  } else {
+    pdl_launch_dependents();  // a following pass 1 (next call) may be placed early; it waits for our completion itself
+  }
+  X3_TRACE(3);
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t sStage = s0 + KV;
+  const uint32_t bars = sStage + NST * STAGE;
+  // barrier map (8 B each)
+  const uint32_t b_full = bars, b_odone = bars + 32, b_kvfull = bars + 64, b_kvfree = bars + 72, b_srdy = bars + 80,
+                 b_sfree = bars + 128, b_prdy = bars + 176, b_ordy = bars + 200;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 240);
+  volatile uint32_t* turn_ptr = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 224);
+
+  const int begin = static_cast<int>(p.total * blockIdx.x / gridDim.x);
+  const int n_items = static_cast<int>(p.total * (blockIdx.x + 1) / gridDim.x) - begin;
+  const uint64_t pol_q = STATS ? policy_evict_last() : policy_evict_first();  // pass 2 reads Q again: keep it in L2
+  const unsigned char* img = reinterpret_cast<const unsigned char*>(p.kv_image);
+
+  auto load_image = [&](const Tile& t) {  // K (| V^T) image of the tile's (batch, head group): one bulk copy
+    mbar_arrive_expect_tx(b_kvfull, KV);
+    bulk_g2s_hint(s0, img + (static_cast<size_t>(t.b) * p.n_hg + t.hg) * IMG_BYTES, KV, b_kvfull, policy_evict_last());
+  };
+  auto load_tile = [&](int i) {  // Q boxes (+ compact W tile) of tile i -> ring stage i % NST
+    const int s = i % NST;
+    const Tile t = decode(begin + i, p);
+    const uint32_t sQ = sStage + s * STAGE, bar = b_full + 8 * s;
+    const int c0 = t.hg * GW;
+    uint32_t wbytes = 0;
+    if constexpr (!STATS) wbytes = static_cast<uint32_t>(min(ROWS, p.L - t.l0)) * (DSC_COMPACT_PITCH * 4);
+    mbar_arrive_expect_tx(bar, QT_BYTES + wbytes);  // out-of-range parts of a box are zero-filled and still counted
+    tma_load_3d(sQ, &tm_qa, c0, t.l0, t.b, bar, pol_q);
+    tma_load_3d(sQ + BOX128_BYTES, &tm_qa, c0 + 64, t.l0, t.b, bar, pol_q);
+    tma_load_3d(sQ + 2 * BOX128_BYTES, &tm_qb, c0 + 128, t.l0, t.b, bar, pol_q);
+    if constexpr (!STATS)  // the compact W rows of a tile are contiguous: one bulk copy
+      bulk_g2s_hint(sQ + QT_BYTES, p.wc + (static_cast<size_t>(t.b / (p.B / p.Bw)) * p.L + t.l0) * DSC_COMPACT_PITCH, wbytes, bar, pol_q);
+    if (t.tile == p.n_sl - 1 && i + 1 < n_items) {  // the run ends with this tile: pull the next image towards L2
+      const Tile n = decode(begin + i + 1, p);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(img + (static_cast<size_t>(n.b) * p.n_hg + n.hg) * IMG_BYTES),
+                   "r"(KV)
+                   : "memory");
+    }
+#if X3_L2_PREFETCH
+    if (i + NST < n_items) {  // the tile that will reuse this stage: one 160-column box (+ its W box) towards L2
+      const Tile n = decode(begin + i + NST, p);
+      asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&tm_qp), "r"(n.hg * GW), "r"(n.l0),
+                   "r"(n.b)
+                   : "memory");
+      if constexpr (!STATS)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                         p.wc + (static_cast<size_t>(n.b / (p.B / p.Bw)) * p.L + n.l0) * DSC_COMPACT_PITCH),
+                     "r"(static_cast<uint32_t>(min(ROWS, p.L - n.l0)) * (DSC_COMPACT_PITCH * 4))
+                     : "memory");
+    }
+#endif
+  };
+
+  // barrier init is spread over the service warps so that the first loads leave as early as possible: the producer
+  // thread initialises only what those loads signal (full[], kvfull), warp 14 the rest (8 bytes apart in map order)
+  if (tid == kProducerTid) {
+    for (int st = 0; st < 4; ++st) mbar_init(b_full + 8 * st, 1);
+    mbar_init(b_kvfull, 1);
+    fence_mbar_init();
+    X3_TRACE(4);
+    if (n_items > 0) {  // only what the first Q K^T needs is issued ahead of the CTA-wide barrier
+      load_image(decode(begin, p));
+      load_tile(0);
+      X3_TRACE(6);
+    }
+  }
+  if (warp == 14) {
+    if (lane >= 4 && lane < 28 && lane != 8) {
+      const uint32_t cnt = lane < 8 ? HPT * 128u : lane == 9 ? static_cast<uint32_t>(CONSUMERS) : lane < 16 ? 1u : lane < 25 ? 128u : 1u;
+      mbar_init(bars + 8 * lane, cnt);
+      fence_mbar_init();
+    }
+    if (lane >= 28) turn_ptr[lane - 28] = 0u;  // whose turn it is on each SM sub-partition (pass 2)
+  }
+  if (warp == 13) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    X3_TRACE(7);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  X3_TRACE(2);
+
+  if (warp >= 12) {
+    if (tid == kProducerTid) {
+      // ============================== producer: TMA loads and stores ===============================
+      uint32_t n_run = 0;
+      for (int i = 1; i < min(NST, n_items); ++i) load_tile(i);  // rest of the first ring fill
+      X3_TRACE(8);
+      auto tile_done = [&](int i) {  // every consumer has handed tile i back
+        const int s = i % NST;
+        X3_TRACE(30);
+        wait_bar<true>(b_odone + 8 * s, (i / NST) & 1, 1);
+        X3_TRACE(31);
+        const Tile t = decode(begin + i, p);
+        if constexpr (!STATS) {
+          const uint32_t sQ = sStage + s * STAGE;
+          const int c0 = t.hg * GW;
+          tma_store_3d(&tm_oa, c0, t.l0, t.b, sQ);  // rows >= L and columns >= H*D are clipped by the TMA
+          tma_store_3d(&tm_oa, c0 + 64, t.l0, t.b, sQ + BOX128_BYTES);
+          tma_store_3d(&tm_ob, c0 + 128, t.l0, t.b, sQ + 2 * BOX128_BYTES);
+          bulk_commit();
+          bulk_wait_read0();
+          X3_TRACE(32);
+        }
+        if (t.tile == p.n_sl - 1 && i + 1 < n_items) {  // (batch, head group) changes: swap the K / V^T image
+          wait_bar<true>(b_kvfree, n_run & 1, 2);
+          ++n_run;
+          load_image(decode(begin + i + 1, p));
+          X3_TRACE(33);
+        }
+      };
+      for (int i = NST; i < n_items; ++i) {
+        tile_done(i - NST);
+        load_tile(i);
+        X3_TRACE(34);
+      }
+      for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) tile_done(i);
+      if constexpr (!STATS) bulk_wait0();
+    } else if (lane == 0 && warp >= 13) {
+      // ============================== tensor-core issuer of warpgroup g ============================
+      const int g = warp - 13;
+      constexpr uint32_t idesc_qk = idesc_f16<T>(80);
+      constexpr uint32_t idesc_pv = idesc_f16<T>(48);
+      const uint32_t tw = tmem_base + g * WG_COLS;
+      uint32_t nqk = 0, npv = 0, n_run = 0;
+      for (int r0 = 0; r0 < n_items;) {
+        const Tile t0 = decode(begin + r0, p);
+        const int r1 = min(n_items, r0 + p.n_sl - t0.tile);
+        const int nit = HPT * (r1 - r0);
+        X3_TRACE(40);
+        wait_bar<true>(b_kvfull, n_run & 1, 3);
+        X3_TRACE(41);
+        ++n_run;
+        auto qk = [&](int j) {
+          const int i = r0 + (j >> 2), h = j & 3, s = i % NST;
+          X3_TRACE(42);
+          wait_bar<true>(b_full + 8 * s, (i / NST) & 1, 4);
+          uint32_t buf = 0;
+          if constexpr (STATS) {
+            buf = nqk & 1;
+            if (nqk >= 2) wait_bar<true>(b_sfree + 16 * g + 8 * buf, ((nqk >> 1) - 1) & 1, 5);
+          } else {
+            if (nqk >= 1) wait_bar<true>(b_sfree + 16 * g, (nqk - 1) & 1, 5);
+          }
+          X3_TRACE(43);
+          ++nqk;
+          tc_fence_after();
+          const uint32_t sQ = sStage + s * STAGE;
+          const uint32_t d = tw + (STATS ? buf * S1_COL : S_COL);
+          const uint32_t kb = s0 + h * K_HEAD;
+          // head h = the three 16-column blocks that cover columns 40h .. 40h+39 (the K image is zero where a block's
+          // columns belong to a neighbour); block t: boxes of 4 blocks (SW128) for t < 8, the SW64 box for t = 8, 9
+          const int t0b = (h * D) >> 4;
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks) {
+            const int t = t0b + ks;
+            const uint64_t ad = t < 8 ? smem_desc_sw128(sQ + (t >> 2) * BOX128_BYTES + (t & 3) * 32)
+                                      : smem_desc_sw64(sQ + 2 * BOX128_BYTES + (t - 8) * 32);
+            umma_ss(d, ad, smem_desc(kb + ks * 2 * K_CH, K_CH, 128), idesc_qk, ks);
+          }
+          tc_commit(b_srdy + 16 * g + 8 * buf);
+          X3_TRACE(44);
+        };
+        if (g < nit) qk(g);
+        for (int j = g; j < nit; j += NWG) {
+          if (j + NWG < nit) qk(j + NWG);
+          if constexpr (!STATS) {
+            const int h = j & 3;
+            X3_TRACE(45);
+            wait_bar<true>(b_prdy + 8 * g, npv & 1, 6);
+            X3_TRACE(46);
+            ++npv;
+            tc_fence_after();
+            const uint64_t vdesc = smem_desc(s0 + K_BYTES + h * VT_HEAD, VT_CH, 128);
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk)
+              umma_ts(tw + O_COL, tw + P_COL + kk * 8, vdesc + static_cast<uint64_t>((kk * 2 * VT_CH) >> 4), idesc_pv, kk);
+            tc_commit(b_ordy + 8 * g);
+            X3_TRACE(47);
+          }
+        }
+        r0 = r1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== consumers: one thread per query row ============================
+    const int g = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t tw = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * WG_COLS;
+    float beta_l2 = 0.f;  // sigma * std * log2(e); read after pass 1 has completed (PDL), right before first use
+    bool have_beta = STATS;
+    const float scale_l2 = p.scale * kLog2e;
+    double dsum = 0.0, dsq = 0.0;
+    uint32_t n_s = 0, n_o = 0;
+    bool pend = false;  // an O row of this thread still sits in TMEM
+    int pend_s = 0, pend_h = 0;
+    bool pre_waited = false;  // the next item's S has already been waited for and its row max taken (m_next)
+    float m_next = 0.f;
+    // The exponentials of an item ("M phase": 77 MUFU.EX2 per row, the bottleneck pipe: 4 lanes per clock and SM
+    // sub-partition) are SERIALISED per sub-partition in item order: warp (g, quarter) waits until turn[quarter] equals
+    // its item's sequence number.  Left alone, the three warps of a sub-partition run in lock-step -- they share the MUFU
+    // pipe fairly, so they finish their M phases together and then all do their MUFU-free work (S row out of TMEM, W,
+    // row max, O drain, barriers: ~1300 cycles) while the pipe idles (profiles/r2_x3_trace_lockstep.txt: 3.3k cycles per
+    // round of 3 items against 1.85k of MUFU work).  With turns, one warp exponentiates at the full pipe rate while the
+    // other two do their MUFU-free part.
+    volatile uint32_t* my_turn = turn_ptr + (warp & 3);
+    uint32_t seq_base = 0;  // items of the CTA's earlier runs
+
+    // O row of the warpgroup's previous item: TMEM -> x 1/rowsum (ones row of V^T: column 40) -> over the row's own Q
+    // columns in the ring stage, stage handed back
+    auto drain = [&]() {
+      X3_TRACE(13);
+      wait_bar<false>(b_ordy + 8 * g, n_o & 1, 7);
+      X3_TRACE(14);
+      ++n_o;
+      tc_fence_after();
+      unsigned char* st = smem + KV + pend_s * STAGE;
+      // 16-byte chunk c of the head's O row = global chunk G = 5h + c of the 160-column tile row: the place its Q columns
+      // had (swizzled: 8 consecutive rows hit 8 distinct bank groups)
+      auto dst_of = [&](int c) -> unsigned char* {
+        const int G = pend_h * 5 + c;
+        return G < 16 ? st + (G >> 3) * BOX128_BYTES + row * 128 + (((G & 7) ^ (row & 7)) << 4)
+                      : st + 2 * BOX128_BYTES + row * 64 + ((((G - 16) & 3) ^ ((row >> 1) & 3)) << 4);
+      };
+      auto chunk = [&](const float* o8, float inv, unsigned char* d) {
+        float t[8];
+        fmul2(t[0], t[1], o8[0], o8[1], inv, inv);
+        fmul2(t[2], t[3], o8[2], o8[3], inv, inv);
+        fmul2(t[4], t[5], o8[4], o8[5], inv, inv);
+        fmul2(t[6], t[7], o8[6], o8[7], inv, inv);
+        uint4 v;
+        v.x = Mma<T>::pack(t[0], t[1]);
+        v.y = Mma<T>::pack(t[2], t[3]);
+        v.z = Mma<T>::pack(t[4], t[5]);
+        v.w = Mma<T>::pack(t[6], t[7]);
+        *reinterpret_cast<uint4*>(d) = v;
+      };
+      float oa[16], oz[4];
+      tmem_ld_x16(tw + O_COL, reinterpret_cast<uint32_t*>(oa));
+      tmem_ld_x4(tw + O_COL + 40, reinterpret_cast<uint32_t*>(oz));
+      tc_wait_ld();
+      const float inv = 1.f / oz[0];
+      float ob[16];
+      tmem_ld_x16(tw + O_COL + 16, reinterpret_cast<uint32_t*>(ob));
+      chunk(oa, inv, dst_of(0));
+      chunk(oa + 8, inv, dst_of(1));
+      tc_wait_ld();
+      float oc[8];
+      tmem_ld_x8(tw + O_COL + 32, reinterpret_cast<uint32_t*>(oc));
+      chunk(ob, inv, dst_of(2));
+      chunk(ob + 8, inv, dst_of(3));
+      tc_wait_ld();
+      tc_fence_before();  // the O columns may be overwritten by the next P V once this thread has arrived on prdy
+      chunk(oc, inv, dst_of(4));
+      fence_proxy_async();  // O rows -> visible to the TMA store
+      mbar_arrive(b_odone + 8 * pend_s);
+      X3_TRACE(15);
+      pend = false;
+    };
+
+    for (int r0 = 0; r0 < n_items;) {
+      const Tile t0 = decode(begin + r0, p);
+      const int r1 = min(n_items, r0 + p.n_sl - t0.tile);
+      const int nit = HPT * (r1 - r0);
+      for (int j = g; j < nit; j += NWG) {
+        const int i = r0 + (j >> 2), h = j & 3, s = i % NST;
+        float sc[80];
+        if constexpr (STATS) {
+          const uint32_t buf = n_s & 1;
+          X3_TRACE(10);
+          wait_bar<false>(b_srdy + 16 * g + 8 * buf, (n_s >> 1) & 1, 8);
+          X3_TRACE(11);
+          ++n_s;
+          tc_fence_after();
+          tmem_ld_x64(tw + buf * S1_COL, reinterpret_cast<uint32_t*>(sc));
+          tmem_ld_x16(tw + buf * S1_COL + 64, reinterpret_cast<uint32_t*>(sc) + 64);
+          tc_wait_ld();
+          tc_fence_before();
+          mbar_arrive(b_sfree + 16 * g + 8 * buf);
+          mbar_arrive(b_odone + 8 * s);  // pass 1 only reads Q: this item's Q K^T is complete
+          X3_TRACE(12);
+          // rows beyond L were zero-filled by the TMA and pad keys are zero rows of K: they add exact zeros
+          float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 80; c += 4) {
+            fadd2(fs[0], fs[1], fs[0], fs[1], sc[c], sc[c + 1]);
+            fadd2(fs[2], fs[3], fs[2], fs[3], sc[c + 2], sc[c + 3]);
+            ffma2(fq[0], fq[1], sc[c], sc[c + 1], sc[c], sc[c + 1], fq[0], fq[1]);
+            ffma2(fq[2], fq[3], sc[c + 2], sc[c + 3], sc[c + 2], sc[c + 3], fq[2], fq[3]);
+          }
+          dsum += static_cast<double>((fs[0] + fs[1]) + (fs[2] + fs[3]));
+          dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
+        } else {
+          X3_TRACE(10);
+          if (!pre_waited) {
+            wait_bar<false>(b_srdy + 16 * g, n_s & 1, 8);
+            ++n_s;
+          }
+          X3_TRACE(11);
+          tc_fence_after();
+          tmem_ld_x64(tw + S_COL, reinterpret_cast<uint32_t*>(sc));
+          tmem_ld_x16(tw + S_COL + 64, reinterpret_cast<uint32_t*>(sc) + 64);
+          tc_wait_ld();
+          tc_fence_before();
+          mbar_arrive(b_sfree + 16 * g);  // the next item's Q K^T may overwrite S
+          X3_TRACE(12);
+          if (!have_beta) {
+            X3_TRACE(17);
+            pdl_wait_prior_grid();  // pass 1 (same stream, launched just before) has published the std
+            X3_TRACE(18);
+            const float sigma = p.sigma_dev ? __ldcg(p.sigma_dev) : p.sigma_host;
+            beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2e;
+            have_beta = true;
+          }
+          // logits in the log2 domain.  Compact region map: the weighted key columns are slots 0..15 (keys permuted in the
+          // prepared image), one 80-byte row of W per query.  y = s * a + w * bw, 2^(e * y - e * max(y)): a = scale / beta,
+          // bw = 1, e = beta -- or, for a vanishing beta, a = scale, bw = beta, e = 1
+          const bool bpos = beta_l2 > 1e-20f;
+          const float ca = bpos ? scale_l2 / beta_l2 : scale_l2, cbw = bpos ? 1.f : beta_l2, ce = bpos ? beta_l2 : 1.f;
+          if (!pre_waited) wait_bar<false>(b_full + 8 * s, (i / NST) & 1, 9);  // (long complete: the Q K^T needed the stage)
+          const float4* wt4 = reinterpret_cast<const float4*>(smem + KV + s * STAGE + QT_BYTES + row * (DSC_COMPACT_PITCH * 4));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float4 w = wt4[c];
+            if (!bpos) {
+              fmul2(w.x, w.y, w.x, w.y, cbw, cbw);
+              fmul2(w.z, w.w, w.z, w.w, cbw, cbw);
+            }
+            ffma2(sc[4 * c], sc[4 * c + 1], sc[4 * c], sc[4 * c + 1], ca, ca, w.x, w.y);
+            ffma2(sc[4 * c + 2], sc[4 * c + 3], sc[4 * c + 2], sc[4 * c + 3], ca, ca, w.z, w.w);
+          }
+          sc[77] = sc[78] = sc[79] = -INFINITY;  // pad keys
+          // slots 16..79 carry no weight: their y is a * s, so the row max is taken on the raw scores (a > 0) and the
+          // scaling folds into the single FFMA that forms the exponent
+          float m = m_next;
+          if (!pre_waited) {
+            float my[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mr[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int c = 0; c < 16; ++c) my[c & 3] = fmaxf(my[c & 3], sc[c]);
+#pragma unroll
+            for (int c = 16; c < 80; ++c) mr[c & 3] = fmaxf(mr[c & 3], sc[c]);
+            m = fmaxf(fmaxf(fmaxf(my[0], my[1]), fmaxf(my[2], my[3])), ca * fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])));
+          }
+          pre_waited = false;
+          const float nb = -ce * m, k2 = ce * ca;
+          // the previous item's O row leaves TMEM while this warp would wait for its turn anyway (its P V was issued when
+          // the previous item published P: long finished after the S read, W and row max above); that also proves
+          // P(previous) has been consumed, so this item's P may go in
+#if X3_TURNS > 0
+          if (pend) drain();
+          {
+            const uint32_t seq = seq_base + j;
+            if (lane == 0) {
+              long long t0 = 0;
+              uint32_t spins = 0;
+              while (static_cast<int>(seq - *my_turn) >= X3_TURNS) {  // at most X3_TURNS items ahead of the oldest unfinished one
+                __nanosleep(20);
+                if (++spins == 256) t0 = clock64();
+                if (spins > 256 && clock64() - t0 > (1ll << 32)) __trap();
+              }
+            }
+            __syncwarp();
+          }
+          X3_TRACE(19);
+#endif
+          const int jn = j + NWG;
+          bool pre = X3_PREPASS && jn < nit;
+          float pmy = -INFINITY, pmr = -INFINITY;
+          uint32_t pre_piece[16];
+          uint32_t pw[40];
+#pragma unroll
+          for (int c = 0; c < 39; ++c) {
+            float e0, e1;
+            if (c < 8) ffma2(e0, e1, sc[2 * c], sc[2 * c + 1], ce, ce, nb, nb);
+            else ffma2(e0, e1, sc[2 * c], sc[2 * c + 1], k2, k2, nb, nb);
+            pw[c] = c < 38 ? Mma<T>::pack(ex2_approx(e0), ex2_approx(e1)) : Mma<T>::pack(ex2_approx(e0), 0.f);
+#if X3_TURNS == 0
+            if (c == X3_DRAIN_AT) {
+              if (pend) drain();
+            }
+#endif
+            if (c == 23) {  // keys 0..47 are done: first part of P
+              tmem_st_x16(tw + P_COL, pw);
+              tmem_st_x8(tw + P_COL + 16, pw + 16);
+            }
+#if X3_PREPASS
+            if (c >= 24 && c <= 38) {
+              const int k = (c - 24) / 3, ph = (c - 24) % 3;  // piece k = S columns 16k .. 16k+15 of the next item
+              if (ph == 0 && pre) {
+                if (k == 0) {
+                  // never block here (P of this item is not published yet): if the next S has not landed, the item takes
+                  // its row max itself.  The TMEM loads are warp-collective, so the decision is made warp-uniform
+                  pre = __all_sync(0xffffffffu, test_bar(b_srdy + 16 * g, n_s & 1));
+                  if (pre) {
+                    ++n_s;
+                    tc_fence_after();
+                  }
+                }
+                if (pre) tmem_ld_x16(tw + S_COL + 16 * k, pre_piece);
+              }
+              if (ph == 2 && pre) {
+                tc_wait_ld();
+                const float* ps = reinterpret_cast<const float*>(pre_piece);
+                if (k == 0) {  // the weighted slots: y = s * a + w, exactly as the item itself will form them
+                  const int sn = (r0 + (jn >> 2)) % NST;
+                  const float4* wn4 = reinterpret_cast<const float4*>(smem + KV + sn * STAGE + QT_BYTES + row * (DSC_COMPACT_PITCH * 4));
+                  float y[16];
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) {
+                    float4 w = wn4[q4];
+                    if (!bpos) {
+                      fmul2(w.x, w.y, w.x, w.y, cbw, cbw);
+                      fmul2(w.z, w.w, w.z, w.w, cbw, cbw);
+                    }
+                    ffma2(y[4 * q4], y[4 * q4 + 1], ps[4 * q4], ps[4 * q4 + 1], ca, ca, w.x, w.y);
+                    ffma2(y[4 * q4 + 2], y[4 * q4 + 3], ps[4 * q4 + 2], ps[4 * q4 + 3], ca, ca, w.z, w.w);
+                  }
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) pmy = fmaxf(pmy, y[q]);
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 16; ++q)
+                    if (16 * k + q < 77) pmr = fmaxf(pmr, ps[q]);
+                }
+              }
+            }
+#endif
+          }
+          pw[39] = 0u;  // pad keys 78, 79
+          tmem_st_x16(tw + P_COL + 24, pw + 24);  // (volatile, reads pw[24..39]: every exponential above precedes it)
+#if X3_TURNS > 0
+          __syncwarp();
+          if (lane == 0) atomicAdd(const_cast<uint32_t*>(my_turn), 1u);  // one more M phase complete: the next warp in line may start
+#endif
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(b_prdy + 8 * g);
+          X3_TRACE(16);
+          pend = true;
+          pend_s = s;
+          pend_h = h;
+          if (pre) {
+            m_next = fmaxf(pmy, ca * pmr);
+            pre_waited = true;
+          }
+        }
+      }
+      if constexpr (!STATS) {
+        if (pend) drain();
+      }
+      mbar_arrive(b_kvfree);  // this thread's share of the run is complete: the K / V^T image may be replaced
+      seq_base += nit;
+      r0 = r1;
+    }
+    if constexpr (STATS) {
+      // CTA partial in a fixed order (warp shuffle tree, then warps 0..11 serially) -> workspace; the last CTA folds
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        dsq += __shfl_xor_sync(0xffffffffu, dsq, o);
+      }
+      double* red = reinterpret_cast<double*>(smem);  // the K image is dead: every Q K^T of this CTA has been consumed
+      asm volatile("bar.sync 1, 384;" ::: "memory");
+      if (lane == 0) {
+        red[warp] = dsum;
+        red[12 + warp] = dsq;
+      }
+      asm volatile("bar.sync 1, 384;" ::: "memory");
+      double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
+      if (warp == 0) {
+        unsigned int last = 0;
+        if (lane == 0) {
+          double a = 0.0, b = 0.0;
+          for (int w = 0; w < 12; ++w) {
+            a += red[w];
+            b += red[12 + w];
+          }
+          partials[2 * blockIdx.x] = a;
+          partials[2 * blockIdx.x + 1] = b;
+          __threadfence();
+          last = atomicAdd(&p.ws->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          __threadfence();
+          finalize_stats(p, partials, lane);
+        }
+      }
+    }
+  }
+
+  X3_TRACE(9);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  X3_CTA_TIME(1);
+  if (warp == 13) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- K / V^T image ------------------------------------------------------------------------------
+// One block per (batch, 4-head group) writes the 61,440-byte image the kernels above bulk-copy into shared memory:
+//   K  : [head 0..3][chunk 0..5][key slot 0..79][16 B]   chunk c = columns 16*floor(40h/16) + 8c .. +7 of the head GROUP (the
+//        three 16-column blocks that cover the head), zeros where those columns belong to a neighbouring head; key slots
+//        >= S = zeros (exact zero scores)
+//   V^T: [head 0..3][key chunk 0..9][row d 0..47][8 key slots x 2 B]   row 40 = ones (softmax row sum), rows 41..47 zeros
+// key slot -> key: the n_active weighted columns of the compact region map first (ascending), then every other key in
+// order (softmax and P V do not depend on the key order; pass 1 sums over all keys).
+struct ActiveCols {
+  int n;
+  int col[DSC_MAX_COMPACT_COLS];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) x3_prepare_kv_kernel(const T* __restrict__ k, const T* __restrict__ v, long long k_sb,
+                                                            long long k_ss, long long v_sb, long long v_ss, int S, int n_hg,
+                                                            const ActiveCols ac, unsigned char* __restrict__ image) {
+  __shared__ int perm[DSC_MAX_KEYS];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / n_hg, hg = blockIdx.x - b * n_hg;
+  if (tid < DSC_MAX_KEYS) {
+    int key = tid;
+    if (tid < ac.n) {
+      key = ac.col[tid];
+    } else {
+      key = tid - ac.n;
+      for (int j = 0; j < ac.n; ++j) key += (ac.col[j] <= key) ? 1 : 0;
+    }
+    perm[tid] = min(key, DSC_MAX_KEYS - 1);
+  }
+  __syncthreads();
+  unsigned char* img = image + static_cast<size_t>(blockIdx.x) * IMG_BYTES;
+  const T* kb = k + b * k_sb + hg * GW;
+  const T* vb = v + b * v_sb + hg * GW;
+  for (int e = tid; e < HPT * 6 * DSC_MAX_KEYS; e += 256) {
+    const int slot = e % DSC_MAX_KEYS, hc = e / DSC_MAX_KEYS, c = hc % 6, h = hc / 6;
+    // chunk c of head h = columns 16 * floor(40h / 16) + 8c .. +7 of the head group; zero outside the head's own columns
+    const int col = ((h * D) >> 4) * 16 + c * 8;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (col >= h * D && col < (h + 1) * D && slot < S) val = *reinterpret_cast<const uint4*>(kb + perm[slot] * k_ss + col);
+    *reinterpret_cast<uint4*>(img + static_cast<size_t>(e) * 16) = val;
+  }
+  const unsigned short one = std::is_same<T, __half>::value ? 0x3C00u : 0x3F80u;
+  for (int e = tid; e < HPT * 10 * 48; e += 256) {
+    const int d = e % 48, hk = e / 48, kc = hk % 10, vh = hk / 10;
+    unsigned short w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int slot = kc * 8 + j;
+      unsigned short x = 0;
+      if (slot < S) {
+        if (d < D) x = *reinterpret_cast<const unsigned short*>(vb + perm[slot] * v_ss + vh * D + d);
+        else if (d == D) x = one;
+      }
+      w[j] = x;
+    }
+    uint4 val;
+    val.x = w[0] | (static_cast<uint32_t>(w[1]) << 16);
+    val.y = w[2] | (static_cast<uint32_t>(w[3]) << 16);
+    val.z = w[4] | (static_cast<uint32_t>(w[5]) << 16);
+    val.w = w[6] | (static_cast<uint32_t>(w[7]) << 16);
+    *reinterpret_cast<uint4*>(img + K_BYTES + static_cast<size_t>(e) * 16) = val;
+  }
+}
+
+// [B, L, cols] 16-bit tensor with element strides (sb, sl, 1) -> boxes of box_cols columns x 128 rows, no swizzle
+static bool make_map_plain(CUtensorMap* m, const void* base, int cols, int L, int B, long long sl, long long sb, int box_cols) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(sl) * 2, static_cast<cuuint64_t>(B > 1 ? sb : sl * L) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), ROWS, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// [B, L, cols] 16-bit tensor -> boxes of 64 columns (SWIZZLE_128B) or 32 columns (SWIZZLE_64B) x 128 rows
+static bool make_map_sw(CUtensorMap* m, const void* base, int cols, int L, int B, long long sl, long long sb, int box_cols) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(sl) * 2, static_cast<cuuint64_t>(B > 1 ? sb : sl * L) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), ROWS, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T, bool STATS>
+static cudaError_t launch(XattnParams p, cudaStream_t st) {
+  constexpr int smem = STATS ? STATS_SMEM : FWD_SMEM;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_x3_kernel<T, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  CUtensorMap tm_qa, tm_qb, tm_qp, tm_oa, tm_ob;
+  if (!make_map_sw(&tm_qa, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, 64)) return cudaErrorInvalidValue;
+  if (!make_map_sw(&tm_qb, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, 32)) return cudaErrorInvalidValue;
+  if (!make_map_plain(&tm_qp, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, GW)) return cudaErrorInvalidValue;  // L2 prefetch only
+  if (STATS) {
+    tm_oa = tm_qa;
+    tm_ob = tm_qb;
+  } else {
+    if (!make_map_sw(&tm_oa, p.out, p.H * D, p.L, p.B, p.o_sl, p.o_sb, 64)) return cudaErrorInvalidValue;
+    if (!make_map_sw(&tm_ob, p.out, p.H * D, p.L, p.B, p.o_sl, p.o_sb, 32)) return cudaErrorInvalidValue;
+  }
+  p.n_hg = p.H / HPT;
+  p.n_sl = (p.L + ROWS - 1) / ROWS;
+  p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
+  if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
+  const int sms = sm_count_cached();
+  const int grid = static_cast<int>(p.total < sms ? p.total : sms);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;  // pass 2 may overlap the tail of pass 1 (and pass 1 its predecessor's)
+  return cudaLaunchKernelEx(&cfg, xattn_x3_kernel<T, STATS>, p, tm_qa, tm_qb, tm_qp, tm_oa, tm_ob);
+}
+
+}  // namespace x3
+
+bool x3_supports(int H, int D, int S) { return D == x3::D && S == 77 && H > 0 && H % x3::HPT == 0; }
+
+size_t x3_image_bytes(int B, int H) { return static_cast<size_t>(B) * (H / x3::HPT) * x3::IMG_BYTES; }
+
+cudaError_t run_prepare_kv_x3(const void* k, const void* v, long long k_sb, long long k_ss, long long v_sb, long long v_ss, int B,
+                              int H, int S, int n_active, const int* cols, int dtype, void* image, cudaStream_t st) {
+  x3::ActiveCols ac{};
+  ac.n = n_active;
+  for (int j = 0; j < n_active; ++j) ac.col[j] = cols[j];
+  const int n_hg = H / x3::HPT;
+  if (dtype == DSC_DTYPE_F16)
+    x3::x3_prepare_kv_kernel<__half><<<B * n_hg, 256, 0, st>>>(static_cast<const __half*>(k), static_cast<const __half*>(v), k_sb,
+                                                               k_ss, v_sb, v_ss, S, n_hg, ac, static_cast<unsigned char*>(image));
+  else
+    x3::x3_prepare_kv_kernel<__nv_bfloat16><<<B * n_hg, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(k),
+                                                                     static_cast<const __nv_bfloat16*>(v), k_sb, k_ss, v_sb, v_ss,
+                                                                     S, n_hg, ac, static_cast<unsigned char*>(image));
+  return cudaGetLastError();
+}
+
+cudaError_t run_stats_x3(const XattnParams& p, int dtype, cudaStream_t st) {
+  return dtype == DSC_DTYPE_F16 ? x3::launch<__half, true>(p, st) : x3::launch<__nv_bfloat16, true>(p, st);
+}
+cudaError_t run_forward_x3(const XattnParams& p, int dtype, cudaStream_t st) {
+  return dtype == DSC_DTYPE_F16 ? x3::launch<__half, false>(p, st) : x3::launch<__nv_bfloat16, false>(p, st);
+}
+
+#ifdef DSC_TRACE
+extern "C" int dsc_debug_x3_trace(long long* out /*HOST 2*7*1024*2*/, int* counts /*HOST 2*7*/, unsigned long long* cta /*HOST 2*160*2*/) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, x3::g_x3_trace, sizeof(long long) * 2 * 7 * 1024 * 2);
+  cudaMemcpyFromSymbol(counts, x3::g_x3_trace_n, sizeof(int) * 14);
+  cudaMemcpyFromSymbol(cta, x3::g_x3_cta, sizeof(unsigned long long) * 2 * 160 * 2);
+  int z[14] = {0};
+  cudaMemcpyToSymbol(x3::g_x3_trace_n, z, sizeof(z));
+  return 0;
+}
+#endif
+
+#ifdef DSC_WATCHDOG
+extern "C" int dsc_debug_x3_watchdog(unsigned int* out /*HOST 5*/) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, x3::g_x3_info, 16);
+  cudaMemcpyFromSymbol(out + 4, x3::g_x3_abort, 4);
+  unsigned int z[5] = {0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(x3::g_x3_info, z, 16);
+  cudaMemcpyToSymbol(x3::g_x3_abort, z, 4);
+  return 0;
+}
+#endif
+
+}  // namespace dsc

@@ -12,7 +12,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from .attention import compact_region_map, padded_region_map
+from .attention import compact_region_map, padded_region_map, prepare_kv, prepared_supported, workspace_bytes
 from .attention_processor import RegionAttnProcessor
 from .region_map import encode_region_map
 from .sampler import KarrasSchedule, dpmpp2m_step
@@ -44,8 +44,9 @@ class RegionTxt2ImgPipeline:
     def __init__(self, unet, tokenizer, processor: Optional[RegionAttnProcessor] = None, use_cuda_graph: bool = False):
         self.unet = unet
         self.tokenizer = tokenizer
-        # inside a captured graph the K/V projections are replayed as captured, so the Python-side cache is moot there
-        self.processor = processor if processor is not None else RegionAttnProcessor(cache_kv=not use_cuda_graph)
+        # K / V are projections of the text embeddings: computed once per generation (eager: the processor's cache;
+        # CUDA graph: static buffers refreshed outside the graph, see _refresh_static_kv), never once per step
+        self.processor = processor if processor is not None else RegionAttnProcessor(cache_kv=True)
         self.unet.set_attn_processor(self.processor)  # same hook as reference app.py:479-481
         self.use_cuda_graph = use_cuda_graph
         self._graphs: Dict[tuple, dict] = {}
@@ -91,21 +92,55 @@ class RegionTxt2ImgPipeline:
             self.processor.register_static_map(
                 st["rs"][L], compact=None if c is None else (st["rsc"][L], list(c[1])),
                 zero=c is not None and len(c[1]) == 0)
+        # the 16 x 2 K / V projections (and the K / V^T images of the tcgen05 kernels) live in static buffers
+        # that are refreshed once per generation OUTSIDE the graph: the captured step holds no to_k / to_v GEMM
+        st["kv"] = []
+        for m in self.unet.modules():
+            if getattr(m, "is_cross_attention", False):
+                k = torch.zeros((2 * n, 77, m.to_k.out_features), device=dev, dtype=dt)
+                v = torch.zeros_like(k)
+                head_dim = m.to_k.out_features // m.heads
+                images = {}
+                for L, c in compacts.items():
+                    if c is not None and prepared_supported(m.heads, head_dim, 77, len(c[1])) and tuple(c[1]) not in images:
+                        view = lambda t: t.view(2 * n, 77, m.heads, head_dim).transpose(1, 2)
+                        images[tuple(c[1])] = prepare_kv(view(k), view(v), c[1])
+                st["kv"].append((m, k, v, images))
+                self.processor.register_static_kv(m, st["ctx"], k, v, images)
         rp = {"region_state": st["rs"], "sigma": st["sigma"], "weight_func": weight_func}
         kw = {"region_prompt": rp}
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):  # warm-up on a side stream (allocations, autotuning, workspace)
-            for _ in range(2):
-                self.unet(st["x"], st["t"], st["ctx"], cross_attention_kwargs=kw)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            # (a channels_last UNet returns a channels_last eps: the sampler kernel wants plain NCHW order)
-            st["eps"] = self.unet(st["x"], st["t"], st["ctx"], cross_attention_kwargs=kw).contiguous()
+        # the statistics workspace of this graph: allocated here, outside the capture, and owned by the graph state (the
+        # replays of one graph are serialised on their stream; two graphs never share a ticket word)
+        st["ws"] = torch.zeros(workspace_bytes(2 * n, 8, (height // 8) * (width // 8), 40, 77), dtype=torch.uint8, device=dev)
+        prev_ws, self.processor.workspace = self.processor.workspace, st["ws"]
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):  # warm-up on a side stream (allocations, autotuning)
+                for _ in range(2):
+                    self.unet(st["x"], st["t"], st["ctx"], cross_attention_kwargs=kw)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                # (a channels_last UNet returns a channels_last eps: the sampler kernel wants plain NCHW order)
+                st["eps"] = self.unet(st["x"], st["t"], st["ctx"], cross_attention_kwargs=kw).contiguous()
+        finally:
+            self.processor.workspace = prev_ws
         st["graph"] = g
         self._graphs[key] = st
         return st
+
+    @staticmethod
+    def _refresh_static_kv(st: dict) -> None:
+        """Recompute the static K / V projections (and K / V^T images) from the static text-embedding buffer: once per
+        generation, outside the captured graph."""
+        for m, k, v, images in st["kv"]:
+            k.copy_(m.to_k(st["ctx"]))
+            v.copy_(m.to_v(st["ctx"]))
+            head_dim = k.shape[-1] // m.heads
+            view = lambda t: t.view(t.shape[0], t.shape[1], m.heads, head_dim).transpose(1, 2)
+            for cols, img in images.items():
+                prepare_kv(view(k), view(v), cols, out=img.image)
 
     def unet_ctx_dim(self) -> int:
         for m in self.unet.modules():
@@ -135,6 +170,7 @@ class RegionTxt2ImgPipeline:
         if self.use_cuda_graph:
             st = self._graph_state(n, height, width, region_state, weight_func)
             st["ctx"].copy_(ctx)
+            self._refresh_static_kv(st)
             for L, w in region_state.items():
                 st["rs"][L].copy_(w)
                 if st["rsc"][L] is not None:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSC_VERSION 104 /* major*10000 + minor*100 + patch */
+#define DSC_VERSION 105 /* major*10000 + minor*100 + patch */
 
 #define DSC_DTYPE_F16 0
 #define DSC_DTYPE_BF16 1
@@ -117,6 +117,29 @@ int dsc_xattn_call_cw(const void* q, const void* k, const void* v, const int64_t
                       const float* Wc, int n_active, const int32_t* active_cols /*HOST*/, const float* sigma_dev_or_null,
                       float sigma_host, void* workspace, void* out, const int64_t o_str[3] /*HOST*/, int B, int H, int L,
                       int D, int S, float scale, int dtype, void* stream);
+
+/* ---- prepared K / V: the fast form of the call for the SD-1.5 shapes ---------------------------------------------------
+ * K and V of a cross-attention layer are projections of the text embeddings: they do not change during a generation
+ * (attention_modify.py:465-466 recomputes the same to_k / to_v on each of the 25 steps).  dsc_xattn_prepare_kv lays
+ * them out ONCE as the shared-memory image the tcgen05 kernels multiply from (UMMA K-major chunks of K, V^T with a ones
+ * row, keys permuted so that the active columns of the compact region map come first); dsc_xattn_call_prepared then
+ * runs pass 1 and pass 2 on that image: each CTA fetches K / V^T with one bulk copy instead of re-gathering them.
+ * Supported (dsc_xattn_prepared_supported != 0): D == 40, S == 77, H a multiple of 4, 1 <= n_active <= 16.
+ * The image depends on k, v AND the active column list: prepare again when any of them changes. */
+int dsc_xattn_prepared_supported(int H, int D, int S);
+int dsc_xattn_kv_image_bytes(int B, int H, int D, int S, size_t* out /*HOST*/);
+int dsc_xattn_prepare_kv(const void* k, const void* v, const int64_t k_str[4] /*HOST*/, const int64_t v_str[4] /*HOST*/,
+                         int n_active, const int32_t* active_cols /*HOST*/, int B, int H, int D, int S, int dtype,
+                         void* kv_image, void* stream);
+/* passes: 1 = pass 1 only (std -> workspace), 2 = pass 2 only (std read from the workspace), 3 = the whole call.
+ * Wc / n_active / Bw as in dsc_xattn_call_cw (the column list itself is baked into the image); same result as
+ * dsc_xattn_call_cw on the k, v the image was prepared from. */
+#define DSC_PASS_STATS 1
+#define DSC_PASS_FORWARD 2
+int dsc_xattn_call_prepared(const void* q, const int64_t q_str[4] /*HOST*/, const void* kv_image, const float* Wc, int Bw,
+                            int n_active, const float* sigma_dev_or_null, float sigma_host, void* workspace, void* out,
+                            const int64_t o_str[3] /*HOST*/, int B, int H, int L, int D, int S, float scale, int dtype,
+                            int passes, void* stream);
 
 /* Number of kernel launches dsc_xattn_call will issue for this shape on the current device: 1 (fused), 2 (pass 1 +
  * pass 2) or 2 * chunks + 1 (long prompts); -1 for an unsupported shape.  Introspection only. */
