@@ -139,104 +139,144 @@ def cross_attention_shapes_list():
     return list(cross_attention_shapes(HEIGHT, WIDTH))
 
 
-def attention_roofline(device):
-    """Live CUDA-event timing of the two attention passes (L2 flushed before every launch) on the dominant
-    layer shape of the workload, plus the byte-weighted figure over all 16 layers of one UNet step."""
+def _eager_reference_call(q4, k4, v4, W_cpu, sigma):
+    """The reference's eager op sequence for one region call on the same GPU, fp16, as its processor runs it
+    (attention_modify.py:479-481 + :74-103): the region map is uploaded host -> device on EVERY call (:481)."""
+    from oracle import attention as oa
+
+    return oa.region_attention(q4, k4, v4, W_cpu.to(q4.device), sigma)
+
+
+def _time_call_shape(device, B, H, L, D, S, flush, peak, n_timed=30, eager_reps=3):
+    """CUDA-event time of ONE attention call as the processor issues it (L2 flushed before every timed call, two
+    alternating input sets), plus the eager reference sequence on the same inputs."""
     from diffusionspatialcontrol_b200 import attention as att
-    from diffusionspatialcontrol_b200._lib import check, lib
+
+    vw = lambda t: t.view(B, -1, H, D).transpose(1, 2)
+    sets = []
+    for i in range(2):
+        q = torch.randn(B, L, H * D, device=device, dtype=torch.float16)
+        k = torch.randn(B, S, H * D, device=device, dtype=torch.float16)
+        v = torch.randn(B, S, H * D, device=device, dtype=torch.float16)
+        W = torch.zeros(B, L, S, device=device)
+        W[:, : L // 2, 1:3] = 0.5
+        W = att.padded_region_map(W)  # the device layout encode_region_map produces (rows 80 floats apart)
+        compact = att.compact_region_map(W)  # + the compact form the processor derives once per map
+        prepared = att.prepared_supported(H, D, S, len(compact[1]))
+        kv = att.prepare_kv(vw(k), vw(v), compact[1]) if prepared else None  # once per generation in the pipeline
+        sets.append((q, k, v, W, compact, kv, torch.empty_like(q)))
+    sigma = torch.tensor(7.0, device=device)
+    ws = att.get_workspace(device, att.workspace_bytes(B, H, L, D, S))
+
+    def call(t, passes=3):
+        q, k, v, W, compact, kv, out = t
+        if kv is not None:  # SD-1.5 layers with 40-wide heads: prepared K / V^T image (dsc_xattn_call_prepared)
+            return att.region_attention_prepared(vw(q), kv, compact, sigma, workspace=ws, passes=passes, out=out)
+        return att.region_attention(vw(q), vw(k), vw(v), W, sigma, workspace=ws, compact=compact)  # dsc_xattn_call_cw
+
+    def timed(fn, n):
+        ts = []
+        for it in range(n):
+            flush.zero_()                                        # evict our inputs (512 MiB write) ...
+            flush[: flush.numel() // 2].view(torch.int64).sum()  # ... and leave clean lines behind
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(sets[it % 2]); b.record(); b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return ts
+
+    for i in range(6):
+        call(sets[i % 2])
+    tc = timed(call, n_timed)
+    rec = {"B": B, "L": L, "D": D, "ms_call": sum(tc) / len(tc), "ms_call_median": sorted(tc)[len(tc) // 2], "n_calls": len(tc),
+           "bytes": 2 * B * H * L * D * 3 + 2 * B * H * S * D * 3 + 4 * B * L * S,
+           "path": "prepared" if sets[0][5] is not None else "raw", "launches": 2 if sets[0][5] is not None else lib_launches(B, H, L, D, S)}
+    rec["frac"] = rec["bytes"] / (rec["ms_call"] * 1e-3) / 1e9 / peak
+    if sets[0][5] is not None:
+        rec["ms_stats_alone"] = sum(t1 := timed(lambda t: call(t, 1), 10)) / len(t1)
+        rec["ms_forward_alone"] = sum(t2 := timed(lambda t: call(t, 2), 10)) / len(t2)
+    if eager_reps:
+        q, k, v, W, *_ = sets[0]
+        W_cpu = W.cpu().contiguous()
+        _eager_reference_call(vw(q), vw(k), vw(v), W_cpu, sigma)
+        te = timed(lambda t: _eager_reference_call(vw(t[0]), vw(t[1]), vw(t[2]), W_cpu, sigma), eager_reps)
+        rec["ms_eager_reference"] = sum(te) / len(te)
+        rec["speedup_vs_eager"] = rec["ms_eager_reference"] / rec["ms_call"]
+    return rec
+
+
+def attention_roofline(device, sweep=True):
+    """Live CUDA-event timing of the attention call (L2 flushed before every launch) on the dominant layer shape of the
+    workload, the byte-weighted figure over all 16 layers of one UNet step, and (BASELINE configs[4] / configs[2]) the
+    sweep over every SD-1.5 cross-attention shape x attention batch 2..32 and the 768 x 768 shapes, each next to the
+    reference's eager op sequence on the same GPU."""
     from diffusionspatialcontrol_b200.unet_sd15 import cross_attention_shapes
 
-    I4, I3 = ctypes.c_int64 * 4, ctypes.c_int64 * 3
     B, H, S = 2 * IMAGES_PER_UNIT, 8, 77
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
-    st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-    ws = att.get_workspace(device)
     peak, how = peak_hbm()
+    layer_shapes = list(cross_attention_shapes(HEIGHT, WIDTH))
     per_shape = {}
-    for (L, D) in sorted(set(cross_attention_shapes(HEIGHT, WIDTH)), reverse=True):
-        vw = lambda t: t.view(B, -1, H, D).transpose(1, 2)
-        sc = 1 / math.sqrt(D)
-        sets = []  # two input/output sets used alternately: a timed launch never sees buffers its predecessor touched
-        for i in range(2):
-            q = torch.randn(B, L, H * D, device=device, dtype=torch.float16)
-            k = torch.randn(B, S, H * D, device=device, dtype=torch.float16)
-            v = torch.randn(B, S, H * D, device=device, dtype=torch.float16)
-            W = torch.zeros(B, L, S, device=device)
-            W[:, : L // 2, 1:3] = 0.5
-            W = att.padded_region_map(W)  # the device layout encode_region_map produces (rows 80 floats apart)
-            Wc, cols = att.compact_region_map(W)  # + the compact form the processor derives once per map (2 weighted columns)
-            sets.append((q, k, v, W, torch.empty_like(q), Wc))
-        qs, ks, vs = I4(*vw(sets[0][0]).stride()), I4(*vw(sets[0][1]).stride()), I4(*vw(sets[0][2]).stride())
-        os_ = I3(*sets[0][4].stride())
-
-        cols_arr = (ctypes.c_int32 * len(cols))(*cols)
-
-        def k1(t):
-            q, k, v, W, out, Wc = t
-            check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), qs, ks, None, B, H, L, D, S, sc, 0, ws.data_ptr(), st))
-
-        def k2(t):
-            q, k, v, W, out, Wc = t
-            check(lib.dsc_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, W.stride(1), None, 7.0,
-                                        ws.data_ptr(), out.data_ptr(), os_, B, H, L, D, S, sc, 0, st))
-
-        def call(t):  # one attention call through the C ABI: pass 1 + pass 2 (pass 2 a programmatic dependent launch of
-            q, k, v, W, out, Wc = t  # pass 1), or ONE fused cooperative launch where the problem fits on chip (small layers)
-            check(lib.dsc_xattn_call_cw(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), B, W.stride(1),
-                                        Wc.data_ptr(), len(cols), cols_arr, None, 7.0, ws.data_ptr(), out.data_ptr(), os_,
-                                        B, H, L, D, S, sc, 0, st))
-
-        for i in range(10):
-            call(sets[i % 2])
-        t1, t2, tc = [], [], []
-        n_launch = 0
-        for it in range(50):
-            for fn, acc in ((k1, t1), (k2, t2), (call, tc)):
-                if fn is not call and it >= 20:
-                    continue  # the single passes are informational: 20 samples each
-                flush.zero_()                                  # evict our inputs (512 MiB write) ...
-                flush[: flush.numel() // 2].view(torch.int64).sum()  # ... and leave clean lines behind
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); fn(sets[n_launch % 2]); b.record(); b.synchronize()
-                n_launch += 1
-                acc.append(a.elapsed_time(b))
-        nbytes = 2 * B * H * L * D * 3 + 2 * B * H * S * D * 3 + 4 * B * L * S
-        per_shape[(L, D)] = {"ms_stats": sum(t1) / len(t1), "ms_forward": sum(t2) / len(t2), "ms_call": sum(tc) / len(tc),
-                             "ms_call_median": sorted(tc)[len(tc) // 2], "n_calls": len(tc), "bytes": nbytes}
-        del sets
+    for (L, D) in sorted(set(layer_shapes), reverse=True):
+        per_shape[(L, D)] = _time_call_shape(device, B, H, L, D, S, flush, peak, n_timed=50, eager_reps=3)
     (L0, D0) = max(per_shape, key=lambda s: per_shape[s]["bytes"])
     d = per_shape[(L0, D0)]
-    ach = d["bytes"] / (d["ms_call"] * 1e-3) / 1e9
-    tot_b = sum(per_shape[s]["bytes"] for s in cross_attention_shapes(HEIGHT, WIDTH))
-    tot_t = sum(per_shape[s]["ms_call"] for s in cross_attention_shapes(HEIGHT, WIDTH))
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of both passes from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tot_b = sum(per_shape[s]["bytes"] for s in layer_shapes)
+    tot_t = sum(per_shape[s]["ms_call"] for s in layer_shapes)
+    tot_e = sum(per_shape[s]["ms_eager_reference"] for s in layer_shapes)
+    traffic, traffic_src = None, None  # dram__bytes_read.sum + dram__bytes_write.sum of both passes, ncu --set full
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.isfile(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_call")
-    return {
-        "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-        "peak_source": how,
-        "kernel": "one attention call = dsc_xattn_call_cw, the call the processor makes (at this shape: two tcgen05 kernels, pass 2 a "
-                  "programmatic dependent launch of pass 1 and fed with the compact region map), one CUDA-event pair around it",
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("dram_bytes_per_call"), "static: " + tj.get("source", "profiles/r2_traffic.json")
+    out = {
+        "bound": "hbm", "achieved": d["bytes"] / (d["ms_call"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": d["frac"],
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": how,
+        "kernel": "one attention call as the processor issues it: dsc_xattn_call_prepared (pass 1 + pass 2 = two 3-warpgroup "
+                  "tcgen05 kernels over the K/V^T image prepared once per generation, pass 2 a programmatic dependent launch of "
+                  "pass 1), one CUDA-event pair around the call",
         "shape": {"B": B, "H": H, "L": L0, "D": D0, "S": S, "dtype": "f16"},
         "algorithmic_bytes_per_call": d["bytes"], "avg_ms_call": d["ms_call"], "median_ms_call": d["ms_call_median"],
-        "timed_calls": d["n_calls"],
-        "avg_ms_stats_alone": d["ms_stats"], "avg_ms_forward_alone": d["ms_forward"],
-        "all_16_layers": {"bytes_per_unet_step": tot_b, "ms_per_unet_step": tot_t,
-                          "achieved": tot_b / (tot_t * 1e-3) / 1e9, "frac": tot_b / (tot_t * 1e-3) / 1e9 / peak},
-        "per_shape": {f"{L}x{D}": {"ms_call": v["ms_call"], "bytes": v["bytes"], "launches": lib_launches(B, H, L, D, S),
-                                   "frac": v["bytes"] / (v["ms_call"] * 1e-3) / 1e9 / peak}
+        "timed_calls": d["n_calls"], "avg_ms_stats_alone": d.get("ms_stats_alone"), "avg_ms_forward_alone": d.get("ms_forward_alone"),
+        "all_16_layers": {"bytes_per_unet_step": tot_b, "ms_per_unet_step": tot_t, "achieved": tot_b / (tot_t * 1e-3) / 1e9,
+                          "frac": tot_b / (tot_t * 1e-3) / 1e9 / peak, "ms_eager_reference": tot_e,
+                          "speedup_vs_eager": tot_e / tot_t},
+        "per_shape": {f"{L}x{D}": {k: v[k] for k in ("ms_call", "bytes", "launches", "frac", "path", "ms_eager_reference",
+                                                    "speedup_vs_eager")}
                       for (L, D), v in sorted(per_shape.items(), reverse=True)},
         "l2": "flushed before every timed call (512 MiB write, then a 256 MiB read so that L2 holds clean lines); two input "
-              "sets alternate, so no timed call reads buffers the previous one touched; 10 warm-up calls",
+              "sets alternate, so no timed call reads buffers the previous one touched; warm-up calls first",
     }
+    if sweep:
+        rows = []
+        for (L, D) in sorted(set(layer_shapes), reverse=True):  # BASELINE configs[4]: every shape x attention batch 2..32
+            for Bs in (2, 8, 16, 32):
+                r = per_shape[(L, D)] if Bs == B else _time_call_shape(device, Bs, H, L, D, S, flush, peak, n_timed=20, eager_reps=2)
+                rows.append({"config": 4, **{k: r[k] for k in ("B", "L", "D", "ms_call", "frac", "path", "launches",
+                                                               "ms_eager_reference", "speedup_vs_eager")}})
+        for (L, D) in ((9216, 40), (2304, 80), (576, 160), (144, 160)):  # BASELINE configs[2]: 768 x 768, batch 4 (+ CFG twin)
+            r = _time_call_shape(device, 8, H, L, D, S, flush, peak, n_timed=20, eager_reps=2)
+            rows.append({"config": 2, **{k: r[k] for k in ("B", "L", "D", "ms_call", "frac", "path", "launches",
+                                                           "ms_eager_reference", "speedup_vs_eager")}})
+        out["sweep"] = rows
+    return out
 
 
-def cpu_baseline_sample(n_samples=1, warmup=0):
-    """The reference's CPU path (oracle port: fp32 PyTorch UNet host + restated reference processor +
-    restated DPM++ 2M loop), timed on a BOUNDED sample: one denoising step of a batch-1 generation
-    (UNet batch 2 with CFG, 16 region-masked cross-attention calls).  images/s = 1 / (25 * t_step)."""
-    from diffusionspatialcontrol_b200.unet_sd15 import UNetSD15
+def _load_unet_module():
+    """unet_sd15.py is plain PyTorch: load it by path so that the reference arm never imports the package (and so never
+    maps libdsc_b200.so)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_dsc_unet_sd15", os.path.join(ROOT, "diffusionspatialcontrol_b200", "unet_sd15.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_baseline_sample(n_samples=1, warmup=0, n_img=IMAGES_PER_UNIT):
+    """The reference's CPU path (oracle port: fp32 PyTorch UNet host + restated reference processor + restated DPM++ 2M
+    loop), timed on a BOUNDED sample of the SAME workload as our arm: single denoising steps of the batch-`n_img`
+    generation (UNet batch 2*n_img with CFG, 16 region-masked cross-attention calls per step) on every host core.
+    images/s = n_img / (25 * t_step).  None of our kernels, engine or library is on this path."""
     from oracle import attention as oa
     from oracle import region_map as orm
     from oracle import sampler as osm
@@ -244,15 +284,15 @@ def cpu_baseline_sample(n_samples=1, warmup=0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    unet = UNetSD15().eval()
+    unet = _load_unet_module().UNetSD15().eval()
     unet.set_attn_processor(oa.OracleAttnProcessor())
     cond, uncond = prompt_embeds()
-    ctx = torch.cat([uncond, cond])
-    rs = orm.encode_region_map(region_state_host(), lambda p: VOCAB[p], WIDTH, HEIGHT, 1, text_ids=text_ids())
+    ctx = torch.cat([uncond.expand(n_img, -1, -1), cond.expand(n_img, -1, -1)])
+    rs = orm.encode_region_map(region_state_host(), lambda p: VOCAB[p], WIDTH, HEIGHT, n_img, text_ids=text_ids())
     train = osm.sd15_train_sigmas()
     sig = osm.get_sigmas_karras(DENOISE_STEPS, train[0].item(), train[-1].item())
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(1, 4, HEIGHT // 8, WIDTH // 8, generator=g) * (sig[0] ** 2 + 1) ** 0.5
+    x = torch.randn(n_img, 4, HEIGHT // 8, WIDTH // 8, generator=g) * (sig[0] ** 2 + 1) ** 0.5
     times = []
 
     def eps_fn(x_in, sigma):
@@ -269,29 +309,81 @@ def cpu_baseline_sample(n_samples=1, warmup=0):
                 times.append(dt)
     t_step = sum(times) / len(times)
     return {
-        "value": 1.0 / (DENOISE_STEPS * t_step), "unit": "images/s", "cores": cores, "kind": "port",
-        "sample": f"{len(times)} denoising step(s) of a batch-1 512x512 generation (UNet batch 2, 16 region-masked "
-                  f"cross-attention calls each), fp32, {t_step:.2f} s/step, extrapolated to 25 steps",
+        "value": n_img / (DENOISE_STEPS * t_step), "unit": "images/s", "cores": cores, "kind": "port",
+        "sample": f"{len(times)} denoising step(s) of the batch-{n_img} 512x512 generation (UNet batch {2 * n_img}, 16 region-masked "
+                  f"cross-attention calls each), fp32, {t_step:.2f} s/step; images/s = {n_img} / (25 x s/step)",
         "seconds_per_denoise_step": t_step,
     }, times
 
 
+REFERENCE_ARM_BUDGET_S = 180.0  # timed region of --impl reference: "the whole run ends within a few minutes"
+
+
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is pure Python
+    with no installable package) on our arm's workload.  A timed "step" here is ONE denoising step of the
+    generation (1/25 of our arm's step) so that `--steps K` stays bounded: `ms_per_step` is the time of that step,
+    `value` = batch / (25 x that time).  Batch 8 like our arm whenever K such steps fit the time budget (one probe step at
+    batch 8 decides); otherwise the largest of 4 / 2 / 1 that fits, stated in `config` (the per-image CPU cost is nearly
+    independent of the batch)."""
     if rank != 0:
         return
-    base, times = cpu_baseline_sample(n_samples=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
+    steps = max(1, args.steps)
+    probe, _ = cpu_baseline_sample(n_samples=1, warmup=0, n_img=IMAGES_PER_UNIT)
+    t8 = probe["seconds_per_denoise_step"]
+    n_img = IMAGES_PER_UNIT
+    while n_img > 1 and steps * t8 * n_img / IMAGES_PER_UNIT > REFERENCE_ARM_BUDGET_S:
+        n_img //= 2
+    base, times = cpu_baseline_sample(n_samples=steps, warmup=max(0, min(args.warmup, 1)), n_img=n_img)
     t_step = base["seconds_per_denoise_step"]
     line = {
         "metric": METRIC, "value": base["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_step * DENOISE_STEPS, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "SD1.5-arch UNet random-init, 512x512, 2 regions, DPM++ 2M Karras 25 steps, CFG 7.5, "
-                               "batch 1, reference CPU path (oracle port), bounded sample per step"},
+        "config": {"workload": f"BASELINE configs[1] workload on the host CPU: SD1.5-arch UNet random-init (seed 0), 512x512, 2 regions "
+                               f"('A girl','bridge'), DPM++ 2M Karras 25 steps, CFG 7.5, batch {n_img} (attention batch {2 * n_img}), "
+                               f"fp32, reference CPU path (oracle port)",
+                   "step": f"ONE denoising step of the batch-{n_img} generation (UNet batch {2 * n_img}, 16 region-masked cross-attention "
+                           f"calls): a bounded sample, 1/25 of a generation; value = {n_img} images / (25 x ms_per_step)",
+                   "batch": n_img, "same_batch_as_gpu_arm": n_img == IMAGES_PER_UNIT,
+                   "probe": f"one batch-{IMAGES_PER_UNIT} step took {t8:.1f} s = {IMAGES_PER_UNIT / (DENOISE_STEPS * t8):.4f} images/s; "
+                            f"{steps} timed steps must fit {REFERENCE_ARM_BUDGET_S:.0f} s",
+                   "timed_region": f"{len(times)} such steps, wall clock, all host cores"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_reference_sample(pipe, device, cond, uncond, ids, state, noise):
+    """SURVEY 8d "GPU reference on the same box": the SAME pipeline, UNet, batch 8, fp16 and sampler with the reference's
+    processor (oracle restatement of AttnProcessor2_0: eager PyTorch ops, region map re-uploaded host -> device on every
+    call as attention_modify.py:481 does) installed instead of ours; eager launches as in the reference (no CUDA graph).
+    One whole 25-step generation timed after one warm-up generation."""
+    from diffusionspatialcontrol_b200.pipeline import RegionTxt2ImgPipeline, SyntheticTokenizer
+    from oracle import attention as oa
+    from oracle import region_map as orm
+
+    rs_cpu = orm.encode_region_map(state, lambda p: VOCAB[p], WIDTH, HEIGHT, IMAGES_PER_UNIT, text_ids=ids)  # CPU tensors
+    ours = pipe.processor
+    ref_pipe = RegionTxt2ImgPipeline(pipe.unet, SyntheticTokenizer(VOCAB), processor=oa.OracleAttnProcessor(), use_cuda_graph=False)
+    try:
+        ms = []
+        for it in range(2):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            x = ref_pipe.txt2img(cond, uncond, ids, None, noise, HEIGHT, WIDTH, DENOISE_STEPS, GUIDANCE,
+                                 weight_func=oa.weight_func, region_state=rs_cpu)
+            b.record()
+            b.synchronize()
+            ms.append(a.elapsed_time(b))
+    finally:
+        pipe.unet.set_attn_processor(ours)
+    return {"value": IMAGES_PER_UNIT / (ms[-1] * 1e-3), "unit": "images/s", "ms_per_generation": ms[-1],
+            "what": "same UNet / batch 8 / fp16 / sampler on this GPU with the reference processor (eager PyTorch ops, region "
+                    "map re-uploaded per call) instead of ours, no CUDA graph; one 25-step generation after one warm-up"}, x
 
 
 def run_ours(args, rank, world, local_rank):
@@ -327,9 +419,12 @@ def run_ours(args, rank, world, local_rank):
     total_steps = args.warmup + args.steps
     noises = [unit_noise(rank + world * i, n_img, lat_shape).to(device) for i in range(total_steps)]
 
+    last = {}
+
     def step_resident(i):
         x = pipe.txt2img(cond_d, uncond_d, ids, None, noises[i], HEIGHT, WIDTH, DENOISE_STEPS, GUIDANCE, region_state=rs_d)
-        return gather(x)
+        last["gathered"] = gather(x)
+        return last["gathered"]
 
     for i in range(args.warmup):
         step_resident(i)
@@ -375,6 +470,28 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    # ---- matched outputs (north_star: "scaling ... at matched outputs"; unit definition SURVEY 8e) -----------------
+    # after the timed region rank 0 recomputes, on ITS GPU, the unit another rank produced in the last timed step and
+    # compares it with the slice that rank contributed to the gather: a unit's result must not depend on where it ran
+    dp_match = None
+    if world > 1:
+        peer = world - 1
+        if rank == 0:
+            unit = peer + world * (total_steps - 1)
+            redo = pipe.txt2img(cond_d, uncond_d, ids, None, unit_noise(unit, n_img, lat_shape).to(device), HEIGHT, WIDTH,
+                                DENOISE_STEPS, GUIDANCE, region_state=rs_d).to(torch.float16)
+            theirs = last["gathered"][peer]
+            mine_again = pipe.txt2img(cond_d, uncond_d, ids, None, noises[total_steps - 1], HEIGHT, WIDTH, DENOISE_STEPS, GUIDANCE,
+                                      region_state=rs_d).to(torch.float16)
+            dp_match = {
+                "bit_identical": bool(torch.equal(redo, theirs)),
+                "cosine": float(torch.nn.functional.cosine_similarity(redo.float().flatten(), theirs.float().flatten(), dim=0)),
+                "max_abs_diff": float((redo.float() - theirs.float()).abs().max()),
+                "own_unit_repeat_bit_identical": bool(torch.equal(mine_again, last["gathered"][0])),
+                "what": f"unit {unit} (seeds {unit * n_img}..{unit * n_img + n_img - 1}) computed by rank {peer} of {world} in the last "
+                        f"timed step vs recomputed by rank 0 on its own GPU; fp16 latents as gathered",
+            }
+        dist.barrier()
     if rank != 0:
         return
     images = world * n_img * args.steps
@@ -392,14 +509,30 @@ def run_ours(args, rank, world, local_rank):
         },
         "e2e": {"value": images / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": args.steps * DENOISE_STEPS * (1 + sum(
-            lib_launches(2 * IMAGES_PER_UNIT, 8, L, D, 77) for (L, D) in cross_attention_shapes_list())),
+        # our kernels inside the timed region: per denoising step the fused sampler step + the attention launches of the 16
+        # cross-attention layers; per generation one K / V^T image build for each 40-wide-head layer
+        "gpu_launches": args.steps * (DENOISE_STEPS * (1 + sum(
+            lib_launches(2 * IMAGES_PER_UNIT, 8, L, D, 77) for (L, D) in cross_attention_shapes_list()))
+            + sum(1 for (L, D) in cross_attention_shapes_list() if D == 40)),
         "clocks": clocks,
         "impl": "dsc_b200",
     }
-    line["roofline"] = attention_roofline(device)
+    if dp_match is not None:
+        # "match" = the cross-rank recomputation agrees as well as a repeat on the same rank does: bit-identical when the
+        # PyTorch host picked the same cuDNN / cuBLAS algorithms on both ranks (cudnn.benchmark autotunes per process)
+        line["dp_outputs_match"] = bool(dp_match["bit_identical"] or dp_match["cosine"] >= 0.9999)
+        line["dp_outputs"] = dp_match
+    line["roofline"] = attention_roofline(device, sweep=(world == 1 and not args.no_sweep))
+    if world == 1 and not args.no_gpu_reference:
+        ref, x_ref = gpu_reference_sample(pipe, device, cond_d, uncond_d, ids, state, noises[total_steps - 1])
+        x_ours = pipe.txt2img(cond_d, uncond_d, ids, None, noises[total_steps - 1], HEIGHT, WIDTH, DENOISE_STEPS, GUIDANCE,
+                              region_state=rs_d)
+        ref["final_latent_cosine_ours_vs_reference_processor"] = float(
+            torch.nn.functional.cosine_similarity(x_ours.float().flatten(), x_ref.float().flatten(), dim=0))
+        ref["speedup_e2e_over_gpu_reference"] = line["e2e"]["value"] / ref["value"]
+        line["gpu_reference"] = ref
     if world == 1 and not args.no_cpu_baseline:
-        base, _ = cpu_baseline_sample(n_samples=2, warmup=1)
+        base, _ = cpu_baseline_sample(n_samples=1, warmup=1)  # two batch-8 denoising steps on the host cores (~10-30 s)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
 
@@ -411,6 +544,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -20,6 +20,7 @@ PASS_STATS, PASS_FORWARD, PASS_BOTH = 1, 2, 3
 SIGNATURES = {
     "dsc_version": (c_int, []),
     "dsc_last_error": (c_char_p, []),
+    "dsc_config_set": (c_int, [c_char_p, c_char_p]),
     "dsc_sm_count": (c_int, []),
     "dsc_xattn_workspace_bytes": (c_int, [c_int] * 5 + [POINTER(c_size_t)]),
     "dsc_xattn_stats": (
@@ -94,6 +95,11 @@ def _load() -> ctypes.CDLL:
 
 
 lib = _load()
+
+
+def config_set(key: str, value=None) -> None:
+    """Kernel-selection override (A/B runs, tests); ``None`` restores the default.  See dsc_config_set."""
+    check(lib.dsc_config_set(key.encode(), None if value is None else str(value).encode()))
 
 
 def check(code: int) -> None:

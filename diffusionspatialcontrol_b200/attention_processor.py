@@ -193,6 +193,11 @@ class RegionAttnProcessor:
         self._img_cache.clear()
         self._sigma_cache = None
 
+    def _score_scale(self, attn, head_dim: int) -> Optional[float]:
+        """Factor on Q K^T on the region path.  The SDPA-style reference processor calls its function without ``scale``
+        (attention_modify.py:479-481), i.e. 1/sqrt(head_dim) (:77) whatever ``attn.scale`` says: ``None``."""
+        return None
+
     # -- processor protocol ---------------------------------------------------------------------
     def __call__(
         self,
@@ -275,13 +280,13 @@ class RegionAttnProcessor:
                     kv = self._kv_image(attn, encoder_hidden_states, key, value, compact[1])
                     hidden_states = region_attention_prepared(
                         query, kv, compact, self._sigma_arg(sigma, query.device), workspace=self.workspace,
-                        scale=None)  # the reference always uses 1/sqrt(head_dim) here (:77), not attn.scale
+                        scale=self._score_scale(attn, head_dim))
                 else:
                     hidden_states = region_attention(
                         query, key, value, w_dev,
                         self._sigma_arg(sigma, query.device),
                         attn_mask=attention_mask,
-                        scale=None,
+                        scale=self._score_scale(attn, head_dim),
                         workspace=self.workspace,
                         compact=compact,
                     )
@@ -311,7 +316,12 @@ class RegionAttnProcessorBaddbmm(RegionAttnProcessor):
     ``torch.baddbmm`` variant the reference falls back to when ``F.scaled_dot_product_attention`` is missing
     (source/app.py:479-481).  Its region branch (:164-175 via ``get_attention_scores`` :39-70) computes exactly the
     same scores, std, bias, softmax and PV as the SDPA-style function (bit-identical on CPU fp32), so
-    the same two CUDA passes serve it; the class exists so either reference processor can be swapped by name."""
+    the same two CUDA passes serve it.  The one difference that is part of the contract: its scores are
+    ``alpha = attn.scale`` times Q K^T (``get_attention_scores`` :58-64), not 1/sqrt(head_dim); the two coincide for every
+    SD-1.5 layer (``attn.scale = dim_head ** -0.5``) and differ for a module built with another scale."""
+
+    def _score_scale(self, attn, head_dim: int) -> Optional[float]:
+        return float(attn.scale)
 
 
 def ip_mask_downsample(mask: torch.Tensor, batch_size: int, num_queries: int, value_embed_dim: int) -> torch.Tensor:
@@ -344,6 +354,8 @@ class RegionIPAdapterAttnProcessor(torch.nn.Module):
     ``to_k_ip`` / ``to_v_ip`` projections, optionally gated by a spatial mask, added with its scale (:640-682).
     Same constructor, parameter names (state dicts load unchanged) and call signature."""
 
+    _core_cls = RegionAttnProcessor
+
     def __init__(self, hidden_size, cross_attention_dim=None, num_tokens=(4,), scale=1.0, cache_kv: bool = False):
         super().__init__()
         self.hidden_size = hidden_size
@@ -360,7 +372,7 @@ class RegionIPAdapterAttnProcessor(torch.nn.Module):
             [torch.nn.Linear(cross_attention_dim, hidden_size, bias=False) for _ in range(len(num_tokens))])
         self.to_v_ip = torch.nn.ModuleList(
             [torch.nn.Linear(cross_attention_dim, hidden_size, bias=False) for _ in range(len(num_tokens))])
-        self._core = RegionAttnProcessor(cache_kv=cache_kv)
+        self._core = self._core_cls(cache_kv=cache_kv)
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
                  region_prompt=None, ip_adapter_masks=None):
@@ -405,5 +417,7 @@ class RegionIPAdapterAttnProcessorBaddbmm(RegionIPAdapterAttnProcessor):
     """Drop-in for the reference's ``IPAdapterAttnProcessor`` (source/modules/attention_modify.py:210-411), the
     ``torch.baddbmm`` twin of ``IPAdapterAttnProcessor2_0`` used when ``F.scaled_dot_product_attention`` is missing
     (source/modules/ip_adapter.py:292).  Same scores, std, bias, softmax and P V in the text branch and the same
-    image-prompt terms, so the same CUDA path serves it; the class exists so either reference class can be swapped
-    by name."""
+    image-prompt terms, so the same CUDA path serves it (text-branch scores scaled by ``attn.scale`` like
+    ``RegionAttnProcessorBaddbmm``)."""
+
+    _core_cls = RegionAttnProcessorBaddbmm

@@ -36,16 +36,53 @@ int sm_count_cached() {
   return sms;
 }
 
-// Kernel family per call.  DSC_XATTN_IMPL=mma forces the legacy mma.sync kernels, =tc5 forces tcgen05/TMEM
+static int parse_impl(const char* v) {
+  if (!v || !v[0]) return kImplAuto;
+  if (strcmp(v, "mma") == 0) return kImplMma;
+  if (strcmp(v, "tc5") == 0) return kImplTc5;
+  if (strcmp(v, "gram") == 0) return kImplGram;
+  return kImplAuto;
+}
+static bool parse_flag(const char* v) { return v && v[0] == '1'; }
+
+static bool config_apply(Config& c, const char* key, const char* v) {
+  if (strcmp(key, "xattn_impl") == 0) c.impl = parse_impl(v);
+  else if (strcmp(key, "stats_impl") == 0) c.stats_impl = parse_impl(v);
+  else if (strcmp(key, "no_fused") == 0) c.no_fused = parse_flag(v);
+  else if (strcmp(key, "tc5_fused") == 0) c.tc5_fused = parse_flag(v);
+  else if (strcmp(key, "no_pdl") == 0) c.no_pdl = parse_flag(v);
+  else if (strcmp(key, "tc5_variant") == 0) c.tc5_x2 = v && v[0] == 'x' && v[1] == '2';
+  else if (strcmp(key, "tc5_flags") == 0) c.tc5_flags = v ? static_cast<unsigned>(atoi(v)) : 0u;
+  else return false;
+  return true;
+}
+
+static Config& config_mut() {
+  static Config c = [] {  // the one place the environment is read: once, at first use
+    Config e;
+    config_apply(e, "xattn_impl", getenv("DSC_XATTN_IMPL"));
+    config_apply(e, "stats_impl", getenv("DSC_XATTN_STATS_IMPL"));
+    config_apply(e, "no_fused", getenv("DSC_NO_FUSED"));
+    config_apply(e, "tc5_fused", getenv("DSC_TC5_FUSED"));
+    config_apply(e, "no_pdl", getenv("DSC_NO_PDL"));
+    config_apply(e, "tc5_variant", getenv("DSC_TC5_VARIANT"));
+    config_apply(e, "tc5_flags", getenv("DSC_TC5_FLAGS"));
+    return e;
+  }();
+  return c;
+}
+const Config& config() { return config_mut(); }
+
+// Kernel family per call.  xattn_impl=mma forces the legacy mma.sync kernels, =tc5 forces tcgen05/TMEM
 // wherever it is implemented (D = 40, 80); default "auto" = whichever measured faster on B200 for the head dim
 // (profiles/): tcgen05 at D = 40 and D = 80 (both passes; since pass 1 stages K by TMA it is level with mma.sync at
 // D = 80 too), mma.sync elsewhere.  The two passes only share the std in the workspace, so the families mix freely.
 static bool use_tc5(int D, bool stats) {
-  const char* e = getenv("DSC_XATTN_IMPL");
-  const char* es = getenv("DSC_XATTN_STATS_IMPL");  // pass 1 alone (A/B runs)
-  if (stats && es) e = es;
-  if (e && strcmp(e, "mma") == 0) return false;
-  if (e && strcmp(e, "tc5") == 0) return tc5_supports(D);
+  const Config& c = config();
+  int e = c.impl;
+  if (stats && c.stats_impl != kImplAuto) e = c.stats_impl;  // pass 1 alone (A/B runs)
+  if (e == kImplMma) return false;
+  if (e == kImplTc5) return tc5_supports(D);
   return D == 40 || D == 80;
 }
 
@@ -102,6 +139,12 @@ const char* dsc_last_error(void) { return g_err; }
 
 int dsc_sm_count(void) { return sm_count_cached(); }
 
+int dsc_config_set(const char* key, const char* value_or_null) {
+  if (!key) return fail(DSC_ERR_INVALID_ARGUMENT, "key is null");
+  if (!config_apply(config_mut(), key, value_or_null)) return fail(DSC_ERR_INVALID_ARGUMENT, "unknown configuration key '%s'", key);
+  return DSC_OK;
+}
+
 int dsc_xattn_workspace_bytes(int B, int H, int L, int D, int S, size_t* out) {
   if (!out) return fail(DSC_ERR_INVALID_ARGUMENT, "out is null");
   if (B <= 0 || H <= 0 || L <= 0 || D <= 0 || S <= 0) return fail(DSC_ERR_INVALID_ARGUMENT, "non-positive dimension");
@@ -136,8 +179,7 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
   p.fold_chunks = 1;
   cudaError_t e = cudaSuccess;
   if (C == 1) {
-    const char* es = getenv("DSC_XATTN_STATS_IMPL");
-    const bool gram = es ? strcmp(es, "gram") == 0 : false;
+    const bool gram = config().stats_impl == kImplGram;
     if (gram && gram_supports(D, S)) e = run_stats_gram(p, D, dtype, static_cast<cudaStream_t>(stream));
     else
       e = use_tc5(D, true) ? run_stats_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
@@ -158,16 +200,14 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
 // Which form dsc_xattn_call takes: 0 = two launches, 1 = single launch with Q resident in shared memory (mma.sync family,
 // small problems), 2 = single launch, two phases over the tile list (tcgen05 family, D = 40 / 80).
 static int call_form(int B, int H, int L, int D, int S) {
-  const char* nf = getenv("DSC_NO_FUSED");
-  if (n_chunks(S) > 1 || (nf && nf[0] == '1')) return 0;
-  const char* impl = getenv("DSC_XATTN_IMPL");
-  const bool want_mma = impl && strcmp(impl, "mma") == 0, want_tc5 = impl && strcmp(impl, "tc5") == 0;
+  const Config& c = config();
+  if (n_chunks(S) > 1 || c.no_fused) return 0;
+  const bool want_mma = c.impl == kImplMma, want_tc5 = c.impl == kImplTc5;
   if (!want_tc5 && fused_plan(B, H, L, D, S, nullptr)) return 1;
   // Form 2 is opt-in (DSC_TC5_FUSED=1): measured on B200 it only ties the two-launch form at D = 40 (62.3 vs 62.5 us --
   // programmatic dependent launch already hides pass 2's prologue behind the tail of pass 1) and loses at D = 80
   // (45 vs 42 us, where pass 1 is faster on the mma.sync kernel).
-  const char* tf = getenv("DSC_TC5_FUSED");
-  if (!want_mma && tf && tf[0] == '1' && tc5_fused_supports(D)) return 2;
+  if (!want_mma && c.tc5_fused && tc5_fused_supports(D)) return 2;
   return 0;
 }
 

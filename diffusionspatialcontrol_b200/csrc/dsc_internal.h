@@ -49,6 +49,21 @@ struct XattnParams {
   const void* kv_image;  // 3-warpgroup tcgen05 kernels: prepared K / V^T images (dsc_xattn_prepare_kv), one per (batch, head group)
 };
 
+// Kernel-selection overrides (A/B runs, tests).  Filled ONCE from the environment when the library is loaded
+// (DSC_XATTN_IMPL, DSC_XATTN_STATS_IMPL, DSC_NO_FUSED, DSC_TC5_FUSED, DSC_NO_PDL, DSC_TC5_FLAGS, DSC_TC5_VARIANT);
+// afterwards only dsc_config_set changes it.  No attention call touches the environment.
+enum Impl { kImplAuto = 0, kImplMma = 1, kImplTc5 = 2, kImplGram = 3 };
+struct Config {
+  int impl = kImplAuto;        // both passes
+  int stats_impl = kImplAuto;  // pass 1 alone (kImplAuto: follow impl)
+  bool no_fused = false;       // never take the single-launch forms
+  bool tc5_fused = false;      // single-launch two-phase tcgen05 form (opt-in)
+  bool no_pdl = false;         // no programmatic dependent launch
+  bool tc5_x2 = false;         // 2-warpgroup tcgen05 variant instead of x4
+  unsigned tc5_flags = 0;      // launch_tc5x4 mode bits
+};
+const Config& config();
+
 int sm_count_cached();
 int heads_per_group(int D);  // 0 if D is unsupported
 int stats_grid(long long total);

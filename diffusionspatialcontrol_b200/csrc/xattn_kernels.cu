@@ -1016,9 +1016,8 @@ static cudaError_t launch_forward(const XattnParams& p_in, cudaStream_t st) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  const char* nopdl = getenv("DSC_NO_PDL");
   cfg.attrs = attr;
-  cfg.numAttrs = (nopdl && nopdl[0] == '1') ? 0 : 1;  // may overlap the tail of pass 1 (griddepcontrol.wait before beta)
+  cfg.numAttrs = config().no_pdl ? 0 : 1;  // may overlap the tail of pass 1 (griddepcontrol.wait before beta)
   return cudaLaunchKernelEx(&cfg, xattn_forward_kernel<T, D>, p, tm_q, tm_k, tm_v, tm_w);
 }
 

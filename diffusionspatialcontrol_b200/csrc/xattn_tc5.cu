@@ -1577,9 +1577,8 @@ static cudaError_t launch_tc5(XattnParams p, cudaStream_t st) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  const char* nopdl = getenv("DSC_NO_PDL");
   cfg.attrs = attr;
-  cfg.numAttrs = (!STATS && !(nopdl && nopdl[0] == '1')) ? 1 : 0;
+  cfg.numAttrs = (!STATS && !config().no_pdl) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, xattn_tc5_kernel<T, D, STATS>, p, tm_q, tm_o);
 }
 
@@ -1634,7 +1633,7 @@ static cudaError_t launch_tc5x4_fused(XattnParams p, cudaStream_t st) {
   if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
   const int sms = sm_count_cached();
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
-  static const unsigned env_flags = [] { const char* e = getenv("DSC_TC5_FLAGS"); return e ? static_cast<unsigned>(atoi(e)) : 0u; }();
+  const unsigned env_flags = config().tc5_flags;
   p.flags = env_flags & 3u;
   CUtensorMap tm_w = tm_q;
   if (!(env_flags & 8u) && p.w_pitch == DSC_MAX_KEYS && p.S == 77 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0) {
@@ -1681,7 +1680,7 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
   // experiment knobs (A/B runs): bit 0 one mbarrier arrival per warp, bit 1 MMA issuers spin instead of
   // nanosleep-polling, bit 3 do not use the padded-W fast path
-  static const unsigned env_flags = [] { const char* e = getenv("DSC_TC5_FLAGS"); return e ? static_cast<unsigned>(atoi(e)) : 0u; }();
+  const unsigned env_flags = config().tc5_flags;
   p.flags = env_flags & 3u;
   CUtensorMap tm_w = tm_q;
   bool compact = false;
@@ -1702,9 +1701,8 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  const char* nopdl = getenv("DSC_NO_PDL");
   cfg.attrs = attr;
-  cfg.numAttrs = !(nopdl && nopdl[0] == '1') ? 1 : 0;  // pass 2 may overlap the tail of pass 1 (and pass 1 its predecessor's)
+  cfg.numAttrs = config().no_pdl ? 0 : 1;  // pass 2 may overlap the tail of pass 1 (and pass 1 its predecessor's)
   if constexpr (!STATS) {
     if (compact) {
       static thread_local int cw_dev = -1;
@@ -1724,8 +1722,7 @@ static cudaError_t launch_tc5x4(XattnParams p, cudaStream_t st) {
 // pipelined heads).  DSC_TC5_VARIANT=x2 selects the latter for A/B runs.
 static bool use_x4(int D) {
   if (D != 40 && D != 80) return false;
-  const char* e = getenv("DSC_TC5_VARIANT");
-  return !(e && e[0] == 'x' && e[1] == '2');
+  return !config().tc5_x2;
 }
 
 bool tc5_supports(int D) { return D == 40 || D == 80; }

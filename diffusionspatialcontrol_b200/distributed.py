@@ -42,15 +42,14 @@ def run_sharded(generate: Callable[[int], torch.Tensor], n_units: int) -> torch.
         rank, world = dist.get_rank(), dist.get_world_size()
     else:
         rank, world = 0, 1
+    if world > 1 and n_units < world:  # same verdict on every rank, before any work or collective: nobody hangs
+        raise ValueError(f"every rank needs at least one unit (n_units={n_units} < world_size={world})")
     mine = units_for_rank(n_units, rank, world)
     local = [generate(u) for u in mine]
     if world == 1:
         return torch.stack(local) if local else torch.empty(0)
     per_rank = (n_units + world - 1) // world
-    proto = local[0] if local else None
-    shape = torch.tensor(list(proto.shape) if proto is not None else [0], device=proto.device if proto is not None else "cpu")
-    if proto is None:
-        raise ValueError("every rank needs at least one unit (n_units >= world_size)")
+    proto = local[0]
     buf = proto.new_zeros((per_rank, *proto.shape))
     for i, t in enumerate(local):
         buf[i] = t
@@ -60,5 +59,4 @@ def run_sharded(generate: Callable[[int], torch.Tensor], n_units: int) -> torch.
     for r in range(world):
         for i, u in enumerate(units_for_rank(n_units, r, world)):
             out[u] = gathered[r][i]
-    del shape
     return out

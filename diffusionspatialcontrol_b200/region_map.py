@@ -102,7 +102,13 @@ def encode_region_map_sp(state, tokenizer, unet, width, height, scale_ratio=8, t
             if v["map"] is None:
                 continue
             phrases.append(_tokenize(tokenizer, k))
-            maps.append(np.ascontiguousarray(np.asarray(v["map"])))
+            m = np.asarray(v["map"])
+            if m.dtype != np.uint8:
+                # the reference tests `map < 255` in the map's OWN dtype (encode_region_map_function.py:49); a uint8 cast
+                # would wrap 300 -> 44 ("inside") or -1 -> 255 ("outside"): binarise here, in the original dtype, into the
+                # two uint8 values the device-side `< 255` test tells apart
+                m = np.where(m < 255, 0, 255).astype(np.uint8)
+            maps.append(np.ascontiguousarray(m))
             weight.append(float(v["weight"]))
             outside.append(float(v["mask_outsides"]))
     cond_spans, cond_found = _spans(cond, phrases)

@@ -264,7 +264,6 @@ class UNetSD15(nn.Module):
         self.conv_in = nn.Conv2d(in_channels, ch[0], 3, padding=1)
         self.time_embedding = nn.ModuleDict({"linear_1": nn.Linear(ch[0], ch[0] * 4), "linear_2": nn.Linear(ch[0] * 4, ch[0] * 4)})
         temb = ch[0] * 4
-        assert temb == 1280 or True
         self.down_blocks = nn.ModuleList()
         cout = ch[0]
         for i, c in enumerate(ch):

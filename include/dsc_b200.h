@@ -4,8 +4,8 @@
  * takes plain pointers and sizes (device pointers unless marked HOST), enqueues its work on the
  * given CUDA stream and returns immediately: 0 = ok, <0 = DSC_ERR_* (invalid argument /
  * unsupported configuration, nothing was launched), >0 = cudaError_t from the launch.  No entry
- * point synchronises the host, throws, or keeps global mutable state (dsc_last_error is
- * thread-local).  `stream` is a cudaStream_t passed as void*.
+ * point synchronises the host or throws; dsc_last_error is thread-local and the only process-wide
+ * state is the kernel-selection table of dsc_config_set (read-only for every other entry point).  `stream` is a cudaStream_t passed as void*.
  *
  * Reference interfaces replaced (paths relative to the reference repository root):
  *   dsc_xattn_stats + dsc_xattn_forward
@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSC_VERSION 105 /* major*10000 + minor*100 + patch */
+#define DSC_VERSION 106 /* major*10000 + minor*100 + patch */
 
 #define DSC_DTYPE_F16 0
 #define DSC_DTYPE_BF16 1
@@ -48,6 +48,14 @@ int dsc_version(void);
 
 /* Message for the last non-zero return on the calling thread ("" if none). */
 const char* dsc_last_error(void);
+
+/* Kernel-selection overrides for A/B runs and tests; the defaults are the measured-fastest choice per shape.
+ * The environment (DSC_XATTN_IMPL, DSC_XATTN_STATS_IMPL, DSC_NO_FUSED, DSC_TC5_FUSED, DSC_NO_PDL, DSC_TC5_VARIANT,
+ * DSC_TC5_FLAGS) is read ONCE, when the library is first used; no attention call ever calls getenv.  Afterwards only
+ * this function changes the table:  key in {"xattn_impl" (mma|tc5), "stats_impl" (mma|tc5|gram), "no_fused" (1),
+ * "tc5_fused" (1), "no_pdl" (1), "tc5_variant" (x2), "tc5_flags" (int)}; value NULL or "" restores the default.
+ * Process-wide: not to be called concurrently with attention calls. */
+int dsc_config_set(const char* key /*HOST*/, const char* value_or_null /*HOST*/);
 
 /* Number of SMs the persistent kernels will be sized for on the current device (148 on B200). */
 int dsc_sm_count(void);

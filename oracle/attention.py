@@ -6,6 +6,7 @@ Follows:
   scaled_dot_product_attention_regionstate  /root/reference/source/modules/attention_modify.py:74-103
   weight_func (lambda)                      /root/reference/source/app.py:1004
   AttnProcessor2_0.__call__                 /root/reference/source/modules/attention_modify.py:414-503
+  AttnProcessor.__call__ (baddbmm variant)  /root/reference/source/modules/attention_modify.py:107-207, :39-70
 
 Pinned: tests/test_oracle_attention.py runs the *unmodified* reference module (oracle/ref_loader.py)
 next to this restatement in the build container and requires bit-identical fp32 outputs; the same
@@ -87,6 +88,41 @@ def processor_forward(attn, hidden_states, encoder_hidden_states=None, region_pr
     out = out.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
     if ip_branch is not None:  # IP-Adapter image-prompt terms (attention_modify.py:640-682), see oracle/ip_adapter.py
         out = ip_branch(out, query, batch_size, head_dim)
+    out = attn.to_out[0](out)
+    out = attn.to_out[1](out)
+    if getattr(attn, "residual_connection", False):
+        out = out + residual
+    return out / getattr(attn, "rescale_output_factor", 1.0)
+
+
+def processor_forward_baddbmm(attn, hidden_states, encoder_hidden_states=None, region_prompt=None):
+    """attention_modify.py:107-207 (``AttnProcessor``, the ``torch.baddbmm`` variant) with ``get_attention_scores``
+    (:39-70) for the SD-1.5 case (3-D input, no mask, no norms, no upcasts).  Differences from the SDPA-style processor
+    that are part of the contract: scores are ``alpha = attn.scale`` times ``Q K^T`` formed by ``torch.baddbmm`` over a
+    [B*H, L, S] batch (the std the weight_func sees is over that tensor: same numbers, another shape), softmax + ``bmm``.
+    """
+    residual = hidden_states
+    img_sequence_length = hidden_states.shape[1]
+    is_xattn = encoder_hidden_states is not None and region_prompt is not None
+    query = attn.to_q(hidden_states)
+    ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
+    key, value = attn.to_k(ctx), attn.to_v(ctx)
+
+    def head_to_batch_dim(t):  # diffusers Attention.head_to_batch_dim, out_dim=3
+        b, n, c = t.shape
+        return t.reshape(b, n, attn.heads, c // attn.heads).permute(0, 2, 1, 3).reshape(b * attn.heads, n, c // attn.heads)
+
+    query, key, value = head_to_batch_dim(query), head_to_batch_dim(key), head_to_batch_dim(value)
+    empty = torch.empty(query.shape[0], query.shape[1], key.shape[1], dtype=query.dtype, device=query.device)
+    scores = torch.baddbmm(empty, query, key.transpose(-1, -2), beta=0, alpha=attn.scale).to(query.dtype)  # :39-70
+    if is_xattn and isinstance(region_prompt["region_state"], dict):
+        w = region_prompt["region_state"][img_sequence_length].to(query.device)
+        cw = region_prompt["weight_func"](w, region_prompt["sigma"], scores)
+        scores += torch.repeat_interleave(cw, repeats=scores.shape[0] // cw.shape[0], dim=0)
+    probs = scores.softmax(dim=-1).to(query.dtype)
+    out = torch.bmm(probs, value)
+    bh, n, d = out.shape  # batch_to_head_dim
+    out = out.reshape(bh // attn.heads, attn.heads, n, d).permute(0, 2, 1, 3).reshape(bh // attn.heads, n, d * attn.heads)
     out = attn.to_out[0](out)
     out = attn.to_out[1](out)
     if getattr(attn, "residual_connection", False):

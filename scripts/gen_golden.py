@@ -7,6 +7,8 @@ the reference tree does not exist.  Everything is seeded; re-running reproduces 
   attn_*.npz     inputs (fp16-representable, stored as float16) + fp32 output of the reference's
                  scaled_dot_product_attention_regionstate (attention_modify.py:74-103) with the
                  reference weight_func (app.py:1004), and the std it saw
+  proc_baddbmm_*.npz  module weights + inputs (float16) + fp32 output of the reference's ``AttnProcessor`` (the
+                 torch.baddbmm variant, attention_modify.py:107-207) on the region path
   region_*.npz   inputs (uint8 maps, strengths, token ids) + the fp32 maps returned by the reference's
                  encode_region_map (encode_region_map_function.py:79-124, which calls cv2.resize)
 """
@@ -125,9 +127,70 @@ def gen_attn():
         print(name, tuple(out.shape), float(std))
 
 
+def load_numpy_weights(attn, seed):
+    """fp16-representable weights from numpy's legacy generator (bit-stable across versions): the fixtures store only the
+    seed.  tests/helpers.py holds the same function."""
+    rng = np.random.RandomState(seed)
+    with torch.no_grad():
+        for _, prm in sorted(attn.named_parameters()):
+            w = (rng.standard_normal(tuple(prm.shape)) * (1.0 / np.sqrt(prm.shape[-1]))).astype(np.float16)
+            prm.copy_(torch.from_numpy(w.astype(np.float32)))
+
+
+def gen_proc_baddbmm():
+    """proc_baddbmm_*.npz: the reference's ``AttnProcessor`` (baddbmm variant, attention_modify.py:107-207) run on a small
+    SD-1.5-shaped attention module: fp16-representable weights / inputs, fp32 output."""
+    import torch.nn as nn
+
+    ref = ref_loader.attention_modify()
+
+    class Attn(nn.Module):
+        upcast_attention = upcast_softmax = False
+
+        def __init__(self, C, H, D):
+            super().__init__()
+            self.heads, self.scale = H, D**-0.5
+            self.to_q, self.to_k, self.to_v = nn.Linear(C, H * D, bias=False), nn.Linear(768, H * D, bias=False), nn.Linear(768, H * D, bias=False)
+            self.to_out = nn.ModuleList([nn.Linear(H * D, C), nn.Dropout(0.0)])
+            self.spatial_norm = self.group_norm = self.norm_cross = None
+            self.residual_connection, self.rescale_output_factor = False, 1.0
+
+        def head_to_batch_dim(self, t, out_dim=3):
+            b, n, c = t.shape
+            t = t.reshape(b, n, self.heads, c // self.heads).permute(0, 2, 1, 3)
+            return t.reshape(b * self.heads, n, c // self.heads) if out_dim == 3 else t
+
+        def batch_to_head_dim(self, t):
+            bh, n, d = t.shape
+            return t.reshape(bh // self.heads, self.heads, n, d).permute(0, 2, 1, 3).reshape(bh // self.heads, n, d * self.heads)
+
+        def prepare_attention_mask(self, m, *_a, **_k):
+            return m
+
+    for name, C, H, D, B, L, sigma in (("proc_baddbmm_L256_D40", 320, 8, 40, 2, 256, 5.0),
+                                       ("proc_baddbmm_L64_D160", 1280, 8, 160, 2, 64, 11.0)):
+        attn = Attn(C, H, D)
+        seed = len(name) + L
+        load_numpy_weights(attn, seed)
+        g = torch.Generator().manual_seed(L)
+        hs = torch.randn(B, L, C, generator=g).half().float()
+        ctx = torch.randn(B, 77, 768, generator=g).half().float()
+        W = torch.zeros(B, L, 77)
+        W[:, : L // 2, 1:3] = 0.5
+        W[:, L // 3 :, 6] += 0.7
+        W[:, L // 4 : L // 2, 3] = -0.25
+        rp = {"region_state": {L: W.clone()}, "sigma": torch.tensor(sigma), "weight_func": weight_func}
+        with torch.no_grad():
+            out = ref.AttnProcessor()(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), hs=hs.half().numpy(), ctx=ctx.half().numpy(), W=W.numpy(),
+                            sigma=np.float32(sigma), heads=H, head_dim=D, weight_seed=seed, out=out.numpy())
+        print(name, tuple(out.shape))
+
+
 if __name__ == "__main__":
     if not ref_loader.reference_available():
         sys.exit("reference tree not available: golden fixtures can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
     gen_region()
     gen_attn()
+    gen_proc_baddbmm()

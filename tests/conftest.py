@@ -37,3 +37,20 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture
+def dsc_config():
+    """Kernel-selection overrides through the C ABI (dsc_config_set), restored to the defaults afterwards.  The library
+    reads the DSC_* environment variables only once, at first use, so tests switch families through this call."""
+    from diffusionspatialcontrol_b200 import _lib
+
+    touched = []
+
+    def set_(key, value):
+        touched.append(key)
+        _lib.config_set(key, value)
+
+    yield set_
+    for key in touched:
+        _lib.config_set(key, None)

@@ -74,3 +74,62 @@ def make_qkv(B, H, L, D, S, seed, dtype=torch.float16, device="cpu", sink=2.0):
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).norm() / b.norm())
+
+
+
+def load_numpy_weights(attn, seed):
+    """Same as scripts/gen_golden.py::load_numpy_weights: fp16-representable weights from numpy's legacy generator
+    (bit-stable across versions), so the proc_* fixtures store only the seed."""
+    rng = np.random.RandomState(seed)
+    with torch.no_grad():
+        for _, prm in sorted(attn.named_parameters()):
+            w = (rng.standard_normal(tuple(prm.shape)) * (1.0 / np.sqrt(prm.shape[-1]))).astype(np.float16)
+            prm.copy_(torch.from_numpy(w.astype(np.float32)))
+
+
+class AttnModule(torch.nn.Module):
+    """Duck-typed diffusers ``Attention`` with everything both reference processors touch
+    (attention_modify.py:107-207 needs head_to_batch_dim / batch_to_head_dim / prepare_attention_mask / scale)."""
+
+    upcast_attention = False
+    upcast_softmax = False
+
+    def __init__(self, C, H, D, ctx=768):
+        super().__init__()
+        nn = torch.nn
+        self.heads, self.scale = H, D**-0.5
+        self.to_q, self.to_k, self.to_v = nn.Linear(C, H * D, bias=False), nn.Linear(ctx, H * D, bias=False), nn.Linear(ctx, H * D, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(H * D, C), nn.Dropout(0.0)])
+        self.spatial_norm = self.group_norm = self.norm_cross = None
+        self.residual_connection, self.rescale_output_factor = False, 1.0
+
+    def head_to_batch_dim(self, t, out_dim=3):
+        b, n, c = t.shape
+        t = t.reshape(b, n, self.heads, c // self.heads).permute(0, 2, 1, 3)
+        return t.reshape(b * self.heads, n, c // self.heads) if out_dim == 3 else t
+
+    def batch_to_head_dim(self, t):
+        bh, n, d = t.shape
+        return t.reshape(bh // self.heads, self.heads, n, d).permute(0, 2, 1, 3).reshape(bh // self.heads, n, d * self.heads)
+
+    def prepare_attention_mask(self, m, *_a, **_k):
+        return m
+
+    def get_attention_scores(self, query, key, attention_mask=None):
+        """diffusers ``Attention.get_attention_scores`` (third party; the reference's non-region branch calls it, :188):
+        softmax of ``scale * Q K^T``."""
+        empty = torch.empty(query.shape[0], query.shape[1], key.shape[1], dtype=query.dtype, device=query.device)
+        scores = torch.baddbmm(empty, query, key.transpose(-1, -2), beta=0, alpha=self.scale)
+        return scores.softmax(dim=-1).to(query.dtype)
+
+
+def baddbmm_fixture(path):
+    """(attn fp32 module, hs, ctx, region_prompt, reference output) of a tests/golden/proc_baddbmm_*.npz fixture."""
+    z = np.load(path)
+    H, D = int(z["heads"]), int(z["head_dim"])
+    hs, ctx = torch.from_numpy(z["hs"]).float(), torch.from_numpy(z["ctx"]).float()
+    attn = AttnModule(hs.shape[-1], H, D)
+    load_numpy_weights(attn, int(z["weight_seed"]))
+    rp = {"region_state": {hs.shape[1]: torch.from_numpy(z["W"]).clone()}, "sigma": torch.tensor(float(z["sigma"])),
+          "weight_func": weight_func}
+    return attn, hs, ctx, rp, torch.from_numpy(z["out"])

@@ -25,6 +25,22 @@ def _worker(rank, world, port, n_units, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_too_few(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from diffusionspatialcontrol_b200.distributed import run_sharded
+
+    calls = []
+    try:
+        run_sharded(lambda u: calls.append(u) or _fake_generate(u), 1)
+        verdict = "no error"
+    except ValueError as e:
+        verdict = f"ValueError after {len(calls)} generate calls: {e}"
+    with open(os.path.join(out_dir, f"r{rank}.txt"), "w") as f:
+        f.write(verdict)
+    dist.destroy_process_group()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -49,3 +65,12 @@ def test_noise_depends_on_seed_only():
     a = unit_noise(1, 8, (4, 8, 8))
     b = unit_noise(0, 16, (4, 8, 8))
     assert torch.equal(a, b[8:])
+
+
+def test_fewer_units_than_ranks_raises_on_every_rank_before_any_work(tmp_path):
+    """a rank without units used to raise only after its peers had entered the all_gather (they hung).  The
+    check now runs first, with the same verdict on every rank, before any generate() call or collective."""
+    mp.spawn(_worker_too_few, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in (0, 1):
+        txt = (tmp_path / f"r{r}.txt").read_text()
+        assert txt.startswith("ValueError after 0 generate calls"), txt

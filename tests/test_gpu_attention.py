@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True, params=["tc5", "tc5-padded", "mma", "mma-padded", "fused", "fused-padded", "tc5fused", "tc5fused-padded",
                                       "tc5-compact"])
-def impl(request, monkeypatch):
+def impl(request, monkeypatch, dsc_config):
     """Every test runs against both kernel families: tcgen05/TMEM (default where implemented: D=40, 80)
     and the legacy mma.sync path (all head dims; also the cross-check of the first) -- and with the region map in
     both device layouts: dense [B', L, 77] as the reference builds it, and the padded fast layout (rows 80 floats
@@ -31,9 +31,9 @@ def impl(request, monkeypatch):
     # "fused": the single-launch mma.sync kernel (both passes, Q resident on chip) wherever the problem fits, two-pass
     # mma.sync elsewhere; "tc5fused": the single-launch two-phase tcgen05 kernel (D = 40 / 80), two-pass elsewhere;
     # "mma" / "tc5": always two launches
-    monkeypatch.setenv("DSC_XATTN_IMPL", {"fused": "mma", "tc5fused": "tc5"}.get(family, family))
-    monkeypatch.setenv("DSC_NO_FUSED", "0" if family in ("fused", "tc5fused") else "1")
-    monkeypatch.setenv("DSC_TC5_FUSED", "1" if family == "tc5fused" else "0")
+    dsc_config("xattn_impl", {"fused": "mma", "tc5fused": "tc5"}.get(family, family))
+    dsc_config("no_fused", "0" if family in ("fused", "tc5fused") else "1")
+    dsc_config("tc5_fused", "1" if family == "tc5fused" else "0")
     if layout == "compact":  # tcgen05 pass 2 fed with the compact region map (weighted key columns only, keys permuted)
         from diffusionspatialcontrol_b200 import attention as att
 
@@ -270,11 +270,11 @@ def test_processor_matches_reference_processor_restatement(C, D, L):
         proc(attn16, hs[:, :64], encoder_hidden_states=ctx, region_prompt=rp)
 
 
-def test_tc5_two_warpgroup_variant_matches_oracle(monkeypatch):
+def test_tc5_two_warpgroup_variant_matches_oracle(dsc_config):
     """D = 40 has two tcgen05 variants; the default tests exercise x4, this one forces x2 (software-pipelined heads)."""
     dsc, _ = _dsc()
-    monkeypatch.setenv("DSC_XATTN_IMPL", "tc5")
-    monkeypatch.setenv("DSC_TC5_VARIANT", "x2")
+    dsc_config("xattn_impl", "tc5")
+    dsc_config("tc5_variant", "x2")
     for (B, H, L, S) in [(2, 8, 1024, 77), (16, 8, 4096, 77), (3, 12, 200, 40)]:
         q, k, v = make_qkv(B, H, L, 40, S, seed=L + S, device="cuda")
         W = synthetic_w(B, L, S).cuda()
@@ -321,11 +321,11 @@ def test_long_prompts_run_as_key_chunks(L, D, S, B):
 
 
 @pytest.mark.parametrize("B,L,S", [(2, 1024, 77), (16, 4096, 77), (3, 200, 40), (1, 64, 77), (4, 9216, 80)])
-def test_gram_identity_stats_kernel(monkeypatch, B, L, S):
+def test_gram_identity_stats_kernel(dsc_config, B, L, S):
     """DSC_XATTN_STATS_IMPL=gram: pass 1 without forming a single score (sum a^2 = scale^2 <Q^T Q, K^T K>, SURVEY 8(f)
     rank 2), D = 40.  Same published statistics as the score-based kernels, and the forward pass that consumes them."""
     dsc, att = _dsc()
-    monkeypatch.setenv("DSC_XATTN_STATS_IMPL", "gram")
+    dsc_config("stats_impl", "gram")
     q, k, v = make_qkv(B, 8, L, 40, S, seed=B + L, device="cuda")
     st = att.read_stats(att.score_stats(q, k))
     want, wsum, wsq = _std64(q, k)
@@ -380,12 +380,12 @@ def test_ip_adapter_processor_matches_oracle(n_adapters, with_masks):
 
 
 @pytest.mark.parametrize("D,L", [(40, 1024), (80, 512)])
-def test_compact_region_map_edge_cases(D, L, monkeypatch):
+def test_compact_region_map_edge_cases(D, L, dsc_config):
     """The compact form (weighted key columns only) with the maximum of 16 columns incl. the first and the last key,
     in arbitrary positions; 17 columns have no compact form and take the dense map."""
     dsc, att = _dsc()
-    monkeypatch.setenv("DSC_XATTN_IMPL", "tc5")
-    monkeypatch.setenv("DSC_NO_FUSED", "1")
+    dsc_config("xattn_impl", "tc5")
+    dsc_config("no_fused", "1")
     B, S = 2, 77
     q, k, v = make_qkv(B, 8, L, D, S, seed=D + L, device="cuda")
     g = torch.Generator().manual_seed(5)

@@ -13,7 +13,7 @@ import torch.nn as nn
 from oracle import attention as oa
 from oracle import ref_loader
 
-from .helpers import make_qkv, synthetic_w, weight_func
+from .helpers import AttnModule, baddbmm_fixture, make_qkv, synthetic_w, weight_func
 
 needs_ref = pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not present")
 
@@ -120,3 +120,30 @@ def test_reference_baddbmm_processor_equals_sdpa_style_processor():
         b = ref.AttnProcessor2_0()(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)
         c = oa.processor_forward(attn, hs, ctx, rp)
     assert torch.allclose(a, b, atol=2e-6, rtol=1e-5) and torch.equal(b, c)
+
+
+@needs_ref
+def test_oracle_baddbmm_processor_matches_reference_processor():
+    """the oracle's restatement of ``AttnProcessor`` (attention_modify.py:107-207, :39-70) is bit-identical
+    to the unmodified reference class."""
+    ref = ref_loader.attention_modify()
+    torch.manual_seed(8)
+    for C, H, D, L in ((320, 8, 40, 96), (640, 8, 80, 40)):
+        attn = AttnModule(C, H, D)
+        hs, ctx = torch.randn(2, L, C), torch.randn(2, 77, 768)
+        rp = {"region_state": {L: synthetic_w(2, L, 77)}, "sigma": torch.tensor(3.0), "weight_func": weight_func}
+        with torch.no_grad():
+            a = ref.AttnProcessor()(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)
+            b = oa.processor_forward_baddbmm(attn, hs, ctx, rp)
+            a_self = ref.AttnProcessor()(attn_self := AttnModule(C, H, D, ctx=C), hs, region_prompt=rp)
+            b_self = oa.processor_forward_baddbmm(attn_self, hs, None, rp)
+        assert torch.equal(a, b) and torch.equal(a_self, b_self)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "proc_baddbmm_*.npz"))))
+def test_oracle_baddbmm_processor_matches_golden(path):
+    """... and to the outputs the reference class produced (scripts/gen_golden.py), which travel to the GPU box."""
+    attn, hs, ctx, rp, want = baddbmm_fixture(path)
+    with torch.no_grad():
+        got = oa.processor_forward_baddbmm(attn, hs, ctx, rp)
+    assert torch.allclose(got, want, atol=1e-6, rtol=1e-5)
