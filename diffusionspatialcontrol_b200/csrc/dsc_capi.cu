@@ -354,8 +354,8 @@ int dsc_xattn_prepared_supported(int H, int D, int S) { return x3_supports(H, D,
 int dsc_xattn_kv_image_bytes(int B, int H, int D, int S, size_t* out) {
   if (!out) return fail(DSC_ERR_INVALID_ARGUMENT, "out is null");
   if (B <= 0) return fail(DSC_ERR_INVALID_ARGUMENT, "non-positive batch");
-  if (!x3_supports(H, D, S)) return fail(DSC_ERR_UNSUPPORTED, "prepared K/V: need D == 40, S == 77, H %% 4 == 0 (H=%d D=%d S=%d)", H, D, S);
-  *out = x3_image_bytes(B, H);
+  if (!x3_supports(H, D, S)) return fail(DSC_ERR_UNSUPPORTED, "prepared K/V: need D in {40, 80, 160}, S == 77, whole 160-column head groups (H=%d D=%d S=%d)", H, D, S);
+  *out = x3_image_bytes(B, H, D);
   return DSC_OK;
 }
 
@@ -372,12 +372,12 @@ int dsc_xattn_prepare_kv(const void* k, const void* v, const int64_t k_str[4], c
                          const int32_t* active_cols, int B, int H, int D, int S, int dtype, void* kv_image, void* stream) {
   int rc = check_dims(B, H, 1, D, S, dtype);
   if (rc) return rc;
-  if (!x3_supports(H, D, S)) return fail(DSC_ERR_UNSUPPORTED, "prepared K/V: need D == 40, S == 77, H %% 4 == 0 (H=%d D=%d S=%d)", H, D, S);
+  if (!x3_supports(H, D, S)) return fail(DSC_ERR_UNSUPPORTED, "prepared K/V: need D in {40, 80, 160}, S == 77, whole 160-column head groups (H=%d D=%d S=%d)", H, D, S);
   if (!kv_image || !aligned16(kv_image)) return fail(DSC_ERR_INVALID_ARGUMENT, "kv_image must be a 16-byte aligned device buffer");
   if ((rc = check_bhxd("k", k, k_str, D))) return rc;
   if ((rc = check_bhxd("v", v, v_str, D))) return rc;
   if ((rc = check_cols(n_active, active_cols, S))) return rc;
-  cudaError_t e = run_prepare_kv_x3(k, v, k_str[0], k_str[2], v_str[0], v_str[2], B, H, S, n_active, active_cols, dtype, kv_image,
+  cudaError_t e = run_prepare_kv_x3(k, v, k_str[0], k_str[2], v_str[0], v_str[2], B, H, D, S, n_active, active_cols, dtype, kv_image,
                                     static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_prepare_kv");
 }
@@ -387,7 +387,7 @@ int dsc_xattn_call_prepared(const void* q, const int64_t q_str[4], const void* k
                             int B, int H, int L, int D, int S, float scale, int dtype, int passes, void* stream) {
   int rc = check_dims(B, H, L, D, S, dtype);
   if (rc) return rc;
-  if (!x3_supports(H, D, S)) return fail(DSC_ERR_UNSUPPORTED, "prepared K/V: need D == 40, S == 77, H %% 4 == 0 (H=%d D=%d S=%d)", H, D, S);
+  if (!x3_supports(H, D, S)) return fail(DSC_ERR_UNSUPPORTED, "prepared K/V: need D in {40, 80, 160}, S == 77, whole 160-column head groups (H=%d D=%d S=%d)", H, D, S);
   if (passes < 1 || passes > 3) return fail(DSC_ERR_INVALID_ARGUMENT, "passes must be 1, 2 or 3");
   if (!workspace || !kv_image || !aligned16(kv_image)) return fail(DSC_ERR_INVALID_ARGUMENT, "null / misaligned workspace or kv_image");
   if ((rc = check_bhxd("q", q, q_str, D))) return rc;
@@ -406,9 +406,9 @@ int dsc_xattn_call_prepared(const void* q, const int64_t q_str[4], const void* k
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
   if (passes & DSC_PASS_STATS) {
-    if (stats_grid(static_cast<long long>(B) * (H / 4) * ((L + 127) / 128)) > kMaxPartials)
+    if (stats_grid(static_cast<long long>(B) * (H * D / 160) * ((L + 127) / 128)) > kMaxPartials)
       return fail(DSC_ERR_UNSUPPORTED, "grid exceeds the workspace's partial slots");
-    e = run_stats_x3(p, dtype, st);
+    e = run_stats_x3(p, D, dtype, st);
     if (e != cudaSuccess) return cuda_fail(e, "dsc_xattn_call_prepared (pass 1)");
   }
   if (passes & DSC_PASS_FORWARD) {
@@ -425,7 +425,7 @@ int dsc_xattn_call_prepared(const void* q, const int64_t q_str[4], const void* k
     p.Bw = Bw;
     p.sigma_dev = sigma_dev_or_null;
     p.sigma_host = sigma_host;
-    e = run_forward_x3(p, dtype, st);
+    e = run_forward_x3(p, D, dtype, st);
     if (e != cudaSuccess) return cuda_fail(e, "dsc_xattn_call_prepared (pass 2)");
   }
   return DSC_OK;

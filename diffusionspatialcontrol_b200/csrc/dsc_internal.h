@@ -86,13 +86,14 @@ cudaError_t run_forward_tc5(const XattnParams& p, int D, int dtype, cudaStream_t
 bool tc5_fused_supports(int D);  // both passes in one cooperative launch
 cudaError_t run_fused_tc5(const XattnParams& p, int D, int dtype, cudaStream_t st);
 
-// 3-warpgroup tcgen05 kernels over a prepared K / V^T image (xattn_x3.cu): D = 40, S = 77, H % 4 == 0, compact region map
+// decoupled-warpgroup tcgen05 kernels over a prepared K / V^T image (xattn_x3.cu): D in {40, 80, 160}, S = 77, whole
+// 160-column head groups (H % 4 / H % 2 / any H), compact region map
 bool x3_supports(int H, int D, int S);
-size_t x3_image_bytes(int B, int H);
+size_t x3_image_bytes(int B, int H, int D);
 cudaError_t run_prepare_kv_x3(const void* k, const void* v, long long k_sb, long long k_ss, long long v_sb, long long v_ss, int B,
-                              int H, int S, int n_active, const int* cols, int dtype, void* image, cudaStream_t st);
-cudaError_t run_stats_x3(const XattnParams& p, int dtype, cudaStream_t st);
-cudaError_t run_forward_x3(const XattnParams& p, int dtype, cudaStream_t st);
+                              int H, int D, int S, int n_active, const int* cols, int dtype, void* image, cudaStream_t st);
+cudaError_t run_stats_x3(const XattnParams& p, int D, int dtype, cudaStream_t st);
+cudaError_t run_forward_x3(const XattnParams& p, int D, int dtype, cudaStream_t st);
 
 cudaError_t run_region_downsample(const uint8_t* maps, int R, int Hpx, int Wpx, int w_r, int h_r, uint8_t* ds,
                                   uint32_t* any_set, cudaStream_t st);

@@ -38,29 +38,53 @@
 
 namespace dsc {
 
+#ifndef X3_TURNS
+#define X3_TURNS 2      // pass 2, 3 warpgroups: at most this many of the three warps that share an SM sub-partition exponentiate at a time (0 = off)
+#endif
+#ifndef X3_L2_PREFETCH
+#define X3_L2_PREFETCH 1  // tile i + NST is pulled towards L2 when tile i is loaded
+#endif
+
 namespace x3 {
+constexpr int X3_TURNS_DEFAULT = X3_TURNS;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int D = 40, HPT = 4, GW = 160, ROWS = 128, NWG = 3;
-constexpr int THREADS = 512, CONSUMERS = NWG * 128;
-// TMEM columns of one warpgroup
-constexpr int WG_COLS = 168, S_COL = 0, P_COL = 80, O_COL = 120, S1_COL = 80;
+constexpr int GW = 160, ROWS = 128;  // a tile: 128 query rows x one 160-column head group (4 / 2 / 1 heads of 40 / 80 / 160)
 // ring stage: Q / O tile = boxes [0,64) | [64,128) (SW128, 16 KB each) | [128,160) (SW64, 8 KB), then the compact W tile
 constexpr int BOX128_BYTES = ROWS * 128, BOX64_BYTES = ROWS * 64;
 constexpr int QT_BYTES = 2 * BOX128_BYTES + BOX64_BYTES;               // 40960
 constexpr int CW_BYTES = ROWS * DSC_COMPACT_PITCH * 4;                 // 10240
 constexpr int FWD_STAGE = QT_BYTES + CW_BYTES, FWD_NST = 3;            // 51200
 constexpr int STATS_STAGE = QT_BYTES, STATS_NST = 4;
-// prepared K / V^T image of one (batch, head group): see dsc_xattn_prepare_kv
-constexpr int K_CH = DSC_MAX_KEYS * 16, K_HEAD = 6 * K_CH, K_BYTES = HPT * K_HEAD;         // 1280, 7680, 30720
-constexpr int VT_CH = 48 * 16, VT_HEAD = 10 * VT_CH, VT_BYTES = HPT * VT_HEAD;             // 768, 7680, 30720
-constexpr int IMG_BYTES = K_BYTES + VT_BYTES;                                              // 61440
 constexpr int BAR_BYTES = 256;
-constexpr int FWD_SMEM = IMG_BYTES + FWD_NST * FWD_STAGE + BAR_BYTES;                      // 215296
-constexpr int STATS_SMEM = K_BYTES + STATS_NST * STATS_STAGE + BAR_BYTES;                  // 194816
-static_assert(IMG_BYTES % 1024 == 0 && K_BYTES % 1024 == 0 && FWD_STAGE % 1024 == 0 && STATS_STAGE % 1024 == 0, "alignment");
-static_assert(FWD_SMEM <= 227 * 1024 && STATS_SMEM <= 227 * 1024, "shared memory budget");
-static_assert(NWG * WG_COLS <= 512, "TMEM budget");
-constexpr int kProducerTid = 12 * 32;
+constexpr int S_COL = 0, P_COL = 80, O_COL = 120, S1_COL = 80;         // TMEM columns of one warpgroup: S | P | O (pass 1: S | S)
+constexpr int K_CH = DSC_MAX_KEYS * 16;                                // one 8-column chunk of K: 80 key slots x 16 B
+constexpr int round_1k(int x) { return (x + 1023) / 1024 * 1024; }
+
+// Per head dim.  Head h of a group starts at column HD * h; its contraction runs over the KSTEPS 16-column blocks that cover
+// it (HD = 40: 3 blocks, partly shared with a neighbour -- the K image is zero there; HD = 80 / 160: 5 / 10 whole blocks).
+// P V has N = ON columns: the head's HD value columns, the ones column (softmax row sum), zero padding to a multiple of 16.
+// A warpgroup owns 120 + ON TMEM columns, so 3 / 2 / 1 warpgroups fit the 512 columns.
+template <int HD>
+struct Cfg {
+  static_assert(HD == 40 || HD == 80 || HD == 160, "head dim");
+  static constexpr int D = HD, HPT = GW / HD, LOG_HPT = HD == 40 ? 2 : HD == 80 ? 1 : 0;
+  static constexpr int NWG = HD == 40 ? 3 : HD == 80 ? 2 : 1;
+  static constexpr int THREADS = NWG * 128 + 128, CONSUMERS = NWG * 128;
+  static constexpr int KSTEPS = HD == 40 ? 3 : HD / 16, NKC = 2 * KSTEPS;
+  static constexpr int ON = HD == 40 ? 48 : HD == 80 ? 96 : 176;
+  static constexpr int WG_COLS = O_COL + ON;
+  static constexpr int CPH = HD / 8;                                   // 16-byte chunks of a head's O row
+  static constexpr int K_HEAD = NKC * K_CH, K_BYTES = round_1k(HPT * K_HEAD);
+  static constexpr int VT_CH = ON * 16, VT_HEAD = 10 * VT_CH, VT_BYTES = HPT * VT_HEAD;
+  static constexpr int IMG_BYTES = round_1k(K_BYTES + VT_BYTES);      // prepared K / V^T image of one (batch, head group)
+  static constexpr int FWD_SMEM = IMG_BYTES + FWD_NST * FWD_STAGE + BAR_BYTES;
+  static constexpr int STATS_SMEM = K_BYTES + STATS_NST * STATS_STAGE + BAR_BYTES;
+  static constexpr int kProducerTid = CONSUMERS;
+  static constexpr int TURNS = NWG == 3 ? X3_TURNS_DEFAULT : 0;
+  static_assert(IMG_BYTES % 1024 == 0 && K_BYTES % 1024 == 0 && FWD_STAGE % 1024 == 0 && STATS_STAGE % 1024 == 0, "alignment");
+  static_assert(FWD_SMEM <= 227 * 1024 && STATS_SMEM <= 227 * 1024, "shared memory budget");
+  static_assert(NWG * WG_COLS <= 512 && 2 * S1_COL * NWG <= 512, "TMEM budget");
+};
 
 struct Tile {
   int b, hg, tile, l0;
@@ -153,9 +177,12 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 }
 #define X3_TRACE_DECL                                                                                   \
   int tr_n = 0;                                                                                         \
+  const int tr_c = Cfg<HD>::CONSUMERS;                                                                  \
   const int tr_k = blockIdx.x != 0 ? -1                                                                 \
-                   : (threadIdx.x & 127) == 0 && threadIdx.x < 384 ? (int)(threadIdx.x >> 7)            \
-                   : threadIdx.x == 384 ? 3 : (threadIdx.x >= 416 && (threadIdx.x & 31) == 0) ? 4 + (int)((threadIdx.x - 416) >> 5) : -1;
+                   : (threadIdx.x & 127) == 0 && (int)threadIdx.x < tr_c ? (int)(threadIdx.x >> 7)      \
+                   : (int)threadIdx.x == tr_c ? 3                                                       \
+                   : ((int)threadIdx.x >= tr_c + 32 && (int)threadIdx.x < tr_c + 32 * (1 + Cfg<HD>::NWG) && (threadIdx.x & 31) == 0) \
+                       ? 4 + (int)((threadIdx.x - tr_c - 32) >> 5) : -1;
 #define X3_TRACE(tag)                                            \
   do {                                                           \
     if (tr_k >= 0 && tr_n < 1024) {                              \
@@ -171,24 +198,15 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 #define X3_CTA_TIME(k) do {} while (0)
 #endif
 
-#ifndef X3_DRAIN_AT
-#define X3_DRAIN_AT 23  // key pair of the current item after which the previous item's O row is taken out of TMEM
-#endif
-#ifndef X3_PREPASS
-#define X3_PREPASS 0    // row max of the NEXT item taken from TMEM while the current item is still being exponentiated
-#endif
-#ifndef X3_TURNS
-#define X3_TURNS 2      // pass 2: at most this many of the three warps that share an SM sub-partition exponentiate at a time (0 = off)
-#endif
-#ifndef X3_L2_PREFETCH
-#define X3_L2_PREFETCH 1  // tile i + NST is pulled towards L2 when tile i is loaded
-#endif
-
-template <typename T, bool STATS>
-__global__ void __launch_bounds__(THREADS, 1)
+template <typename T, int HD, bool STATS>
+__global__ void __launch_bounds__(Cfg<HD>::THREADS, 1)
 xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, const __grid_constant__ CUtensorMap tm_qb,
                 const __grid_constant__ CUtensorMap tm_qp, const __grid_constant__ CUtensorMap tm_oa,
                 const __grid_constant__ CUtensorMap tm_ob) {
+  using C = Cfg<HD>;
+  constexpr int D = C::D, HPT = C::HPT, LOG_HPT = C::LOG_HPT, NWG = C::NWG, CONSUMERS = C::CONSUMERS, WG_COLS = C::WG_COLS;
+  constexpr int K_HEAD = C::K_HEAD, K_BYTES = C::K_BYTES, VT_CH = C::VT_CH, VT_HEAD = C::VT_HEAD, IMG_BYTES = C::IMG_BYTES;
+  constexpr int kProducerTid = C::kProducerTid, SW0 = 4 * NWG;  // first service warp
   constexpr int NST = STATS ? STATS_NST : FWD_NST;
   constexpr int STAGE = STATS ? STATS_STAGE : FWD_STAGE;
   constexpr int KV = STATS ? K_BYTES : IMG_BYTES;
@@ -197,7 +215,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   X3_TRACE_DECL
   X3_CTA_TIME(0);
   X3_TRACE(1);
-  if (warp == 15 && lane < 5) {  // hide the descriptor fetches behind the rest of the prologue
+  if (warp == SW0 + 3 && lane < 5) {  // hide the descriptor fetches behind the rest of the prologue
     const CUtensorMap* m = lane == 0 ? &tm_qa : lane == 1 ? &tm_qb : lane == 2 ? &tm_qp : lane == 3 ? &tm_oa : &tm_ob;
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
   }
@@ -275,7 +293,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       X3_TRACE(6);
     }
   }
-  if (warp == 14) {
+  if (warp == SW0 + 2) {
     if (lane >= 4 && lane < 28 && lane != 8) {
       const uint32_t cnt = lane < 8 ? HPT * 128u : lane == 9 ? static_cast<uint32_t>(CONSUMERS) : lane < 16 ? 1u : lane < 25 ? 128u : 1u;
       mbar_init(bars + 8 * lane, cnt);
@@ -283,7 +301,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     }
     if (lane >= 28) turn_ptr[lane - 28] = 0u;  // whose turn it is on each SM sub-partition (pass 2)
   }
-  if (warp == 13) {
+  if (warp == SW0 + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
                      smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)))
                  : "memory");
@@ -296,7 +314,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   const uint32_t tmem_base = *tmem_ptr_smem;
   X3_TRACE(2);
 
-  if (warp >= 12) {
+  if (warp >= SW0) {
     if (tid == kProducerTid) {
       // ============================== producer: TMA loads and stores ===============================
       uint32_t n_run = 0;
@@ -332,11 +350,11 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       }
       for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) tile_done(i);
       if constexpr (!STATS) bulk_wait0();
-    } else if (lane == 0 && warp >= 13) {
+    } else if (lane == 0 && warp > SW0 && warp - SW0 - 1 < NWG) {
       // ============================== tensor-core issuer of warpgroup g ============================
-      const int g = warp - 13;
+      const int g = warp - SW0 - 1;
       constexpr uint32_t idesc_qk = idesc_f16<T>(80);
-      constexpr uint32_t idesc_pv = idesc_f16<T>(48);
+      constexpr uint32_t idesc_pv = idesc_f16<T>(C::ON);
       const uint32_t tw = tmem_base + g * WG_COLS;
       uint32_t nqk = 0, npv = 0, n_run = 0;
       for (int r0 = 0; r0 < n_items;) {
@@ -348,7 +366,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
         X3_TRACE(41);
         ++n_run;
         auto qk = [&](int j) {
-          const int i = r0 + (j >> 2), h = j & 3, s = i % NST;
+          const int i = r0 + (j >> LOG_HPT), h = j & (HPT - 1), s = i % NST;
           X3_TRACE(42);
           wait_bar<true>(b_full + 8 * s, (i / NST) & 1, 4);
           uint32_t buf = 0;
@@ -364,11 +382,11 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           const uint32_t sQ = sStage + s * STAGE;
           const uint32_t d = tw + (STATS ? buf * S1_COL : S_COL);
           const uint32_t kb = s0 + h * K_HEAD;
-          // head h = the three 16-column blocks that cover columns 40h .. 40h+39 (the K image is zero where a block's
-          // columns belong to a neighbour); block t: boxes of 4 blocks (SW128) for t < 8, the SW64 box for t = 8, 9
+          // head h = the KSTEPS 16-column blocks that cover columns HD*h .. HD*h + HD-1 (HD = 40: the K image is zero where a
+          // block's columns belong to a neighbour); block t: boxes of 4 blocks (SW128) for t < 8, the SW64 box for t = 8, 9
           const int t0b = (h * D) >> 4;
 #pragma unroll
-          for (int ks = 0; ks < 3; ++ks) {
+          for (int ks = 0; ks < C::KSTEPS; ++ks) {
             const int t = t0b + ks;
             const uint64_t ad = t < 8 ? smem_desc_sw128(sQ + (t >> 2) * BOX128_BYTES + (t & 3) * 32)
                                       : smem_desc_sw64(sQ + 2 * BOX128_BYTES + (t - 8) * 32);
@@ -381,7 +399,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
         for (int j = g; j < nit; j += NWG) {
           if (j + NWG < nit) qk(j + NWG);
           if constexpr (!STATS) {
-            const int h = j & 3;
+            const int h = j & (HPT - 1);
             X3_TRACE(45);
             wait_bar<true>(b_prdy + 8 * g, npv & 1, 6);
             X3_TRACE(46);
@@ -407,23 +425,30 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     float beta_l2 = 0.f;  // sigma * std * log2(e); read after pass 1 has completed (PDL), right before first use
     bool have_beta = STATS;
     const float scale_l2 = p.scale * kLog2e;
+    // logits in the log2 domain.  Compact region map: the weighted key columns are slots 0..15 (keys permuted in the
+    // prepared image), one 80-byte row of W per query.  y = s * a + w * bw, 2^(e * y - e * max(y)): a = scale / beta,
+    // bw = 1, e = beta -- or, for a vanishing beta, a = scale, bw = beta, e = 1   (set once, when beta is known)
+    bool bpos = true;
+    float ca = 0.f, cbw = 1.f, ce = 1.f;
+    // sigma does not depend on pass 1 (whatever wrote it completed before pass 1 released its dependents): fetched now, so
+    // that a DRAM-cold line is not waited for after the std has arrived
+    float sigma_v = 0.f;
+    if constexpr (!STATS) sigma_v = p.sigma_dev ? __ldcg(p.sigma_dev) : p.sigma_host;
     double dsum = 0.0, dsq = 0.0;
     uint32_t n_s = 0, n_o = 0;
     bool pend = false;  // an O row of this thread still sits in TMEM
     int pend_s = 0, pend_h = 0;
-    bool pre_waited = false;  // the next item's S has already been waited for and its row max taken (m_next)
-    float m_next = 0.f;
-    // The exponentials of an item ("M phase": 77 MUFU.EX2 per row, the bottleneck pipe: 4 lanes per clock and SM
-    // sub-partition) are SERIALISED per sub-partition in item order: warp (g, quarter) waits until turn[quarter] equals
-    // its item's sequence number.  Left alone, the three warps of a sub-partition run in lock-step -- they share the MUFU
-    // pipe fairly, so they finish their M phases together and then all do their MUFU-free work (S row out of TMEM, W,
-    // row max, O drain, barriers: ~1300 cycles) while the pipe idles (profiles/r2_x3_trace_lockstep.txt: 3.3k cycles per
-    // round of 3 items against 1.85k of MUFU work).  With turns, one warp exponentiates at the full pipe rate while the
-    // other two do their MUFU-free part.
+    // 3 warpgroups (HD = 40): the exponentials of an item ("M phase": 77 MUFU.EX2 per row, the bottleneck pipe: 4 lanes per
+    // clock and SM sub-partition) are SERIALISED per sub-partition in item order: warp (g, quarter) waits until
+    // turn[quarter] is within TURNS of its item's sequence number.  Left alone, the three warps of a sub-partition run in
+    // lock-step -- they share the MUFU pipe fairly, so they finish their M phases together and then all do their MUFU-free
+    // work (S row out of TMEM, W, row max, O drain, barriers: ~1300 cycles) while the pipe idles
+    // (profiles/r2_x3_trace_lockstep.txt: 3.3k cycles per round of 3 items against 1.85k of MUFU work).  With turns, one or
+    // two warps exponentiate at the full pipe rate while the others do their MUFU-free part.
     volatile uint32_t* my_turn = turn_ptr + (warp & 3);
     uint32_t seq_base = 0;  // items of the CTA's earlier runs
 
-    // O row of the warpgroup's previous item: TMEM -> x 1/rowsum (ones row of V^T: column 40) -> over the row's own Q
+    // O row of the warpgroup's previous item: TMEM -> x 1/rowsum (ones row of V^T: column HD) -> over the row's own Q
     // columns in the ring stage, stage handed back
     auto drain = [&]() {
       X3_TRACE(13);
@@ -432,10 +457,10 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       ++n_o;
       tc_fence_after();
       unsigned char* st = smem + KV + pend_s * STAGE;
-      // 16-byte chunk c of the head's O row = global chunk G = 5h + c of the 160-column tile row: the place its Q columns
-      // had (swizzled: 8 consecutive rows hit 8 distinct bank groups)
+      // 16-byte chunk c of the head's O row = global chunk G = (HD/8) h + c of the 160-column tile row: the place its Q
+      // columns had (swizzled: 8 consecutive rows hit 8 distinct bank groups)
       auto dst_of = [&](int c) -> unsigned char* {
-        const int G = pend_h * 5 + c;
+        const int G = pend_h * C::CPH + c;
         return G < 16 ? st + (G >> 3) * BOX128_BYTES + row * 128 + (((G & 7) ^ (row & 7)) << 4)
                       : st + 2 * BOX128_BYTES + row * 64 + ((((G - 16) & 3) ^ ((row >> 1) & 3)) << 4);
       };
@@ -452,23 +477,48 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
         v.w = Mma<T>::pack(t[6], t[7]);
         *reinterpret_cast<uint4*>(d) = v;
       };
-      float oa[16], oz[4];
-      tmem_ld_x16(tw + O_COL, reinterpret_cast<uint32_t*>(oa));
-      tmem_ld_x4(tw + O_COL + 40, reinterpret_cast<uint32_t*>(oz));
-      tc_wait_ld();
-      const float inv = 1.f / oz[0];
-      float ob[16];
-      tmem_ld_x16(tw + O_COL + 16, reinterpret_cast<uint32_t*>(ob));
-      chunk(oa, inv, dst_of(0));
-      chunk(oa + 8, inv, dst_of(1));
-      tc_wait_ld();
-      float oc[8];
-      tmem_ld_x8(tw + O_COL + 32, reinterpret_cast<uint32_t*>(oc));
-      chunk(ob, inv, dst_of(2));
-      chunk(ob + 8, inv, dst_of(3));
-      tc_wait_ld();
-      tc_fence_before();  // the O columns may be overwritten by the next P V once this thread has arrived on prdy
-      chunk(oc, inv, dst_of(4));
+      if constexpr (HD == 40) {
+        float oa[16], oz[4];
+        tmem_ld_x16(tw + O_COL, reinterpret_cast<uint32_t*>(oa));
+        tmem_ld_x4(tw + O_COL + 40, reinterpret_cast<uint32_t*>(oz));
+        tc_wait_ld();
+        const float inv = 1.f / oz[0];
+        float ob[16];
+        tmem_ld_x16(tw + O_COL + 16, reinterpret_cast<uint32_t*>(ob));
+        chunk(oa, inv, dst_of(0));
+        chunk(oa + 8, inv, dst_of(1));
+        tc_wait_ld();
+        float oc[8];
+        tmem_ld_x8(tw + O_COL + 32, reinterpret_cast<uint32_t*>(oc));
+        chunk(ob, inv, dst_of(2));
+        chunk(ob + 8, inv, dst_of(3));
+        tc_wait_ld();
+        tc_fence_before();  // the O columns may be overwritten by the next P V once this thread has arrived on odone / prdy
+        chunk(oc, inv, dst_of(4));
+      } else {
+        // HD = 80 / 160: the row sum (column HD) first, then PIECE columns at a time (16 at HD = 80, where the 80 scores of
+        // the current item are live in registers; 32 at HD = 160), the next piece in flight while the current one is
+        // scaled, packed and stored
+        constexpr int PIECE = HD == 160 ? 32 : 16, NP = HD / PIECE;
+        float oz[4], oa[PIECE], ob[PIECE];
+        auto ld_piece = [&](int pc, float* dst) {
+          if constexpr (PIECE == 32) tmem_ld_x32(tw + O_COL + PIECE * pc, reinterpret_cast<uint32_t*>(dst));
+          else tmem_ld_x16(tw + O_COL + PIECE * pc, reinterpret_cast<uint32_t*>(dst));
+        };
+        tmem_ld_x4(tw + O_COL + HD, reinterpret_cast<uint32_t*>(oz));
+        ld_piece(0, oa);
+        tc_wait_ld();
+        const float inv = 1.f / oz[0];
+#pragma unroll
+        for (int pc = 0; pc < NP; ++pc) {
+          float* cur = (pc & 1) ? ob : oa;
+          if (pc + 1 < NP) ld_piece(pc + 1, (pc & 1) ? oa : ob);
+#pragma unroll
+          for (int q = 0; q < PIECE / 8; ++q) chunk(cur + 8 * q, inv, dst_of((PIECE / 8) * pc + q));
+          if (pc + 1 < NP) tc_wait_ld();
+        }
+        tc_fence_before();
+      }
       fence_proxy_async();  // O rows -> visible to the TMA store
       mbar_arrive(b_odone + 8 * pend_s);
       X3_TRACE(15);
@@ -480,7 +530,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       const int r1 = min(n_items, r0 + p.n_sl - t0.tile);
       const int nit = HPT * (r1 - r0);
       for (int j = g; j < nit; j += NWG) {
-        const int i = r0 + (j >> 2), h = j & 3, s = i % NST;
+        const int i = r0 + (j >> LOG_HPT), h = j & (HPT - 1), s = i % NST;
         float sc[80];
         if constexpr (STATS) {
           const uint32_t buf = n_s & 1;
@@ -509,10 +559,8 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
         } else {
           X3_TRACE(10);
-          if (!pre_waited) {
-            wait_bar<false>(b_srdy + 16 * g, n_s & 1, 8);
-            ++n_s;
-          }
+          wait_bar<false>(b_srdy + 16 * g, n_s & 1, 8);
+          ++n_s;
           X3_TRACE(11);
           tc_fence_after();
           tmem_ld_x64(tw + S_COL, reinterpret_cast<uint32_t*>(sc));
@@ -525,16 +573,14 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
             X3_TRACE(17);
             pdl_wait_prior_grid();  // pass 1 (same stream, launched just before) has published the std
             X3_TRACE(18);
-            const float sigma = p.sigma_dev ? __ldcg(p.sigma_dev) : p.sigma_host;
-            beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2e;
+            beta_l2 = sigma_v * __ldcg(&p.ws->std_unbiased) * kLog2e;
             have_beta = true;
+            bpos = beta_l2 > 1e-20f;
+            ca = bpos ? scale_l2 / beta_l2 : scale_l2;
+            cbw = bpos ? 1.f : beta_l2;
+            ce = bpos ? beta_l2 : 1.f;
           }
-          // logits in the log2 domain.  Compact region map: the weighted key columns are slots 0..15 (keys permuted in the
-          // prepared image), one 80-byte row of W per query.  y = s * a + w * bw, 2^(e * y - e * max(y)): a = scale / beta,
-          // bw = 1, e = beta -- or, for a vanishing beta, a = scale, bw = beta, e = 1
-          const bool bpos = beta_l2 > 1e-20f;
-          const float ca = bpos ? scale_l2 / beta_l2 : scale_l2, cbw = bpos ? 1.f : beta_l2, ce = bpos ? beta_l2 : 1.f;
-          if (!pre_waited) wait_bar<false>(b_full + 8 * s, (i / NST) & 1, 9);  // (long complete: the Q K^T needed the stage)
+          wait_bar<false>(b_full + 8 * s, (i / NST) & 1, 9);  // (long complete: the Q K^T needed the stage)
           const float4* wt4 = reinterpret_cast<const float4*>(smem + KV + s * STAGE + QT_BYTES + row * (DSC_COMPACT_PITCH * 4));
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -549,28 +595,23 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           sc[77] = sc[78] = sc[79] = -INFINITY;  // pad keys
           // slots 16..79 carry no weight: their y is a * s, so the row max is taken on the raw scores (a > 0) and the
           // scaling folds into the single FFMA that forms the exponent
-          float m = m_next;
-          if (!pre_waited) {
-            float my[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mr[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          float my[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mr[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int c = 0; c < 16; ++c) my[c & 3] = fmaxf(my[c & 3], sc[c]);
+          for (int c = 0; c < 16; ++c) my[c & 3] = fmaxf(my[c & 3], sc[c]);
 #pragma unroll
-            for (int c = 16; c < 80; ++c) mr[c & 3] = fmaxf(mr[c & 3], sc[c]);
-            m = fmaxf(fmaxf(fmaxf(my[0], my[1]), fmaxf(my[2], my[3])), ca * fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])));
-          }
-          pre_waited = false;
+          for (int c = 16; c < 80; ++c) mr[c & 3] = fmaxf(mr[c & 3], sc[c]);
+          const float m = fmaxf(fmaxf(fmaxf(my[0], my[1]), fmaxf(my[2], my[3])), ca * fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])));
           const float nb = -ce * m, k2 = ce * ca;
           // the previous item's O row leaves TMEM while this warp would wait for its turn anyway (its P V was issued when
           // the previous item published P: long finished after the S read, W and row max above); that also proves
           // P(previous) has been consumed, so this item's P may go in
-#if X3_TURNS > 0
           if (pend) drain();
-          {
+          if constexpr (C::TURNS > 0) {
             const uint32_t seq = seq_base + j;
             if (lane == 0) {
               long long t0 = 0;
               uint32_t spins = 0;
-              while (static_cast<int>(seq - *my_turn) >= X3_TURNS) {  // at most X3_TURNS items ahead of the oldest unfinished one
+              while (static_cast<int>(seq - *my_turn) >= C::TURNS) {  // at most TURNS items ahead of the oldest unfinished one
                 __nanosleep(20);
                 if (++spins == 256) t0 = clock64();
                 if (spins > 256 && clock64() - t0 > (1ll << 32)) __trap();
@@ -579,11 +620,6 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
             __syncwarp();
           }
           X3_TRACE(19);
-#endif
-          const int jn = j + NWG;
-          bool pre = X3_PREPASS && jn < nit;
-          float pmy = -INFINITY, pmr = -INFINITY;
-          uint32_t pre_piece[16];
           uint32_t pw[40];
 #pragma unroll
           for (int c = 0; c < 39; ++c) {
@@ -591,64 +627,17 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
             if (c < 8) ffma2(e0, e1, sc[2 * c], sc[2 * c + 1], ce, ce, nb, nb);
             else ffma2(e0, e1, sc[2 * c], sc[2 * c + 1], k2, k2, nb, nb);
             pw[c] = c < 38 ? Mma<T>::pack(ex2_approx(e0), ex2_approx(e1)) : Mma<T>::pack(ex2_approx(e0), 0.f);
-#if X3_TURNS == 0
-            if (c == X3_DRAIN_AT) {
-              if (pend) drain();
-            }
-#endif
             if (c == 23) {  // keys 0..47 are done: first part of P
               tmem_st_x16(tw + P_COL, pw);
               tmem_st_x8(tw + P_COL + 16, pw + 16);
             }
-#if X3_PREPASS
-            if (c >= 24 && c <= 38) {
-              const int k = (c - 24) / 3, ph = (c - 24) % 3;  // piece k = S columns 16k .. 16k+15 of the next item
-              if (ph == 0 && pre) {
-                if (k == 0) {
-                  // never block here (P of this item is not published yet): if the next S has not landed, the item takes
-                  // its row max itself.  The TMEM loads are warp-collective, so the decision is made warp-uniform
-                  pre = __all_sync(0xffffffffu, test_bar(b_srdy + 16 * g, n_s & 1));
-                  if (pre) {
-                    ++n_s;
-                    tc_fence_after();
-                  }
-                }
-                if (pre) tmem_ld_x16(tw + S_COL + 16 * k, pre_piece);
-              }
-              if (ph == 2 && pre) {
-                tc_wait_ld();
-                const float* ps = reinterpret_cast<const float*>(pre_piece);
-                if (k == 0) {  // the weighted slots: y = s * a + w, exactly as the item itself will form them
-                  const int sn = (r0 + (jn >> 2)) % NST;
-                  const float4* wn4 = reinterpret_cast<const float4*>(smem + KV + sn * STAGE + QT_BYTES + row * (DSC_COMPACT_PITCH * 4));
-                  float y[16];
-#pragma unroll
-                  for (int q4 = 0; q4 < 4; ++q4) {
-                    float4 w = wn4[q4];
-                    if (!bpos) {
-                      fmul2(w.x, w.y, w.x, w.y, cbw, cbw);
-                      fmul2(w.z, w.w, w.z, w.w, cbw, cbw);
-                    }
-                    ffma2(y[4 * q4], y[4 * q4 + 1], ps[4 * q4], ps[4 * q4 + 1], ca, ca, w.x, w.y);
-                    ffma2(y[4 * q4 + 2], y[4 * q4 + 3], ps[4 * q4 + 2], ps[4 * q4 + 3], ca, ca, w.z, w.w);
-                  }
-#pragma unroll
-                  for (int q = 0; q < 16; ++q) pmy = fmaxf(pmy, y[q]);
-                } else {
-#pragma unroll
-                  for (int q = 0; q < 16; ++q)
-                    if (16 * k + q < 77) pmr = fmaxf(pmr, ps[q]);
-                }
-              }
-            }
-#endif
           }
           pw[39] = 0u;  // pad keys 78, 79
           tmem_st_x16(tw + P_COL + 24, pw + 24);  // (volatile, reads pw[24..39]: every exponential above precedes it)
-#if X3_TURNS > 0
-          __syncwarp();
-          if (lane == 0) atomicAdd(const_cast<uint32_t*>(my_turn), 1u);  // one more M phase complete: the next warp in line may start
-#endif
+          if constexpr (C::TURNS > 0) {
+            __syncwarp();
+            if (lane == 0) atomicAdd(const_cast<uint32_t*>(my_turn), 1u);  // one more M phase complete: the next warp in line may start
+          }
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(b_prdy + 8 * g);
@@ -656,10 +645,6 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           pend = true;
           pend_s = s;
           pend_h = h;
-          if (pre) {
-            m_next = fmaxf(pmy, ca * pmr);
-            pre_waited = true;
-          }
         }
       }
       if constexpr (!STATS) {
@@ -670,27 +655,27 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       r0 = r1;
     }
     if constexpr (STATS) {
-      // CTA partial in a fixed order (warp shuffle tree, then warps 0..11 serially) -> workspace; the last CTA folds
+      // CTA partial in a fixed order (warp shuffle tree, then the consumer warps serially) -> workspace; the last CTA folds
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
         dsq += __shfl_xor_sync(0xffffffffu, dsq, o);
       }
       double* red = reinterpret_cast<double*>(smem);  // the K image is dead: every Q K^T of this CTA has been consumed
-      asm volatile("bar.sync 1, 384;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
       if (lane == 0) {
         red[warp] = dsum;
-        red[12 + warp] = dsq;
+        red[4 * NWG + warp] = dsq;
       }
-      asm volatile("bar.sync 1, 384;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
       double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(p.ws) + kWorkspaceHeader);
       if (warp == 0) {
         unsigned int last = 0;
         if (lane == 0) {
           double a = 0.0, b = 0.0;
-          for (int w = 0; w < 12; ++w) {
+          for (int w = 0; w < 4 * NWG; ++w) {
             a += red[w];
-            b += red[12 + w];
+            b += red[4 * NWG + w];
           }
           partials[2 * blockIdx.x] = a;
           partials[2 * blockIdx.x + 1] = b;
@@ -711,17 +696,18 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   __syncthreads();
   tc_fence_after();
   X3_CTA_TIME(1);
-  if (warp == 13) {
+  if (warp == SW0 + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
 // ---- K / V^T image ------------------------------------------------------------------------------
-// One block per (batch, 4-head group) writes the 61,440-byte image the kernels above bulk-copy into shared memory:
-//   K  : [head 0..3][chunk 0..5][key slot 0..79][16 B]   chunk c = columns 16*floor(40h/16) + 8c .. +7 of the head GROUP (the
-//        three 16-column blocks that cover the head), zeros where those columns belong to a neighbouring head; key slots
-//        >= S = zeros (exact zero scores)
-//   V^T: [head 0..3][key chunk 0..9][row d 0..47][8 key slots x 2 B]   row 40 = ones (softmax row sum), rows 41..47 zeros
+// One block per (batch, head group) writes the image the kernels above bulk-copy into shared memory (HPT heads of HD
+// columns; NKC = 2 * KSTEPS; ON = HD + 1 rounded up to 16):
+//   K  : [head][chunk 0..NKC-1][key slot 0..79][16 B]   chunk c = columns 16*floor(HD*h/16) + 8c .. +7 of the head GROUP (the
+//        16-column blocks that cover the head), zeros where those columns belong to a neighbouring head (HD = 40 only);
+//        key slots >= S = zeros (exact zero scores); padded to a multiple of 1 KB
+//   V^T: [head][key chunk 0..9][row d 0..ON-1][8 key slots x 2 B]   row HD = ones (softmax row sum), rows above = zeros
 // key slot -> key: the n_active weighted columns of the compact region map first (ascending), then every other key in
 // order (softmax and P V do not depend on the key order; pass 1 sums over all keys).
 struct ActiveCols {
@@ -729,10 +715,12 @@ struct ActiveCols {
   int col[DSC_MAX_COMPACT_COLS];
 };
 
-template <typename T>
+template <typename T, int HD>
 __global__ void __launch_bounds__(256) x3_prepare_kv_kernel(const T* __restrict__ k, const T* __restrict__ v, long long k_sb,
                                                             long long k_ss, long long v_sb, long long v_ss, int S, int n_hg,
                                                             const ActiveCols ac, unsigned char* __restrict__ image) {
+  using C = Cfg<HD>;
+  constexpr int D = C::D, HPT = C::HPT, NKC = C::NKC, ON = C::ON;
   __shared__ int perm[DSC_MAX_KEYS];
   const int tid = threadIdx.x;
   const int b = blockIdx.x / n_hg, hg = blockIdx.x - b * n_hg;
@@ -747,20 +735,22 @@ __global__ void __launch_bounds__(256) x3_prepare_kv_kernel(const T* __restrict_
     perm[tid] = min(key, DSC_MAX_KEYS - 1);
   }
   __syncthreads();
-  unsigned char* img = image + static_cast<size_t>(blockIdx.x) * IMG_BYTES;
+  unsigned char* img = image + static_cast<size_t>(blockIdx.x) * C::IMG_BYTES;
   const T* kb = k + b * k_sb + hg * GW;
   const T* vb = v + b * v_sb + hg * GW;
-  for (int e = tid; e < HPT * 6 * DSC_MAX_KEYS; e += 256) {
-    const int slot = e % DSC_MAX_KEYS, hc = e / DSC_MAX_KEYS, c = hc % 6, h = hc / 6;
-    // chunk c of head h = columns 16 * floor(40h / 16) + 8c .. +7 of the head group; zero outside the head's own columns
+  for (int e = tid; e < HPT * NKC * DSC_MAX_KEYS; e += 256) {
+    const int slot = e % DSC_MAX_KEYS, hc = e / DSC_MAX_KEYS, c = hc % NKC, h = hc / NKC;
+    // chunk c of head h = columns 16 * floor(HD h / 16) + 8c .. +7 of the head group; zero outside the head's own columns
     const int col = ((h * D) >> 4) * 16 + c * 8;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (col >= h * D && col < (h + 1) * D && slot < S) val = *reinterpret_cast<const uint4*>(kb + perm[slot] * k_ss + col);
     *reinterpret_cast<uint4*>(img + static_cast<size_t>(e) * 16) = val;
   }
+  for (int e = tid + HPT * NKC * DSC_MAX_KEYS; e < C::K_BYTES / 16; e += 256)  // padding up to the 1 KB boundary
+    *reinterpret_cast<uint4*>(img + static_cast<size_t>(e) * 16) = make_uint4(0, 0, 0, 0);
   const unsigned short one = std::is_same<T, __half>::value ? 0x3C00u : 0x3F80u;
-  for (int e = tid; e < HPT * 10 * 48; e += 256) {
-    const int d = e % 48, hk = e / 48, kc = hk % 10, vh = hk / 10;
+  for (int e = tid; e < HPT * 10 * ON; e += 256) {
+    const int d = e % ON, hk = e / ON, kc = hk % 10, vh = hk / 10;
     unsigned short w[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -777,8 +767,10 @@ __global__ void __launch_bounds__(256) x3_prepare_kv_kernel(const T* __restrict_
     val.y = w[2] | (static_cast<uint32_t>(w[3]) << 16);
     val.z = w[4] | (static_cast<uint32_t>(w[5]) << 16);
     val.w = w[6] | (static_cast<uint32_t>(w[7]) << 16);
-    *reinterpret_cast<uint4*>(img + K_BYTES + static_cast<size_t>(e) * 16) = val;
+    *reinterpret_cast<uint4*>(img + C::K_BYTES + static_cast<size_t>(e) * 16) = val;
   }
+  for (int e = tid + HPT * 10 * ON; e < (C::IMG_BYTES - C::K_BYTES) / 16; e += 256)
+    *reinterpret_cast<uint4*>(img + C::K_BYTES + static_cast<size_t>(e) * 16) = make_uint4(0, 0, 0, 0);
 }
 
 // [B, L, cols] 16-bit tensor with element strides (sb, sl, 1) -> boxes of box_cols columns x 128 rows, no swizzle
@@ -807,29 +799,30 @@ static bool make_map_sw(CUtensorMap* m, const void* base, int cols, int L, int B
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename T, bool STATS>
+template <typename T, int HD, bool STATS>
 static cudaError_t launch(XattnParams p, cudaStream_t st) {
-  constexpr int smem = STATS ? STATS_SMEM : FWD_SMEM;
+  using C = Cfg<HD>;
+  constexpr int smem = STATS ? C::STATS_SMEM : C::FWD_SMEM;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(xattn_x3_kernel<T, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(xattn_x3_kernel<T, HD, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured_dev = dev;
   }
   CUtensorMap tm_qa, tm_qb, tm_qp, tm_oa, tm_ob;
-  if (!make_map_sw(&tm_qa, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, 64)) return cudaErrorInvalidValue;
-  if (!make_map_sw(&tm_qb, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, 32)) return cudaErrorInvalidValue;
-  if (!make_map_plain(&tm_qp, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, GW)) return cudaErrorInvalidValue;  // L2 prefetch only
+  if (!make_map_sw(&tm_qa, p.q, p.H * HD, p.L, p.B, p.q_sl, p.q_sb, 64)) return cudaErrorInvalidValue;
+  if (!make_map_sw(&tm_qb, p.q, p.H * HD, p.L, p.B, p.q_sl, p.q_sb, 32)) return cudaErrorInvalidValue;
+  if (!make_map_plain(&tm_qp, p.q, p.H * HD, p.L, p.B, p.q_sl, p.q_sb, GW)) return cudaErrorInvalidValue;  // L2 prefetch only
   if (STATS) {
     tm_oa = tm_qa;
     tm_ob = tm_qb;
   } else {
-    if (!make_map_sw(&tm_oa, p.out, p.H * D, p.L, p.B, p.o_sl, p.o_sb, 64)) return cudaErrorInvalidValue;
-    if (!make_map_sw(&tm_ob, p.out, p.H * D, p.L, p.B, p.o_sl, p.o_sb, 32)) return cudaErrorInvalidValue;
+    if (!make_map_sw(&tm_oa, p.out, p.H * HD, p.L, p.B, p.o_sl, p.o_sb, 64)) return cudaErrorInvalidValue;
+    if (!make_map_sw(&tm_ob, p.out, p.H * HD, p.L, p.B, p.o_sl, p.o_sb, 32)) return cudaErrorInvalidValue;
   }
-  p.n_hg = p.H / HPT;
+  p.n_hg = p.H / C::HPT;
   p.n_sl = (p.L + ROWS - 1) / ROWS;
   p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
   if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
@@ -837,45 +830,64 @@ static cudaError_t launch(XattnParams p, cudaStream_t st) {
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;  // pass 2 may overlap the tail of pass 1 (and pass 1 its predecessor's)
-  return cudaLaunchKernelEx(&cfg, xattn_x3_kernel<T, STATS>, p, tm_qa, tm_qb, tm_qp, tm_oa, tm_ob);
+  cfg.numAttrs = config().no_pdl ? 0 : 1;  // pass 2 may overlap the tail of pass 1 (and pass 1 its predecessor's)
+  return cudaLaunchKernelEx(&cfg, xattn_x3_kernel<T, HD, STATS>, p, tm_qa, tm_qb, tm_qp, tm_oa, tm_ob);
+}
+
+template <typename T, int HD>
+static cudaError_t prepare(const void* k, const void* v, long long k_sb, long long k_ss, long long v_sb, long long v_ss, int B, int H,
+                           int S, const ActiveCols& ac, void* image, cudaStream_t st) {
+  const int n_hg = H / Cfg<HD>::HPT;
+  x3_prepare_kv_kernel<T, HD><<<B * n_hg, 256, 0, st>>>(static_cast<const T*>(k), static_cast<const T*>(v), k_sb, k_ss, v_sb, v_ss,
+                                                        S, n_hg, ac, static_cast<unsigned char*>(image));
+  return cudaGetLastError();
 }
 
 }  // namespace x3
 
-bool x3_supports(int H, int D, int S) { return D == x3::D && S == 77 && H > 0 && H % x3::HPT == 0; }
+// Prepared-K/V path: head dims 40 / 80 / 160 (4 / 2 / 1 heads per 160-column group), the 77 keys of one CLIP window
+bool x3_supports(int H, int D, int S) {
+  if (S != 77 || H <= 0) return false;
+  return (D == 40 && H % 4 == 0) || (D == 80 && H % 2 == 0) || D == 160;
+}
 
-size_t x3_image_bytes(int B, int H) { return static_cast<size_t>(B) * (H / x3::HPT) * x3::IMG_BYTES; }
+int x3_tile_count_per_batch_row(int D) { return D == 40 ? 4 : D == 80 ? 2 : 1; }
+
+size_t x3_image_bytes(int B, int H, int D) {
+  const size_t per = D == 40 ? x3::Cfg<40>::IMG_BYTES : D == 80 ? x3::Cfg<80>::IMG_BYTES : x3::Cfg<160>::IMG_BYTES;
+  return static_cast<size_t>(B) * (H / x3_tile_count_per_batch_row(D)) * per;
+}
+
+#define X3_DISPATCH(FN, ...)                                                                                    \
+  (dtype == DSC_DTYPE_F16                                                                                       \
+       ? (D == 40 ? FN<__half, 40>(__VA_ARGS__) : D == 80 ? FN<__half, 80>(__VA_ARGS__) : FN<__half, 160>(__VA_ARGS__)) \
+       : (D == 40 ? FN<__nv_bfloat16, 40>(__VA_ARGS__)                                                          \
+                  : D == 80 ? FN<__nv_bfloat16, 80>(__VA_ARGS__) : FN<__nv_bfloat16, 160>(__VA_ARGS__)))
 
 cudaError_t run_prepare_kv_x3(const void* k, const void* v, long long k_sb, long long k_ss, long long v_sb, long long v_ss, int B,
-                              int H, int S, int n_active, const int* cols, int dtype, void* image, cudaStream_t st) {
+                              int H, int D, int S, int n_active, const int* cols, int dtype, void* image, cudaStream_t st) {
   x3::ActiveCols ac{};
   ac.n = n_active;
   for (int j = 0; j < n_active; ++j) ac.col[j] = cols[j];
-  const int n_hg = H / x3::HPT;
-  if (dtype == DSC_DTYPE_F16)
-    x3::x3_prepare_kv_kernel<__half><<<B * n_hg, 256, 0, st>>>(static_cast<const __half*>(k), static_cast<const __half*>(v), k_sb,
-                                                               k_ss, v_sb, v_ss, S, n_hg, ac, static_cast<unsigned char*>(image));
-  else
-    x3::x3_prepare_kv_kernel<__nv_bfloat16><<<B * n_hg, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(k),
-                                                                     static_cast<const __nv_bfloat16*>(v), k_sb, k_ss, v_sb, v_ss,
-                                                                     S, n_hg, ac, static_cast<unsigned char*>(image));
-  return cudaGetLastError();
+  return X3_DISPATCH(x3::prepare, k, v, k_sb, k_ss, v_sb, v_ss, B, H, S, ac, image, st);
 }
 
-cudaError_t run_stats_x3(const XattnParams& p, int dtype, cudaStream_t st) {
-  return dtype == DSC_DTYPE_F16 ? x3::launch<__half, true>(p, st) : x3::launch<__nv_bfloat16, true>(p, st);
-}
-cudaError_t run_forward_x3(const XattnParams& p, int dtype, cudaStream_t st) {
-  return dtype == DSC_DTYPE_F16 ? x3::launch<__half, false>(p, st) : x3::launch<__nv_bfloat16, false>(p, st);
-}
+namespace x3 {
+template <typename T, int HD>
+static cudaError_t launch_stats(const XattnParams& p, cudaStream_t st) { return launch<T, HD, true>(p, st); }
+template <typename T, int HD>
+static cudaError_t launch_forward(const XattnParams& p, cudaStream_t st) { return launch<T, HD, false>(p, st); }
+}  // namespace x3
+
+cudaError_t run_stats_x3(const XattnParams& p, int D, int dtype, cudaStream_t st) { return X3_DISPATCH(x3::launch_stats, p, st); }
+cudaError_t run_forward_x3(const XattnParams& p, int D, int dtype, cudaStream_t st) { return X3_DISPATCH(x3::launch_forward, p, st); }
 
 #ifdef DSC_TRACE
 extern "C" int dsc_debug_x3_trace(long long* out /*HOST 2*7*1024*2*/, int* counts /*HOST 2*7*/, unsigned long long* cta /*HOST 2*160*2*/) {

@@ -1,6 +1,6 @@
 """In-kernel timeline of the 3-warpgroup tcgen05 kernels (-DDSC_TRACE build selected with DSC_LIB): block 0's consumer
 warpgroups, TMA producer and tensor-core issuers, plus the start / end of every CTA (globaltimer).
-Usage: DSC_LIB=.../libdsc_trace.so python scripts/x3_trace.py [B L] > profiles/...txt"""
+Usage: DSC_LIB=.../libdsc_trace.so python scripts/x3_trace.py [B L [D]] > profiles/...txt"""
 import ctypes
 import math
 import os
@@ -14,7 +14,8 @@ sys.path.insert(0, ROOT)
 from diffusionspatialcontrol_b200 import _lib, attention as att  # noqa: E402
 
 B, L = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (16, 4096)
-H, D, S = 8, 40, 77
+D = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+H, S = 8, 77
 dev = torch.device("cuda")
 q = torch.randn(B, L, H * D, device=dev).half()
 k = torch.randn(B, S, H * D, device=dev).half()

@@ -48,12 +48,16 @@ def _run(att, q, k, v, W, sigma, **kw):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("B,L", [(2, 4096), (8, 9216), (1, 128), (2, 1000), (3, 200), (5, 37), (16, 1024)])
-def test_prepared_matches_oracle(B, L, dtype):
-    """SD-1.5 shapes with 40-wide heads (512^2: L = 4096, 768^2: L = 9216), ragged tails (L not a multiple of the 128-row
-    tile), single-tile and many-tiles-per-CTA cases, K / V^T image swaps inside a CTA's tile range."""
+@pytest.mark.parametrize("B,L,D", [(2, 4096, 40), (8, 9216, 40), (1, 128, 40), (2, 1000, 40), (3, 200, 40), (5, 37, 40), (16, 1024, 40),
+                                   (2, 1024, 80), (8, 2304, 80), (16, 1024, 80), (1, 128, 80), (3, 200, 80), (5, 37, 80),
+                                   (2, 256, 160), (8, 576, 160), (16, 256, 160), (16, 64, 160), (8, 144, 160), (3, 200, 160),
+                                   (5, 37, 160)])
+def test_prepared_matches_oracle(B, L, D, dtype):
+    """Every SD-1.5 cross-attention shape (512^2: 4096 x 40, 1024 x 80, 256 x 160, 64 x 160; 768^2: 9216 / 2304 / 576 / 144),
+    ragged tails (L not a multiple of the 128-row tile), single-tile and many-tiles-per-CTA cases, K / V^T image swaps
+    inside a CTA's tile range; 3 / 2 / 1 consumer warpgroups at head dim 40 / 80 / 160."""
     att = _att()
-    q, k, v = make_qkv(B, 8, L, 40, 77, seed=L + B, dtype=dtype, device="cuda")
+    q, k, v = make_qkv(B, 8, L, D, 77, seed=L + B, dtype=dtype, device="cuda")
     W = synthetic_w(B, L, 77).cuda()
     for sigma in (14.6146, 0.3350):
         out, _, _ = _run(att, q, k, v, W, sigma)
@@ -93,8 +97,8 @@ def test_active_column_sets(cols):
     negative weights (S' suppression), region-map batch smaller than the attention batch."""
     att = _att()
     B, L = 4, 640
-    q, k, v = make_qkv(B, 8, L, 40, 77, seed=len(cols) * 7 + cols[0], device="cuda")
-    for Bw in (1, 2, 4):
+    for D, Bw in ((40, 1), (40, 2), (40, 4), (80, 2), (160, 1)):
+        q, k, v = make_qkv(B, 8, L, D, 77, seed=len(cols) * 7 + cols[0], device="cuda")
         g = torch.Generator().manual_seed(11)
         W = torch.zeros(Bw, L, 77)
         W[:, :, cols] = (torch.rand(Bw, L, len(cols), generator=g) - 0.3)
@@ -133,16 +137,16 @@ def test_std_couples_the_whole_call():
     assert rel_l2(b.float(), _oracle(q2, k, v, W, 8.0)) <= TOL
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "attn_*D40*.npz"))))
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "attn_*.npz"))))
 def test_golden_vectors_from_the_reference(path):
-    """Outputs of the unmodified reference function (scripts/gen_golden.py) for the D = 40 fixtures."""
+    """Outputs of the unmodified reference function (scripts/gen_golden.py): the D = 40 / 80 / 160 fixtures with 77 keys."""
     att = _att()
     z = np.load(path)
     H = int(z["heads"])
     q, k, v = (torch.from_numpy(z[n]).cuda() for n in "qkv")
     B, L, HD = q.shape
     D = HD // H
-    if k.shape[1] != 77 or not att.prepared_supported(H, D, 77, 1):
+    if k.shape[1] != 77 or not att.prepared_supported(H, D, 77, 1):  # (the S = 40 fixture)
         pytest.skip("fixture outside the prepared path's shapes")
     view = lambda t: t.view(B, -1, H, D).transpose(1, 2)
     out, _, _ = _run(att, view(q), view(k), view(v), torch.from_numpy(z["W"]).cuda(), float(z["sigma"]))
@@ -166,12 +170,14 @@ def test_argument_checks():
     with pytest.raises(ValueError):  # wrong dtype
         att.region_attention_prepared(q, kv, compact, 1.0, workspace=torch.zeros(1 << 16, dtype=torch.float32, device="cuda"))
     with pytest.raises(DscError):  # head dim outside the prepared path
-        att.kv_image_bytes(2, 8, 80, 77)
-    q80, k80, v80 = make_qkv(2, 8, 256, 80, 77, seed=1, device="cuda")
+        att.kv_image_bytes(2, 8, 64, 77)
+    q64, k64, v64 = make_qkv(2, 8, 256, 64, 77, seed=1, device="cuda")
     with pytest.raises(DscError):
-        att.prepare_kv(k80, v80, [1])
+        att.prepare_kv(k64, v64, [1])
     assert not att.prepared_supported(8, 40, 77, 0) and not att.prepared_supported(8, 40, 77, 17)
     assert not att.prepared_supported(6, 40, 77, 2) and not att.prepared_supported(8, 40, 78, 2)
+    assert att.prepared_supported(8, 80, 77, 2) and att.prepared_supported(5, 160, 77, 2) and not att.prepared_supported(5, 80, 77, 2)
+    assert att.kv_image_bytes(2, 8, 80, 77) == 2 * 4 * 56320 and att.kv_image_bytes(2, 8, 160, 77) == 2 * 8 * 54272
 
 
 class _Attn(nn.Module):
