@@ -53,9 +53,9 @@ constexpr int GW = 160, ROWS = 128;  // a tile: 128 query rows x one 160-column 
 constexpr int BOX128_BYTES = ROWS * 128, BOX64_BYTES = ROWS * 64;
 constexpr int QT_BYTES = 2 * BOX128_BYTES + BOX64_BYTES;               // 40960
 constexpr int CW_BYTES = ROWS * DSC_COMPACT_PITCH * 4;                 // 10240
-constexpr int FWD_STAGE = QT_BYTES + CW_BYTES, FWD_NST = 3;            // 51200
+constexpr int FWD_STAGE = QT_BYTES + CW_BYTES;                         // 51200
 constexpr int STATS_STAGE = QT_BYTES, STATS_NST = 4;
-constexpr int BAR_BYTES = 256;
+constexpr int BAR_BYTES = 512;
 constexpr int S_COL = 0, P_COL = 80, O_COL = 120, S1_COL = 80;         // TMEM columns of one warpgroup: S | P | O (pass 1: S | S)
 constexpr int K_CH = DSC_MAX_KEYS * 16;                                // one 8-column chunk of K: 80 key slots x 16 B
 constexpr int round_1k(int x) { return (x + 1023) / 1024 * 1024; }
@@ -74,14 +74,23 @@ struct Cfg {
   static constexpr int ON = HD == 40 ? 48 : HD == 80 ? 96 : 176;
   static constexpr int WG_COLS = O_COL + ON;
   static constexpr int CPH = HD / 8;                                   // 16-byte chunks of a head's O row
-  static constexpr int K_HEAD = NKC * K_CH, K_BYTES = round_1k(HPT * K_HEAD);
-  static constexpr int VT_CH = ON * 16, VT_HEAD = 10 * VT_CH, VT_BYTES = HPT * VT_HEAD;
-  static constexpr int IMG_BYTES = round_1k(K_BYTES + VT_BYTES);      // prepared K / V^T image of one (batch, head group)
-  static constexpr int FWD_SMEM = IMG_BYTES + FWD_NST * FWD_STAGE + BAR_BYTES;
-  static constexpr int STATS_SMEM = K_BYTES + STATS_NST * STATS_STAGE + BAR_BYTES;
+  // prepared image of one (batch, head group) = HPT head RECORDS [K_h | V^T_h]; shared memory holds NSLOT records, used as a
+  // ring in record order (run R, head h) -> record R * HPT + h -> slot record % NSLOT: a head's slot is refilled with the next
+  // (batch, head group)'s record as soon as the last item that reads it has finished, while the other heads of the old
+  // group are still being worked on (HD = 160: one head per group, so two whole records alternate and the ring of Q
+  // stages shrinks to 2)
+  static constexpr int K_HEAD = NKC * K_CH;
+  static constexpr int VT_CH = ON * 16, VT_HEAD = 10 * VT_CH;
+  static constexpr int REC_BYTES = K_HEAD + VT_HEAD;                   // 15360 / 28160 / 53760
+  static constexpr int IMG_BYTES = HPT * REC_BYTES;                    // 61440 / 56320 / 53760
+  static constexpr int NSLOT = HD == 40 ? 4 : 2;
+  static constexpr int FWD_NST = HD == 160 ? 2 : 3;
+  static constexpr int FWD_SMEM = NSLOT * REC_BYTES + FWD_NST * FWD_STAGE + BAR_BYTES;
+  static constexpr int STATS_SMEM = NSLOT * K_HEAD + STATS_NST * STATS_STAGE + BAR_BYTES;
   static constexpr int kProducerTid = CONSUMERS;
   static constexpr int TURNS = NWG == 3 ? X3_TURNS_DEFAULT : 0;
-  static_assert(IMG_BYTES % 1024 == 0 && K_BYTES % 1024 == 0 && FWD_STAGE % 1024 == 0 && STATS_STAGE % 1024 == 0, "alignment");
+  static_assert((NSLOT * REC_BYTES) % 1024 == 0 && (NSLOT * K_HEAD) % 1024 == 0 && FWD_STAGE % 1024 == 0 && STATS_STAGE % 1024 == 0 &&
+                    REC_BYTES % 16 == 0 && K_HEAD % 16 == 0, "alignment");
   static_assert(FWD_SMEM <= 227 * 1024 && STATS_SMEM <= 227 * 1024, "shared memory budget");
   static_assert(NWG * WG_COLS <= 512 && 2 * S1_COL * NWG <= 512, "TMEM budget");
 };
@@ -133,6 +142,25 @@ __device__ __forceinline__ bool test_bar(uint32_t bar, uint32_t parity) {  // no
   asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
+}
+// event loops (producer, issuers): back off when nothing could be done; a loop that makes no progress for ~2 s traps
+__device__ __forceinline__ void idle_or_trap(bool progress, uint32_t& spins, long long& t0, unsigned ns) {
+  if (progress) {
+    spins = 0;
+    return;
+  }
+  __nanosleep(ns);
+  if (++spins == 4096) t0 = clock64();
+  if (spins > 4096 && (spins & 1023) == 0 && clock64() - t0 > (1ll << 32)) {
+#ifdef DSC_WATCHDOG
+    if (atomicCAS(&g_x3_abort, 0u, 1u) == 0u) {
+      g_x3_info[0] = 99;
+      g_x3_info[1] = blockIdx.x;
+      g_x3_info[2] = threadIdx.x;
+    }
+#endif
+    __trap();
+  }
 }
 template <bool RELAXED>
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t tag) {
@@ -205,11 +233,12 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
                 const __grid_constant__ CUtensorMap tm_ob) {
   using C = Cfg<HD>;
   constexpr int D = C::D, HPT = C::HPT, LOG_HPT = C::LOG_HPT, NWG = C::NWG, CONSUMERS = C::CONSUMERS, WG_COLS = C::WG_COLS;
-  constexpr int K_HEAD = C::K_HEAD, K_BYTES = C::K_BYTES, VT_CH = C::VT_CH, VT_HEAD = C::VT_HEAD, IMG_BYTES = C::IMG_BYTES;
+  constexpr int K_HEAD = C::K_HEAD, VT_CH = C::VT_CH, IMG_BYTES = C::IMG_BYTES, NSLOT = C::NSLOT;
   constexpr int kProducerTid = C::kProducerTid, SW0 = 4 * NWG;  // first service warp
-  constexpr int NST = STATS ? STATS_NST : FWD_NST;
+  constexpr int NST = STATS ? STATS_NST : C::FWD_NST;
   constexpr int STAGE = STATS ? STATS_STAGE : FWD_STAGE;
-  constexpr int KV = STATS ? K_BYTES : IMG_BYTES;
+  constexpr int RECB = STATS ? K_HEAD : C::REC_BYTES;  // bytes of a record this pass needs (pass 1: its K part) = slot pitch
+  constexpr int KV = NSLOT * RECB;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   X3_TRACE_DECL
@@ -231,20 +260,26 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sStage = s0 + KV;
   const uint32_t bars = sStage + NST * STAGE;
-  // barrier map (8 B each)
-  const uint32_t b_full = bars, b_odone = bars + 32, b_kvfull = bars + 64, b_kvfree = bars + 72, b_srdy = bars + 80,
-                 b_sfree = bars + 128, b_prdy = bars + 176, b_ordy = bars + 200;
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 240);
-  volatile uint32_t* turn_ptr = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 224);
+  // barrier map (8 B each): full[4] | odone[4] | kvfull[4] | kvfree[4] | srdy[3][2] | sfree[3][2] | prdy[3] | ordy[3]
+  const uint32_t b_full = bars, b_odone = bars + 32, b_kvfull = bars + 64, b_kvfree = bars + 96, b_srdy = bars + 128,
+                 b_sfree = bars + 176, b_prdy = bars + 224, b_ordy = bars + 248;
+  constexpr int N_BARS = 34;
+  volatile uint32_t* turn_ptr = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 272);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 288);
 
   const int begin = static_cast<int>(p.total * blockIdx.x / gridDim.x);
   const int n_items = static_cast<int>(p.total * (blockIdx.x + 1) / gridDim.x) - begin;
+  // the CTA's tiles span the (batch, head group) segments seg0 .. seg0 + n_runs - 1 ("runs"); records = n_runs * HPT
+  const int seg0 = begin / p.n_sl;
+  const int n_rec = n_items > 0 ? ((begin + n_items - 1) / p.n_sl - seg0 + 1) * HPT : 0;
   const uint64_t pol_q = STATS ? policy_evict_last() : policy_evict_first();  // pass 2 reads Q again: keep it in L2
   const unsigned char* img = reinterpret_cast<const unsigned char*>(p.kv_image);
 
-  auto load_image = [&](const Tile& t) {  // K (| V^T) image of the tile's (batch, head group): one bulk copy
-    mbar_arrive_expect_tx(b_kvfull, KV);
-    bulk_g2s_hint(s0, img + (static_cast<size_t>(t.b) * p.n_hg + t.hg) * IMG_BYTES, KV, b_kvfull, policy_evict_last());
+  auto load_record = [&](int rec) {  // head record (K_h | V^T_h; pass 1: K_h) of run rec / HPT -> slot rec % NSLOT: one bulk copy
+    const int slot = rec % NSLOT;
+    mbar_arrive_expect_tx(b_kvfull + 8 * slot, RECB);
+    bulk_g2s_hint(s0 + slot * RECB, img + static_cast<size_t>(seg0 + (rec >> LOG_HPT)) * IMG_BYTES + (rec & (HPT - 1)) * C::REC_BYTES, RECB,
+                  b_kvfull + 8 * slot, policy_evict_last());
   };
   auto load_tile = [&](int i) {  // Q boxes (+ compact W tile) of tile i -> ring stage i % NST
     const int s = i % NST;
@@ -262,7 +297,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     if (t.tile == p.n_sl - 1 && i + 1 < n_items) {  // the run ends with this tile: pull the next image towards L2
       const Tile n = decode(begin + i + 1, p);
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(img + (static_cast<size_t>(n.b) * p.n_hg + n.hg) * IMG_BYTES),
-                   "r"(KV)
+                   "r"(IMG_BYTES)
                    : "memory");
     }
 #if X3_L2_PREFETCH
@@ -281,24 +316,26 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   };
 
   // barrier init is spread over the service warps so that the first loads leave as early as possible: the producer
-  // thread initialises only what those loads signal (full[], kvfull), warp 14 the rest (8 bytes apart in map order)
+  // thread initialises only what those loads signal (full[], kvfull[]), service warp 2 the rest
   if (tid == kProducerTid) {
     for (int st = 0; st < 4; ++st) mbar_init(b_full + 8 * st, 1);
-    mbar_init(b_kvfull, 1);
+    for (int st = 0; st < 4; ++st) mbar_init(b_kvfull + 8 * st, 1);
     fence_mbar_init();
     X3_TRACE(4);
     if (n_items > 0) {  // only what the first Q K^T needs is issued ahead of the CTA-wide barrier
-      load_image(decode(begin, p));
+      load_record(0);
       load_tile(0);
       X3_TRACE(6);
     }
   }
   if (warp == SW0 + 2) {
-    if (lane >= 4 && lane < 28 && lane != 8) {
-      const uint32_t cnt = lane < 8 ? HPT * 128u : lane == 9 ? static_cast<uint32_t>(CONSUMERS) : lane < 16 ? 1u : lane < 25 ? 128u : 1u;
-      mbar_init(bars + 8 * lane, cnt);
-      fence_mbar_init();
+    for (int idx = 4 + lane; idx < N_BARS; idx += 32) {
+      if (idx >= 8 && idx < 12) continue;  // kvfull[]: the producer's
+      // odone[]: every consumer of every head of the tile | kvfree[]: every consumer | srdy, ordy: one commit | sfree, prdy: a warpgroup
+      const uint32_t cnt = idx < 8 ? HPT * 128u : idx < 16 ? static_cast<uint32_t>(CONSUMERS) : idx < 22 ? 1u : idx < 31 ? 128u : 1u;
+      mbar_init(bars + 8 * idx, cnt);
     }
+    fence_mbar_init();
     if (lane >= 28) turn_ptr[lane - 28] = 0u;  // whose turn it is on each SM sub-partition (pass 2)
   }
   if (warp == SW0 + 1) {
@@ -314,106 +351,129 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   const uint32_t tmem_base = *tmem_ptr_smem;
   X3_TRACE(2);
 
+  const int n_jobs = n_items * HPT;  // (tile, head) work items of this CTA, in order; item J -> warpgroup J % NWG
+  auto rec_of = [&](int J) { return (((begin + (J >> LOG_HPT)) / p.n_sl) - seg0) * HPT + (J & (HPT - 1)); };
+
   if (warp >= SW0) {
     if (tid == kProducerTid) {
       // ============================== producer: TMA loads and stores ===============================
-      uint32_t n_run = 0;
-      for (int i = 1; i < min(NST, n_items); ++i) load_tile(i);  // rest of the first ring fill
+      // one thread, event loop (nothing here ever blocks on one condition while another could make progress):
+      //   * tile ld goes into ring stage ld % NST as soon as tile ld - NST has been retired and its store has read the stage
+      //   * head record rec goes into slot rec % NSLOT as soon as every warpgroup has released record rec - NSLOT
+      //   * tile dn is retired (pass 2: its O rows leave through three tensor-map stores) when every consumer has handed it back
+      int ld = n_items > 0 ? 1 : 0, dn = 0, rec = n_rec > 0 ? 1 : 0;
+      uint32_t idle_spins = 0;
+      long long idle_t0 = 0;
       X3_TRACE(8);
-      auto tile_done = [&](int i) {  // every consumer has handed tile i back
-        const int s = i % NST;
-        X3_TRACE(30);
-        wait_bar<true>(b_odone + 8 * s, (i / NST) & 1, 1);
-        X3_TRACE(31);
-        const Tile t = decode(begin + i, p);
-        if constexpr (!STATS) {
-          const uint32_t sQ = sStage + s * STAGE;
-          const int c0 = t.hg * GW;
-          tma_store_3d(&tm_oa, c0, t.l0, t.b, sQ);  // rows >= L and columns >= H*D are clipped by the TMA
-          tma_store_3d(&tm_oa, c0 + 64, t.l0, t.b, sQ + BOX128_BYTES);
-          tma_store_3d(&tm_ob, c0 + 128, t.l0, t.b, sQ + 2 * BOX128_BYTES);
-          bulk_commit();
-          bulk_wait_read0();
-          X3_TRACE(32);
-        }
-        if (t.tile == p.n_sl - 1 && i + 1 < n_items) {  // (batch, head group) changes: swap the K / V^T image
-          wait_bar<true>(b_kvfree, n_run & 1, 2);
-          ++n_run;
-          load_image(decode(begin + i + 1, p));
+      while (dn < n_items) {
+        bool progress = false;
+        if (rec < n_rec && (rec < NSLOT || test_bar(b_kvfree + 8 * (rec % NSLOT), (rec / NSLOT - 1) & 1))) {
+          load_record(rec++);
           X3_TRACE(33);
+          progress = true;
         }
-      };
-      for (int i = NST; i < n_items; ++i) {
-        tile_done(i - NST);
-        load_tile(i);
-        X3_TRACE(34);
+        if (ld < n_items && ld < dn + NST) {
+          if constexpr (!STATS) {
+            if (ld >= NST) {  // the store of tile ld - NST (bulk group ld - NST of dn committed so far) must have read the stage
+              const int later = dn - 1 - (ld - NST);  // groups committed after it: may stay pending
+              if (later <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              else if (later == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+            }
+          }
+          load_tile(ld++);
+          X3_TRACE(34);
+          progress = true;
+        }
+        if (test_bar(b_odone + 8 * (dn % NST), (dn / NST) & 1)) {
+          X3_TRACE(31);
+          if constexpr (!STATS) {
+            const Tile t = decode(begin + dn, p);
+            const uint32_t sQ = sStage + (dn % NST) * STAGE;
+            const int c0 = t.hg * GW;
+            tma_store_3d(&tm_oa, c0, t.l0, t.b, sQ);  // rows >= L and columns >= H*D are clipped by the TMA
+            tma_store_3d(&tm_oa, c0 + 64, t.l0, t.b, sQ + BOX128_BYTES);
+            tma_store_3d(&tm_ob, c0 + 128, t.l0, t.b, sQ + 2 * BOX128_BYTES);
+            bulk_commit();
+            X3_TRACE(32);
+          }
+          ++dn;
+          progress = true;
+        }
+        idle_or_trap(progress, idle_spins, idle_t0, 32);
       }
-      for (int i = (n_items > NST ? n_items - NST : 0); i < n_items; ++i) tile_done(i);
       if constexpr (!STATS) bulk_wait0();
     } else if (lane == 0 && warp > SW0 && warp - SW0 - 1 < NWG) {
       // ============================== tensor-core issuer of warpgroup g ============================
+      // Q K^T of the warpgroup's next item is issued as soon as its Q tile, its head record and the S columns are there
+      // (pass 2: one item ahead of the softmax; pass 1: two, S is double-buffered); P V of an item when its P is published.
+      // Neither waits for the other: a Q K^T that is blocked on a head record (whose slot is released only after an
+      // earlier P V has been drained) must not hold up that P V.
       const int g = warp - SW0 - 1;
       constexpr uint32_t idesc_qk = idesc_f16<T>(80);
       constexpr uint32_t idesc_pv = idesc_f16<T>(C::ON);
       const uint32_t tw = tmem_base + g * WG_COLS;
-      uint32_t nqk = 0, npv = 0, n_run = 0;
-      for (int r0 = 0; r0 < n_items;) {
-        const Tile t0 = decode(begin + r0, p);
-        const int r1 = min(n_items, r0 + p.n_sl - t0.tile);
-        const int nit = HPT * (r1 - r0);
-        X3_TRACE(40);
-        wait_bar<true>(b_kvfull, n_run & 1, 3);
-        X3_TRACE(41);
-        ++n_run;
-        auto qk = [&](int j) {
-          const int i = r0 + (j >> LOG_HPT), h = j & (HPT - 1), s = i % NST;
-          X3_TRACE(42);
-          wait_bar<true>(b_full + 8 * s, (i / NST) & 1, 4);
+      uint32_t nqk = 0, npv = 0, idle_spins = 0;
+      long long idle_t0 = 0;
+      int jq = g, jp = g;
+      // records this issuer has SEEN loaded, in record order.  Every record is observed, used by this warpgroup or not: a
+      // parity test is only meaningful against the phase right after the last one observed (testing the phase of a later
+      // record while an earlier load into the same slot is still in flight would read as "complete")
+      int rec_seen = 0;
+      while (STATS ? jq < n_jobs : jp < n_jobs) {
+        bool progress = false;
+        if (jq < n_jobs) {
+          const int i = jq >> LOG_HPT, h = jq & (HPT - 1), s = i % NST;
+          const int rc = rec_of(jq), slot = rc % NSLOT;
           uint32_t buf = 0;
+          while (rec_seen <= rc && test_bar(b_kvfull + 8 * (rec_seen % NSLOT), (rec_seen / NSLOT) & 1)) ++rec_seen;
+          bool ready = rec_seen > rc && test_bar(b_full + 8 * s, (i / NST) & 1);
           if constexpr (STATS) {
             buf = nqk & 1;
-            if (nqk >= 2) wait_bar<true>(b_sfree + 16 * g + 8 * buf, ((nqk >> 1) - 1) & 1, 5);
+            if (ready && nqk >= 2) ready = test_bar(b_sfree + 16 * g + 8 * buf, ((nqk >> 1) - 1) & 1);
           } else {
-            if (nqk >= 1) wait_bar<true>(b_sfree + 16 * g, (nqk - 1) & 1, 5);
+            if (ready && nqk >= 1) ready = test_bar(b_sfree + 16 * g, (nqk - 1) & 1);
           }
-          X3_TRACE(43);
-          ++nqk;
-          tc_fence_after();
-          const uint32_t sQ = sStage + s * STAGE;
-          const uint32_t d = tw + (STATS ? buf * S1_COL : S_COL);
-          const uint32_t kb = s0 + h * K_HEAD;
-          // head h = the KSTEPS 16-column blocks that cover columns HD*h .. HD*h + HD-1 (HD = 40: the K image is zero where a
-          // block's columns belong to a neighbour); block t: boxes of 4 blocks (SW128) for t < 8, the SW64 box for t = 8, 9
-          const int t0b = (h * D) >> 4;
+          if (ready) {
+            X3_TRACE(43);
+            ++nqk;
+            tc_fence_after();
+            const uint32_t sQ = sStage + s * STAGE;
+            const uint32_t d = tw + (STATS ? buf * S1_COL : S_COL);
+            const uint32_t kb = s0 + slot * RECB;
+            // head h = the KSTEPS 16-column blocks that cover columns HD*h .. HD*h + HD-1 (HD = 40: the K image is zero where
+            // a block's columns belong to a neighbour); block t: boxes of 4 blocks (SW128) for t < 8, the SW64 box for t = 8, 9
+            const int t0b = (h * D) >> 4;
 #pragma unroll
-          for (int ks = 0; ks < C::KSTEPS; ++ks) {
-            const int t = t0b + ks;
-            const uint64_t ad = t < 8 ? smem_desc_sw128(sQ + (t >> 2) * BOX128_BYTES + (t & 3) * 32)
-                                      : smem_desc_sw64(sQ + 2 * BOX128_BYTES + (t - 8) * 32);
-            umma_ss(d, ad, smem_desc(kb + ks * 2 * K_CH, K_CH, 128), idesc_qk, ks);
+            for (int ks = 0; ks < C::KSTEPS; ++ks) {
+              const int t = t0b + ks;
+              const uint64_t ad = t < 8 ? smem_desc_sw128(sQ + (t >> 2) * BOX128_BYTES + (t & 3) * 32)
+                                        : smem_desc_sw64(sQ + 2 * BOX128_BYTES + (t - 8) * 32);
+              umma_ss(d, ad, smem_desc(kb + ks * 2 * K_CH, K_CH, 128), idesc_qk, ks);
+            }
+            tc_commit(b_srdy + 16 * g + 8 * buf);
+            X3_TRACE(44);
+            jq += NWG;
+            progress = true;
           }
-          tc_commit(b_srdy + 16 * g + 8 * buf);
-          X3_TRACE(44);
-        };
-        if (g < nit) qk(g);
-        for (int j = g; j < nit; j += NWG) {
-          if (j + NWG < nit) qk(j + NWG);
-          if constexpr (!STATS) {
-            const int h = j & (HPT - 1);
-            X3_TRACE(45);
-            wait_bar<true>(b_prdy + 8 * g, npv & 1, 6);
+        }
+        if constexpr (!STATS) {
+          if (jp < jq && test_bar(b_prdy + 8 * g, npv & 1)) {
             X3_TRACE(46);
             ++npv;
             tc_fence_after();
-            const uint64_t vdesc = smem_desc(s0 + K_BYTES + h * VT_HEAD, VT_CH, 128);
+            const uint32_t vb = s0 + (rec_of(jp) % NSLOT) * RECB + K_HEAD;
+            const uint64_t vdesc = smem_desc(vb, VT_CH, 128);
 #pragma unroll
             for (int kk = 0; kk < 5; ++kk)
               umma_ts(tw + O_COL, tw + P_COL + kk * 8, vdesc + static_cast<uint64_t>((kk * 2 * VT_CH) >> 4), idesc_pv, kk);
             tc_commit(b_ordy + 8 * g);
             X3_TRACE(47);
+            jp += NWG;
+            progress = true;
           }
         }
-        r0 = r1;
+        idle_or_trap(progress, idle_spins, idle_t0, 20);
       }
     }
     __syncwarp();
@@ -446,7 +506,6 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     // (profiles/r2_x3_trace_lockstep.txt: 3.3k cycles per round of 3 items against 1.85k of MUFU work).  With turns, one or
     // two warps exponentiate at the full pipe rate while the others do their MUFU-free part.
     volatile uint32_t* my_turn = turn_ptr + (warp & 3);
-    uint32_t seq_base = 0;  // items of the CTA's earlier runs
 
     // O row of the warpgroup's previous item: TMEM -> x 1/rowsum (ones row of V^T: column HD) -> over the row's own Q
     // columns in the ring stage, stage handed back
@@ -525,12 +584,29 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       pend = false;
     };
 
-    for (int r0 = 0; r0 < n_items;) {
-      const Tile t0 = decode(begin + r0, p);
-      const int r1 = min(n_items, r0 + p.n_sl - t0.tile);
-      const int nit = HPT * (r1 - r0);
-      for (int j = g; j < nit; j += NWG) {
-        const int i = r0 + (j >> LOG_HPT), h = j & (HPT - 1), s = i % NST;
+    // Head records are released in record order: this warpgroup arrives on kvfree[record] once it has no item left
+    // that is <= the record's last item -- checked at the top of every item, after the pending O row (whose P V read the
+    // record's V^T) has been drained.  (The check must not sit behind the wait for the item's own S: its Q K^T may need
+    // the very slot this arrival frees.)
+    int arr_next = 0;
+    auto last_job_of = [&](int rc) {  // last (tile, head) item that reads record rc
+      const int e = min(n_items, (seg0 + (rc >> LOG_HPT) + 1) * p.n_sl - begin) - 1;
+      return e * HPT + (rc & (HPT - 1));
+    };
+    int arr_last = n_rec > 0 ? last_job_of(0) : 0x7fffffff;
+    {
+      for (int j = g; j < n_jobs; j += NWG) {
+        const int i = j >> LOG_HPT, h = j & (HPT - 1), s = i % NST;
+        if (arr_last < j) {
+          if constexpr (!STATS) {
+            if (pend) drain();
+          }
+          do {
+            mbar_arrive(b_kvfree + 8 * (arr_next % NSLOT));
+            ++arr_next;
+            arr_last = arr_next < n_rec ? last_job_of(arr_next) : 0x7fffffff;
+          } while (arr_last < j);
+        }
         float sc[80];
         if constexpr (STATS) {
           const uint32_t buf = n_s & 1;
@@ -607,7 +683,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           // P(previous) has been consumed, so this item's P may go in
           if (pend) drain();
           if constexpr (C::TURNS > 0) {
-            const uint32_t seq = seq_base + j;
+            const uint32_t seq = static_cast<uint32_t>(j);
             if (lane == 0) {
               long long t0 = 0;
               uint32_t spins = 0;
@@ -650,9 +726,6 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       if constexpr (!STATS) {
         if (pend) drain();
       }
-      mbar_arrive(b_kvfree);  // this thread's share of the run is complete: the K / V^T image may be replaced
-      seq_base += nit;
-      r0 = r1;
     }
     if constexpr (STATS) {
       // CTA partial in a fixed order (warp shuffle tree, then the consumer warps serially) -> workspace; the last CTA folds
@@ -702,12 +775,12 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
 }
 
 // ---- K / V^T image ------------------------------------------------------------------------------
-// One block per (batch, head group) writes the image the kernels above bulk-copy into shared memory (HPT heads of HD
-// columns; NKC = 2 * KSTEPS; ON = HD + 1 rounded up to 16):
-//   K  : [head][chunk 0..NKC-1][key slot 0..79][16 B]   chunk c = columns 16*floor(HD*h/16) + 8c .. +7 of the head GROUP (the
-//        16-column blocks that cover the head), zeros where those columns belong to a neighbouring head (HD = 40 only);
-//        key slots >= S = zeros (exact zero scores); padded to a multiple of 1 KB
-//   V^T: [head][key chunk 0..9][row d 0..ON-1][8 key slots x 2 B]   row HD = ones (softmax row sum), rows above = zeros
+// One block per (batch, head group) writes the image the kernels above bulk-copy into shared memory record by record: HPT
+// head records of REC_BYTES = K_HEAD + VT_HEAD (HPT heads of HD columns; NKC = 2 * KSTEPS; ON = HD + 1 rounded up to 16):
+//   K_h  : [chunk 0..NKC-1][key slot 0..79][16 B]   chunk c = columns 16*floor(HD*h/16) + 8c .. +7 of the head GROUP (the
+//          16-column blocks that cover the head), zeros where those columns belong to a neighbouring head (HD = 40 only);
+//          key slots >= S = zeros (exact zero scores)
+//   V^T_h: [key chunk 0..9][row d 0..ON-1][8 key slots x 2 B]   row HD = ones (softmax row sum), rows above = zeros
 // key slot -> key: the n_active weighted columns of the compact region map first (ascending), then every other key in
 // order (softmax and P V do not depend on the key order; pass 1 sums over all keys).
 struct ActiveCols {
@@ -744,10 +817,8 @@ __global__ void __launch_bounds__(256) x3_prepare_kv_kernel(const T* __restrict_
     const int col = ((h * D) >> 4) * 16 + c * 8;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (col >= h * D && col < (h + 1) * D && slot < S) val = *reinterpret_cast<const uint4*>(kb + perm[slot] * k_ss + col);
-    *reinterpret_cast<uint4*>(img + static_cast<size_t>(e) * 16) = val;
+    *reinterpret_cast<uint4*>(img + static_cast<size_t>(h) * C::REC_BYTES + static_cast<size_t>(c * DSC_MAX_KEYS + slot) * 16) = val;
   }
-  for (int e = tid + HPT * NKC * DSC_MAX_KEYS; e < C::K_BYTES / 16; e += 256)  // padding up to the 1 KB boundary
-    *reinterpret_cast<uint4*>(img + static_cast<size_t>(e) * 16) = make_uint4(0, 0, 0, 0);
   const unsigned short one = std::is_same<T, __half>::value ? 0x3C00u : 0x3F80u;
   for (int e = tid; e < HPT * 10 * ON; e += 256) {
     const int d = e % ON, hk = e / ON, kc = hk % 10, vh = hk / 10;
@@ -767,10 +838,8 @@ __global__ void __launch_bounds__(256) x3_prepare_kv_kernel(const T* __restrict_
     val.y = w[2] | (static_cast<uint32_t>(w[3]) << 16);
     val.z = w[4] | (static_cast<uint32_t>(w[5]) << 16);
     val.w = w[6] | (static_cast<uint32_t>(w[7]) << 16);
-    *reinterpret_cast<uint4*>(img + C::K_BYTES + static_cast<size_t>(e) * 16) = val;
+    *reinterpret_cast<uint4*>(img + static_cast<size_t>(vh) * C::REC_BYTES + C::K_HEAD + static_cast<size_t>(kc * ON + d) * 16) = val;
   }
-  for (int e = tid + HPT * 10 * ON; e < (C::IMG_BYTES - C::K_BYTES) / 16; e += 256)
-    *reinterpret_cast<uint4*>(img + C::K_BYTES + static_cast<size_t>(e) * 16) = make_uint4(0, 0, 0, 0);
 }
 
 // [B, L, cols] 16-bit tensor with element strides (sb, sl, 1) -> boxes of box_cols columns x 128 rows, no swizzle
