@@ -357,22 +357,22 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   if (warp >= SW0) {
     if (tid == kProducerTid) {
       // ============================== producer: TMA loads and stores ===============================
-      // one thread, event loop (nothing here ever blocks on one condition while another could make progress):
-      //   * tile ld goes into ring stage ld % NST as soon as tile ld - NST has been retired and its store has read the stage
+      // one thread.  It never blocks on one condition while another could make progress:
       //   * head record rec goes into slot rec % NSLOT as soon as every warpgroup has released record rec - NSLOT
+      //   * tile ld goes into ring stage ld % NST as soon as tile ld - NST has been retired and its store has read the stage
       //   * tile dn is retired (pass 2: its O rows leave through three tensor-map stores) when every consumer has handed it back
+      // While a record refill may become possible (the consumers are within a tile of the end of the run that still
+      // uses the slot) both conditions are polled; otherwise the thread sleeps on the hand-back barrier.
       int ld = n_items > 0 ? 1 : 0, dn = 0, rec = n_rec > 0 ? 1 : 0;
       uint32_t idle_spins = 0;
       long long idle_t0 = 0;
       X3_TRACE(8);
       while (dn < n_items) {
-        bool progress = false;
-        if (rec < n_rec && (rec < NSLOT || test_bar(b_kvfree + 8 * (rec % NSLOT), (rec / NSLOT - 1) & 1))) {
+        while (rec < n_rec && (rec < NSLOT || test_bar(b_kvfree + 8 * (rec % NSLOT), (rec / NSLOT - 1) & 1))) {
           load_record(rec++);
           X3_TRACE(33);
-          progress = true;
         }
-        if (ld < n_items && ld < dn + NST) {
+        while (ld < n_items && ld < dn + NST) {
           if constexpr (!STATS) {
             if (ld >= NST) {  // the store of tile ld - NST (bulk group ld - NST of dn committed so far) must have read the stage
               const int later = dn - 1 - (ld - NST);  // groups committed after it: may stay pending
@@ -383,35 +383,47 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           }
           load_tile(ld++);
           X3_TRACE(34);
-          progress = true;
         }
-        if (test_bar(b_odone + 8 * (dn % NST), (dn / NST) & 1)) {
-          X3_TRACE(31);
-          if constexpr (!STATS) {
-            const Tile t = decode(begin + dn, p);
-            const uint32_t sQ = sStage + (dn % NST) * STAGE;
-            const int c0 = t.hg * GW;
-            tma_store_3d(&tm_oa, c0, t.l0, t.b, sQ);  // rows >= L and columns >= H*D are clipped by the TMA
-            tma_store_3d(&tm_oa, c0 + 64, t.l0, t.b, sQ + BOX128_BYTES);
-            tma_store_3d(&tm_ob, c0 + 128, t.l0, t.b, sQ + 2 * BOX128_BYTES);
-            bulk_commit();
-            X3_TRACE(32);
+        bool poll = false;
+        if (rec < n_rec) {  // last tile of the run whose record occupies the slot record `rec` is waiting for
+          const int e_old = min(n_items, (seg0 + ((rec - NSLOT) >> LOG_HPT) + 1) * p.n_sl - begin) - 1;
+          poll = dn + 1 >= e_old;
+        }
+        if (poll) {
+          if (!test_bar(b_odone + 8 * (dn % NST), (dn / NST) & 1)) {
+            idle_or_trap(false, idle_spins, idle_t0, 32);
+            continue;
           }
-          ++dn;
-          progress = true;
+          idle_spins = 0;
+        } else {
+          wait_bar<true>(b_odone + 8 * (dn % NST), (dn / NST) & 1, 1);
         }
-        idle_or_trap(progress, idle_spins, idle_t0, 32);
+        X3_TRACE(31);
+        if constexpr (!STATS) {
+          const Tile t = decode(begin + dn, p);
+          const uint32_t sQ = sStage + (dn % NST) * STAGE;
+          const int c0 = t.hg * GW;
+          tma_store_3d(&tm_oa, c0, t.l0, t.b, sQ);  // rows >= L and columns >= H*D are clipped by the TMA
+          tma_store_3d(&tm_oa, c0 + 64, t.l0, t.b, sQ + BOX128_BYTES);
+          tma_store_3d(&tm_ob, c0 + 128, t.l0, t.b, sQ + 2 * BOX128_BYTES);
+          bulk_commit();
+          X3_TRACE(32);
+        }
+        ++dn;
       }
       if constexpr (!STATS) bulk_wait0();
     } else if (lane == 0 && warp > SW0 && warp - SW0 - 1 < NWG) {
       // ============================== tensor-core issuer of warpgroup g ============================
-      // Q K^T of the warpgroup's next item is issued as soon as its Q tile, its head record and the S columns are there
-      // (pass 2: one item ahead of the softmax; pass 1: two, S is double-buffered); P V of an item when its P is published.
-      // Neither waits for the other: a Q K^T that is blocked on a head record (whose slot is released only after an
-      // earlier P V has been drained) must not hold up that P V.
+      // Steady state: Q K^T of item j + NWG when the S columns are free (the consumers have read S(j)), then P V of item j
+      // when its P is published -- each a sleeping wait on one barrier.  The exception is a Q K^T whose head record has not
+      // arrived yet: its slot is released only after earlier P Vs have been drained, so the issuer never blocks on a record
+      // while a P V is outstanding; it issues that P V first and comes back.
+      // Invariant that keeps the consumers' top-of-item drain alive: before blocking for Q K^T(jq), P V(jq - 2 NWG) has
+      // been issued (jq - jp <= NWG).
       const int g = warp - SW0 - 1;
       constexpr uint32_t idesc_qk = idesc_f16<T>(80);
       constexpr uint32_t idesc_pv = idesc_f16<T>(C::ON);
+      constexpr int AHEAD = STATS ? 2 * NWG : NWG;  // pass 1: S is double-buffered
       const uint32_t tw = tmem_base + g * WG_COLS;
       uint32_t nqk = 0, npv = 0, idle_spins = 0;
       long long idle_t0 = 0;
@@ -421,44 +433,56 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       // record while an earlier load into the same slot is still in flight would read as "complete")
       int rec_seen = 0;
       while (STATS ? jq < n_jobs : jp < n_jobs) {
-        bool progress = false;
-        if (jq < n_jobs) {
-          const int i = jq >> LOG_HPT, h = jq & (HPT - 1), s = i % NST;
-          const int rc = rec_of(jq), slot = rc % NSLOT;
-          uint32_t buf = 0;
+        bool qk_now = false;
+        int rc = 0;
+        if (jq < n_jobs && (STATS || jq - jp <= AHEAD)) {
+          rc = rec_of(jq);
           while (rec_seen <= rc && test_bar(b_kvfull + 8 * (rec_seen % NSLOT), (rec_seen / NSLOT) & 1)) ++rec_seen;
-          bool ready = rec_seen > rc && test_bar(b_full + 8 * s, (i / NST) & 1);
+          qk_now = rec_seen > rc;
+          if (!qk_now && (STATS || jp == jq)) {  // nothing else to do: sleep on the record that is next in line
+            wait_bar<true>(b_kvfull + 8 * (rec_seen % NSLOT), (rec_seen / NSLOT) & 1, 3);
+            ++rec_seen;
+            continue;
+          }
+        }
+        if (qk_now) {
+          const int i = jq >> LOG_HPT, h = jq & (HPT - 1), s = i % NST, slot = rc % NSLOT;
+          X3_TRACE(42);
+          wait_bar<true>(b_full + 8 * s, (i / NST) & 1, 4);
+          uint32_t buf = 0;
           if constexpr (STATS) {
             buf = nqk & 1;
-            if (ready && nqk >= 2) ready = test_bar(b_sfree + 16 * g + 8 * buf, ((nqk >> 1) - 1) & 1);
+            if (nqk >= 2) wait_bar<true>(b_sfree + 16 * g + 8 * buf, ((nqk >> 1) - 1) & 1, 5);
           } else {
-            if (ready && nqk >= 1) ready = test_bar(b_sfree + 16 * g, (nqk - 1) & 1);
+            if (nqk >= 1) wait_bar<true>(b_sfree + 16 * g, (nqk - 1) & 1, 5);
           }
-          if (ready) {
-            X3_TRACE(43);
-            ++nqk;
-            tc_fence_after();
-            const uint32_t sQ = sStage + s * STAGE;
-            const uint32_t d = tw + (STATS ? buf * S1_COL : S_COL);
-            const uint32_t kb = s0 + slot * RECB;
-            // head h = the KSTEPS 16-column blocks that cover columns HD*h .. HD*h + HD-1 (HD = 40: the K image is zero where
-            // a block's columns belong to a neighbour); block t: boxes of 4 blocks (SW128) for t < 8, the SW64 box for t = 8, 9
-            const int t0b = (h * D) >> 4;
+          X3_TRACE(43);
+          ++nqk;
+          tc_fence_after();
+          const uint32_t sQ = sStage + s * STAGE;
+          const uint32_t d = tw + (STATS ? buf * S1_COL : S_COL);
+          const uint32_t kb = s0 + slot * RECB;
+          // head h = the KSTEPS 16-column blocks that cover columns HD*h .. HD*h + HD-1 (HD = 40: the K image is zero where
+          // a block's columns belong to a neighbour); block t: boxes of 4 blocks (SW128) for t < 8, the SW64 box for t = 8, 9
+          const int t0b = (h * D) >> 4;
 #pragma unroll
-            for (int ks = 0; ks < C::KSTEPS; ++ks) {
-              const int t = t0b + ks;
-              const uint64_t ad = t < 8 ? smem_desc_sw128(sQ + (t >> 2) * BOX128_BYTES + (t & 3) * 32)
-                                        : smem_desc_sw64(sQ + 2 * BOX128_BYTES + (t - 8) * 32);
-              umma_ss(d, ad, smem_desc(kb + ks * 2 * K_CH, K_CH, 128), idesc_qk, ks);
-            }
-            tc_commit(b_srdy + 16 * g + 8 * buf);
-            X3_TRACE(44);
-            jq += NWG;
-            progress = true;
+          for (int ks = 0; ks < C::KSTEPS; ++ks) {
+            const int t = t0b + ks;
+            const uint64_t ad = t < 8 ? smem_desc_sw128(sQ + (t >> 2) * BOX128_BYTES + (t & 3) * 32)
+                                      : smem_desc_sw64(sQ + 2 * BOX128_BYTES + (t - 8) * 32);
+            umma_ss(d, ad, smem_desc(kb + ks * 2 * K_CH, K_CH, 128), idesc_qk, ks);
+          }
+          tc_commit(b_srdy + 16 * g + 8 * buf);
+          X3_TRACE(44);
+          jq += NWG;
+          if constexpr (!STATS) {
+            if (jq - jp <= AHEAD && jq < n_jobs) continue;  // start-up: the first item's Q K^T pair before any P V
           }
         }
         if constexpr (!STATS) {
-          if (jp < jq && test_bar(b_prdy + 8 * g, npv & 1)) {
+          if (jp < jq) {
+            X3_TRACE(45);
+            wait_bar<true>(b_prdy + 8 * g, npv & 1, 6);
             X3_TRACE(46);
             ++npv;
             tc_fence_after();
@@ -470,10 +494,10 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
             tc_commit(b_ordy + 8 * g);
             X3_TRACE(47);
             jp += NWG;
-            progress = true;
           }
         }
-        idle_or_trap(progress, idle_spins, idle_t0, 20);
+        (void)idle_spins;
+        (void)idle_t0;
       }
     }
     __syncwarp();
