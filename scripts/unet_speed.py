@@ -40,6 +40,18 @@ def run(channels_last, bench, graph):
         for _ in range(10): fn()
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 10
     print(f"channels_last={channels_last} cudnn.benchmark={bench} graph={graph}: {dt*1e3:.2f} ms per UNet step (batch 16), finite={bool(torch.isfinite(y.float()).all())}", flush=True)
-for cfg in [(False, False, False), (False, True, False), (True, True, False), (True, True, True), (False, True, True)]:
-    try: run(*cfg)
+    if os.environ.get("DSC_UNET_PROFILE") and not graph:
+        from torch.profiler import ProfilerActivity, profile
+        with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
+            net(x, t, ctx, cross_attention_kwargs=kw)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=90), flush=True)
+    return y
+outs = {}
+for cfg in [(False, True, False), (True, True, False), (True, True, True), (False, True, True)]:
+    try: outs[cfg] = run(*cfg).float()
     except Exception as e: print(cfg, "FAILED", repr(e)[:300], flush=True)
+if (False, True, False) in outs and (True, True, False) in outs:
+    a, b = outs[(False, True, False)], outs[(True, True, False)]
+    print("channels_last (NHWC GroupNorm) vs NCHW (F.group_norm) output: cosine",
+          float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)), "max abs", float((a - b).abs().max()))
