@@ -69,7 +69,16 @@ struct Cfg {
   static_assert(HD == 40 || HD == 80 || HD == 160, "head dim");
   static constexpr int D = HD, HPT = GW / HD, LOG_HPT = HD == 40 ? 2 : HD == 80 ? 1 : 0;
   static constexpr int NWG = HD == 40 ? 3 : HD == 80 ? 2 : 1;
-  static constexpr int THREADS = NWG * 128 + 128, CONSUMERS = NWG * 128;
+  // pass 1: consumer warpgroups + 4 service warps.  pass 2: consumer warpgroups + one DRAIN warpgroup (O rows: TMEM -> x 1/rowsum
+  // -> ring stage; warp d serves TMEM lanes 32d..32d+31 of every consumer warpgroup) + 4 service warps; the register file is
+  // re-divided with setmaxnreg (consumers up, drain / service warps down)
+  static constexpr int CONSUMERS = NWG * 128;
+  static constexpr int threads(bool stats) { return CONSUMERS + (stats ? 128 : 256); }
+  static constexpr int REGS_CONSUMER = HD == 40 ? 128 : HD == 80 ? 184 : 232;  // x CONSUMERS
+  static constexpr int REGS_DRAIN = HD == 40 ? 56 : HD == 80 ? 80 : 96;        // x 128
+  static constexpr int REGS_SERVICE = 40;                                      // x 128
+  static constexpr int REGS_LAUNCH = (65536 / threads(false)) / 8 * 8;         // what __launch_bounds__(threads, 1) grants: 96 / 128 / 168
+  static_assert(CONSUMERS * REGS_CONSUMER + 128 * (REGS_DRAIN + REGS_SERVICE) <= threads(false) * REGS_LAUNCH, "register pool");
   static constexpr int KSTEPS = HD == 40 ? 3 : HD / 16, NKC = 2 * KSTEPS;
   static constexpr int ON = HD == 40 ? 48 : HD == 80 ? 96 : 176;
   static constexpr int WG_COLS = O_COL + ON;
@@ -87,7 +96,6 @@ struct Cfg {
   static constexpr int FWD_NST = HD == 160 ? 2 : 3;
   static constexpr int FWD_SMEM = NSLOT * REC_BYTES + FWD_NST * FWD_STAGE + BAR_BYTES;
   static constexpr int STATS_SMEM = NSLOT * K_HEAD + STATS_NST * STATS_STAGE + BAR_BYTES;
-  static constexpr int kProducerTid = CONSUMERS;
   static constexpr int TURNS = NWG == 3 ? X3_TURNS_DEFAULT : 0;
   static_assert((NSLOT * REC_BYTES) % 1024 == 0 && (NSLOT * K_HEAD) % 1024 == 0 && FWD_STAGE % 1024 == 0 && STATS_STAGE % 1024 == 0 &&
                     REC_BYTES % 16 == 0 && K_HEAD % 16 == 0, "alignment");
@@ -162,6 +170,26 @@ __device__ __forceinline__ void idle_or_trap(bool progress, uint32_t& spins, lon
     __trap();
   }
 }
+// warp-converged variants (tensor-core issuer warps): every lane probes, the vote makes the answer warp-uniform
+__device__ __forceinline__ bool test_bar_u(uint32_t bar, uint32_t parity) { return __all_sync(0xffffffffu, test_bar(bar, parity)); }
+__device__ __forceinline__ void wait_bar_u(uint32_t bar, uint32_t parity) {
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (__all_sync(0xffffffffu, ok != 0)) return;
+    __nanosleep(40);
+    if (++spins == 64) t0 = clock64();
+    if (spins > 64 && clock64() - t0 > (1ll << 32)) __trap();  // ~2 s: unreachable unless the barrier protocol is broken
+  }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 template <bool RELAXED>
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t tag) {
   long long t0 = 0;
@@ -195,8 +223,8 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t
 #ifdef DSC_TRACE
 // Debug build only: clock64 timeline of block 0 -- thread 0 of each consumer warpgroup, the producer, the three issuers
 // -> g_x3_trace[pass][who][slot] = {tag, clock}; globaltimer at start / end of every CTA.
-__device__ long long g_x3_trace[2][7][1024][2];
-__device__ int g_x3_trace_n[2][7];
+__device__ long long g_x3_trace[2][8][1024][2];
+__device__ int g_x3_trace_n[2][8];
 __device__ unsigned long long g_x3_cta[2][160][2];
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
@@ -205,12 +233,13 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 }
 #define X3_TRACE_DECL                                                                                   \
   int tr_n = 0;                                                                                         \
-  const int tr_c = Cfg<HD>::CONSUMERS;                                                                  \
+  const int tr_c = Cfg<HD>::CONSUMERS, tr_s = tr_c + (STATS ? 0 : 128);                                 \
   const int tr_k = blockIdx.x != 0 ? -1                                                                 \
                    : (threadIdx.x & 127) == 0 && (int)threadIdx.x < tr_c ? (int)(threadIdx.x >> 7)      \
-                   : (int)threadIdx.x == tr_c ? 3                                                       \
-                   : ((int)threadIdx.x >= tr_c + 32 && (int)threadIdx.x < tr_c + 32 * (1 + Cfg<HD>::NWG) && (threadIdx.x & 31) == 0) \
-                       ? 4 + (int)((threadIdx.x - tr_c - 32) >> 5) : -1;
+                   : (int)threadIdx.x == tr_s ? 3                                                       \
+                   : ((int)threadIdx.x >= tr_s + 32 && (int)threadIdx.x < tr_s + 32 * (1 + Cfg<HD>::NWG) && (threadIdx.x & 31) == 0) \
+                       ? 4 + (int)((threadIdx.x - tr_s - 32) >> 5)                                      \
+                   : (!STATS && (int)threadIdx.x == tr_c) ? 7 : -1;
 #define X3_TRACE(tag)                                            \
   do {                                                           \
     if (tr_k >= 0 && tr_n < 1024) {                              \
@@ -226,15 +255,29 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 #define X3_CTA_TIME(k) do {} while (0)
 #endif
 
+#ifdef DSC_PHASE
+// Debug build only: cycles per phase of the pass-2 consumer loop, accumulated in registers (no stores inside the loop), written
+// once at the end by lane 0 of every consumer warp of blocks 0..3 -> g_x3_phase[block][warp][phase]
+__device__ unsigned int g_x3_phase[4][12][8];
+#define X3_PH_DECL long long ph_t = clock64(); unsigned int ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define X3_PH(k) do { const long long ph_c = clock64(); ph[k] += static_cast<unsigned int>(ph_c - ph_t); ph_t = ph_c; } while (0)
+#define X3_PH_FLUSH do { if (!STATS && lane == 0 && blockIdx.x < 4 && warp < 12) { for (int k = 0; k < 8; ++k) g_x3_phase[blockIdx.x][warp][k] = ph[k]; } } while (0)
+#else
+#define X3_PH_DECL
+#define X3_PH(k) do {} while (0)
+#define X3_PH_FLUSH do {} while (0)
+#endif
+
 template <typename T, int HD, bool STATS>
-__global__ void __launch_bounds__(Cfg<HD>::THREADS, 1)
+__global__ void __launch_bounds__(Cfg<HD>::threads(STATS), 1)
 xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, const __grid_constant__ CUtensorMap tm_qb,
                 const __grid_constant__ CUtensorMap tm_qp, const __grid_constant__ CUtensorMap tm_oa,
                 const __grid_constant__ CUtensorMap tm_ob) {
   using C = Cfg<HD>;
   constexpr int D = C::D, HPT = C::HPT, LOG_HPT = C::LOG_HPT, NWG = C::NWG, CONSUMERS = C::CONSUMERS, WG_COLS = C::WG_COLS;
   constexpr int K_HEAD = C::K_HEAD, VT_CH = C::VT_CH, IMG_BYTES = C::IMG_BYTES, NSLOT = C::NSLOT;
-  constexpr int kProducerTid = C::kProducerTid, SW0 = 4 * NWG;  // first service warp
+  constexpr int DW0 = 4 * NWG;                    // pass 2: first warp of the drain warpgroup
+  constexpr int SW0 = STATS ? 4 * NWG : 4 * NWG + 4;  // first service warp
   constexpr int NST = STATS ? STATS_NST : C::FWD_NST;
   constexpr int STAGE = STATS ? STATS_STAGE : FWD_STAGE;
   constexpr int RECB = STATS ? K_HEAD : C::REC_BYTES;  // bytes of a record this pass needs (pass 1: its K part) = slot pitch
@@ -260,12 +303,12 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sStage = s0 + KV;
   const uint32_t bars = sStage + NST * STAGE;
-  // barrier map (8 B each): full[4] | odone[4] | kvfull[4] | kvfree[4] | srdy[3][2] | sfree[3][2] | prdy[3] | ordy[3]
+  // barrier map (8 B each): full[4] | odone[4] | kvfull[4] | kvfree[4] | srdy[3][2] | sfree[3][2] | prdy[3] | ordy[3] | ofree[3]
   const uint32_t b_full = bars, b_odone = bars + 32, b_kvfull = bars + 64, b_kvfree = bars + 96, b_srdy = bars + 128,
-                 b_sfree = bars + 176, b_prdy = bars + 224, b_ordy = bars + 248;
-  constexpr int N_BARS = 34;
-  volatile uint32_t* turn_ptr = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 272);
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 288);
+                 b_sfree = bars + 176, b_prdy = bars + 224, b_ordy = bars + 248, b_ofree = bars + 272;
+  constexpr int N_BARS = 37;
+  volatile uint32_t* turn_ptr = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 320);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 336);
 
   const int begin = static_cast<int>(p.total * blockIdx.x / gridDim.x);
   const int n_items = static_cast<int>(p.total * (blockIdx.x + 1) / gridDim.x) - begin;
@@ -275,11 +318,16 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   const uint64_t pol_q = STATS ? policy_evict_last() : policy_evict_first();  // pass 2 reads Q again: keep it in L2
   const unsigned char* img = reinterpret_cast<const unsigned char*>(p.kv_image);
 
+  // The producer WARP runs converged (see the issuer warps below): addresses / coordinates are warp-uniform, the TMA
+  // instructions are issued by the elected lane (always the same one: bulk groups are per thread)
   auto load_record = [&](int rec) {  // head record (K_h | V^T_h; pass 1: K_h) of run rec / HPT -> slot rec % NSLOT: one bulk copy
     const int slot = rec % NSLOT;
-    mbar_arrive_expect_tx(b_kvfull + 8 * slot, RECB);
-    bulk_g2s_hint(s0 + slot * RECB, img + static_cast<size_t>(seg0 + (rec >> LOG_HPT)) * IMG_BYTES + (rec & (HPT - 1)) * C::REC_BYTES, RECB,
-                  b_kvfull + 8 * slot, policy_evict_last());
+    const unsigned char* src = img + static_cast<size_t>(seg0 + (rec >> LOG_HPT)) * IMG_BYTES + (rec & (HPT - 1)) * C::REC_BYTES;
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_kvfull + 8 * slot, RECB);
+      bulk_g2s_hint(s0 + slot * RECB, src, RECB, b_kvfull + 8 * slot, policy_evict_last());
+    }
+    __syncwarp();
   };
   auto load_tile = [&](int i) {  // Q boxes (+ compact W tile) of tile i -> ring stage i % NST
     const int s = i % NST;
@@ -287,40 +335,46 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     const uint32_t sQ = sStage + s * STAGE, bar = b_full + 8 * s;
     const int c0 = t.hg * GW;
     uint32_t wbytes = 0;
-    if constexpr (!STATS) wbytes = static_cast<uint32_t>(min(ROWS, p.L - t.l0)) * (DSC_COMPACT_PITCH * 4);
-    mbar_arrive_expect_tx(bar, QT_BYTES + wbytes);  // out-of-range parts of a box are zero-filled and still counted
-    tma_load_3d(sQ, &tm_qa, c0, t.l0, t.b, bar, pol_q);
-    tma_load_3d(sQ + BOX128_BYTES, &tm_qa, c0 + 64, t.l0, t.b, bar, pol_q);
-    tma_load_3d(sQ + 2 * BOX128_BYTES, &tm_qb, c0 + 128, t.l0, t.b, bar, pol_q);
-    if constexpr (!STATS)  // the compact W rows of a tile are contiguous: one bulk copy
-      bulk_g2s_hint(sQ + QT_BYTES, p.wc + (static_cast<size_t>(t.b / (p.B / p.Bw)) * p.L + t.l0) * DSC_COMPACT_PITCH, wbytes, bar, pol_q);
-    if (t.tile == p.n_sl - 1 && i + 1 < n_items) {  // the run ends with this tile: pull the next image towards L2
-      const Tile n = decode(begin + i + 1, p);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(img + (static_cast<size_t>(n.b) * p.n_hg + n.hg) * IMG_BYTES),
-                   "r"(IMG_BYTES)
-                   : "memory");
+    const float* wsrc = nullptr;
+    if constexpr (!STATS) {
+      wbytes = static_cast<uint32_t>(min(ROWS, p.L - t.l0)) * (DSC_COMPACT_PITCH * 4);
+      wsrc = p.wc + (static_cast<size_t>(t.b / (p.B / p.Bw)) * p.L + t.l0) * DSC_COMPACT_PITCH;
     }
-#if X3_L2_PREFETCH
-    if (i + NST < n_items) {  // the tile that will reuse this stage: one 160-column box (+ its W box) towards L2
-      const Tile n = decode(begin + i + NST, p);
-      asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&tm_qp), "r"(n.hg * GW), "r"(n.l0),
-                   "r"(n.b)
-                   : "memory");
-      if constexpr (!STATS)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
-                         p.wc + (static_cast<size_t>(n.b / (p.B / p.Bw)) * p.L + n.l0) * DSC_COMPACT_PITCH),
-                     "r"(static_cast<uint32_t>(min(ROWS, p.L - n.l0)) * (DSC_COMPACT_PITCH * 4))
+    const bool run_ends = t.tile == p.n_sl - 1 && i + 1 < n_items;  // pull the next image towards L2
+    const bool pre = X3_L2_PREFETCH && i + NST < n_items;           // the tile that will reuse this stage: towards L2
+    const Tile n1 = decode(begin + min(i + 1, n_items - 1), p);
+    const Tile n2 = decode(begin + min(i + NST, n_items - 1), p);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar, QT_BYTES + wbytes);  // out-of-range parts of a box are zero-filled and still counted
+      tma_load_3d(sQ, &tm_qa, c0, t.l0, t.b, bar, pol_q);
+      tma_load_3d(sQ + BOX128_BYTES, &tm_qa, c0 + 64, t.l0, t.b, bar, pol_q);
+      tma_load_3d(sQ + 2 * BOX128_BYTES, &tm_qb, c0 + 128, t.l0, t.b, bar, pol_q);
+      if constexpr (!STATS)  // the compact W rows of a tile are contiguous: one bulk copy
+        bulk_g2s_hint(sQ + QT_BYTES, wsrc, wbytes, bar, pol_q);
+      if (run_ends)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(img + (static_cast<size_t>(n1.b) * p.n_hg + n1.hg) * IMG_BYTES),
+                     "r"(IMG_BYTES)
                      : "memory");
+      if (pre) {  // one 160-column box (+ its W rows)
+        asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&tm_qp), "r"(n2.hg * GW), "r"(n2.l0),
+                     "r"(n2.b)
+                     : "memory");
+        if constexpr (!STATS)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                           p.wc + (static_cast<size_t>(n2.b / (p.B / p.Bw)) * p.L + n2.l0) * DSC_COMPACT_PITCH),
+                       "r"(static_cast<uint32_t>(min(ROWS, p.L - n2.l0)) * (DSC_COMPACT_PITCH * 4))
+                       : "memory");
+      }
     }
-#endif
+    __syncwarp();
   };
 
   // barrier init is spread over the service warps so that the first loads leave as early as possible: the producer
-  // thread initialises only what those loads signal (full[], kvfull[]), service warp 2 the rest
-  if (tid == kProducerTid) {
-    for (int st = 0; st < 4; ++st) mbar_init(b_full + 8 * st, 1);
-    for (int st = 0; st < 4; ++st) mbar_init(b_kvfull + 8 * st, 1);
+  // warp initialises only what those loads signal (full[], kvfull[]), service warp 2 the rest
+  if (warp == SW0) {
+    if (lane < 8) mbar_init((lane < 4 ? b_full : b_kvfull - 32) + 8 * lane, 1);
     fence_mbar_init();
+    __syncwarp();
     X3_TRACE(4);
     if (n_items > 0) {  // only what the first Q K^T needs is issued ahead of the CTA-wide barrier
       load_record(0);
@@ -331,8 +385,9 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   if (warp == SW0 + 2) {
     for (int idx = 4 + lane; idx < N_BARS; idx += 32) {
       if (idx >= 8 && idx < 12) continue;  // kvfull[]: the producer's
-      // odone[]: every consumer of every head of the tile | kvfree[]: every consumer | srdy, ordy: one commit | sfree, prdy: a warpgroup
-      const uint32_t cnt = idx < 8 ? HPT * 128u : idx < 16 ? static_cast<uint32_t>(CONSUMERS) : idx < 22 ? 1u : idx < 31 ? 128u : 1u;
+      // odone[]: 128 rows of every head of the tile | kvfree[]: every consumer | srdy, ordy: one commit | sfree, prdy: a warpgroup |
+      // ofree[]: the drain warpgroup
+      const uint32_t cnt = idx < 8 ? HPT * 128u : idx < 16 ? static_cast<uint32_t>(CONSUMERS) : idx < 22 ? 1u : idx < 31 ? 128u : idx < 34 ? 1u : 128u;
       mbar_init(bars + 8 * idx, cnt);
     }
     fence_mbar_init();
@@ -352,23 +407,23 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   X3_TRACE(2);
 
   const int n_jobs = n_items * HPT;  // (tile, head) work items of this CTA, in order; item J -> warpgroup J % NWG
-  auto rec_of = [&](int J) { return (((begin + (J >> LOG_HPT)) / p.n_sl) - seg0) * HPT + (J & (HPT - 1)); };
 
   if (warp >= SW0) {
-    if (tid == kProducerTid) {
-      // ============================== producer: TMA loads and stores ===============================
-      // one thread.  It never blocks on one condition while another could make progress:
+    if constexpr (!STATS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_SERVICE));
+    if (warp == SW0) {
+      // ============================== producer warp: TMA loads and stores ==========================
+      // It never blocks on one condition while another could make progress:
       //   * head record rec goes into slot rec % NSLOT as soon as every warpgroup has released record rec - NSLOT
       //   * tile ld goes into ring stage ld % NST as soon as tile ld - NST has been retired and its store has read the stage
-      //   * tile dn is retired (pass 2: its O rows leave through three tensor-map stores) when every consumer has handed it back
+      //   * tile dn is retired (pass 2: its O rows leave through three tensor-map stores) when every row has been handed back
       // While a record refill may become possible (the consumers are within a tile of the end of the run that still
-      // uses the slot) both conditions are polled; otherwise the thread sleeps on the hand-back barrier.
+      // uses the slot) both conditions are polled; otherwise the warp sleeps on the hand-back barrier.
       int ld = n_items > 0 ? 1 : 0, dn = 0, rec = n_rec > 0 ? 1 : 0;
       uint32_t idle_spins = 0;
       long long idle_t0 = 0;
       X3_TRACE(8);
       while (dn < n_items) {
-        while (rec < n_rec && (rec < NSLOT || test_bar(b_kvfree + 8 * (rec % NSLOT), (rec / NSLOT - 1) & 1))) {
+        while (rec < n_rec && (rec < NSLOT || test_bar_u(b_kvfree + 8 * (rec % NSLOT), (rec / NSLOT - 1) & 1))) {
           load_record(rec++);
           X3_TRACE(33);
         }
@@ -376,9 +431,12 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           if constexpr (!STATS) {
             if (ld >= NST) {  // the store of tile ld - NST (bulk group ld - NST of dn committed so far) must have read the stage
               const int later = dn - 1 - (ld - NST);  // groups committed after it: may stay pending
-              if (later <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              else if (later == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-              else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+              if (elect_one()) {
+                if (later <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                else if (later == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+              }
+              __syncwarp();
             }
           }
           load_tile(ld++);
@@ -390,44 +448,57 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           poll = dn + 1 >= e_old;
         }
         if (poll) {
-          if (!test_bar(b_odone + 8 * (dn % NST), (dn / NST) & 1)) {
+          if (!test_bar_u(b_odone + 8 * (dn % NST), (dn / NST) & 1)) {
             idle_or_trap(false, idle_spins, idle_t0, 32);
             continue;
           }
           idle_spins = 0;
         } else {
-          wait_bar<true>(b_odone + 8 * (dn % NST), (dn / NST) & 1, 1);
+          wait_bar_u(b_odone + 8 * (dn % NST), (dn / NST) & 1);
         }
         X3_TRACE(31);
         if constexpr (!STATS) {
           const Tile t = decode(begin + dn, p);
           const uint32_t sQ = sStage + (dn % NST) * STAGE;
           const int c0 = t.hg * GW;
-          tma_store_3d(&tm_oa, c0, t.l0, t.b, sQ);  // rows >= L and columns >= H*D are clipped by the TMA
-          tma_store_3d(&tm_oa, c0 + 64, t.l0, t.b, sQ + BOX128_BYTES);
-          tma_store_3d(&tm_ob, c0 + 128, t.l0, t.b, sQ + 2 * BOX128_BYTES);
-          bulk_commit();
+          if (elect_one()) {
+            tma_store_3d(&tm_oa, c0, t.l0, t.b, sQ);  // rows >= L and columns >= H*D are clipped by the TMA
+            tma_store_3d(&tm_oa, c0 + 64, t.l0, t.b, sQ + BOX128_BYTES);
+            tma_store_3d(&tm_ob, c0 + 128, t.l0, t.b, sQ + 2 * BOX128_BYTES);
+            bulk_commit();
+          }
+          __syncwarp();
           X3_TRACE(32);
         }
         ++dn;
       }
-      if constexpr (!STATS) bulk_wait0();
-    } else if (lane == 0 && warp > SW0 && warp - SW0 - 1 < NWG) {
+      if constexpr (!STATS) {
+        if (elect_one()) bulk_wait0();
+        __syncwarp();
+      }
+    } else if (warp > SW0 && warp - SW0 - 1 < NWG) {
       // ============================== tensor-core issuer of warpgroup g ============================
+      // The WHOLE warp runs this loop converged: every value that feeds an MMA (descriptors, TMEM addresses) is
+      // warp-uniform to the compiler (warp index through a shuffle, barrier probes through votes), so it lives in uniform
+      // registers and an MMA is ONE predicated UTCHMMA issued by the elected lane -- a single-lane loop gets every operand
+      // through an ELECT / R2UR.BROADCAST waterfall, ~120 cycles per MMA (profiles/r2_x3_trace_*: 350 / 700 cycles to issue
+      // the 3 / 5 MMAs of an item), and that latency sits on the consumers' critical path (P published -> P V done).
       // Steady state: Q K^T of item j + NWG when the S columns are free (the consumers have read S(j)), then P V of item j
       // when its P is published -- each a sleeping wait on one barrier.  The exception is a Q K^T whose head record has not
-      // arrived yet: its slot is released only after earlier P Vs have been drained, so the issuer never blocks on a record
+      // arrived yet: its slot is released only after earlier P Vs have completed, so the issuer never blocks on a record
       // while a P V is outstanding; it issues that P V first and comes back.
-      // Invariant that keeps the consumers' top-of-item drain alive: before blocking for Q K^T(jq), P V(jq - 2 NWG) has
+      // Invariant that keeps the consumers' record release alive: before blocking for Q K^T(jq), P V(jq - 2 NWG) has
       // been issued (jq - jp <= NWG).
-      const int g = warp - SW0 - 1;
+      const int g = __shfl_sync(0xffffffffu, warp, 0) - SW0 - 1;
       constexpr uint32_t idesc_qk = idesc_f16<T>(80);
       constexpr uint32_t idesc_pv = idesc_f16<T>(C::ON);
       constexpr int AHEAD = STATS ? 2 * NWG : NWG;  // pass 1: S is double-buffered
-      const uint32_t tw = tmem_base + g * WG_COLS;
-      uint32_t nqk = 0, npv = 0, idle_spins = 0;
-      long long idle_t0 = 0;
+      const uint32_t tw = __shfl_sync(0xffffffffu, tmem_base, 0) + g * WG_COLS;
+      uint32_t nqk = 0, npv = 0;
       int jq = g, jp = g;
+      // (batch, head group) run of a tile, tracked without divisions: tiles only move forward
+      const int run_end0 = (seg0 + 1) * p.n_sl - begin;  // first local tile of run 1
+      int q_run = 0, q_next = run_end0, p_run = 0, p_next = run_end0;
       // records this issuer has SEEN loaded, in record order.  Every record is observed, used by this warpgroup or not: a
       // parity test is only meaningful against the phase right after the last one observed (testing the phase of a later
       // record while an earlier load into the same slot is still in flight would read as "complete")
@@ -436,11 +507,16 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
         bool qk_now = false;
         int rc = 0;
         if (jq < n_jobs && (STATS || jq - jp <= AHEAD)) {
-          rc = rec_of(jq);
-          while (rec_seen <= rc && test_bar(b_kvfull + 8 * (rec_seen % NSLOT), (rec_seen / NSLOT) & 1)) ++rec_seen;
+          const int iq = jq >> LOG_HPT;
+          while (iq >= q_next) {
+            ++q_run;
+            q_next += p.n_sl;
+          }
+          rc = q_run * HPT + (jq & (HPT - 1));
+          while (rec_seen <= rc && test_bar_u(b_kvfull + 8 * (rec_seen % NSLOT), (rec_seen / NSLOT) & 1)) ++rec_seen;
           qk_now = rec_seen > rc;
           if (!qk_now && (STATS || jp == jq)) {  // nothing else to do: sleep on the record that is next in line
-            wait_bar<true>(b_kvfull + 8 * (rec_seen % NSLOT), (rec_seen / NSLOT) & 1, 3);
+            wait_bar_u(b_kvfull + 8 * (rec_seen % NSLOT), (rec_seen / NSLOT) & 1);
             ++rec_seen;
             continue;
           }
@@ -448,13 +524,13 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
         if (qk_now) {
           const int i = jq >> LOG_HPT, h = jq & (HPT - 1), s = i % NST, slot = rc % NSLOT;
           X3_TRACE(42);
-          wait_bar<true>(b_full + 8 * s, (i / NST) & 1, 4);
+          wait_bar_u(b_full + 8 * s, (i / NST) & 1);
           uint32_t buf = 0;
           if constexpr (STATS) {
             buf = nqk & 1;
-            if (nqk >= 2) wait_bar<true>(b_sfree + 16 * g + 8 * buf, ((nqk >> 1) - 1) & 1, 5);
+            if (nqk >= 2) wait_bar_u(b_sfree + 16 * g + 8 * buf, ((nqk >> 1) - 1) & 1);
           } else {
-            if (nqk >= 1) wait_bar<true>(b_sfree + 16 * g, (nqk - 1) & 1, 5);
+            if (nqk >= 1) wait_bar_u(b_sfree + 16 * g, (nqk - 1) & 1);
           }
           X3_TRACE(43);
           ++nqk;
@@ -465,14 +541,17 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           // head h = the KSTEPS 16-column blocks that cover columns HD*h .. HD*h + HD-1 (HD = 40: the K image is zero where
           // a block's columns belong to a neighbour); block t: boxes of 4 blocks (SW128) for t < 8, the SW64 box for t = 8, 9
           const int t0b = (h * D) >> 4;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < C::KSTEPS; ++ks) {
-            const int t = t0b + ks;
-            const uint64_t ad = t < 8 ? smem_desc_sw128(sQ + (t >> 2) * BOX128_BYTES + (t & 3) * 32)
-                                      : smem_desc_sw64(sQ + 2 * BOX128_BYTES + (t - 8) * 32);
-            umma_ss(d, ad, smem_desc(kb + ks * 2 * K_CH, K_CH, 128), idesc_qk, ks);
+            for (int ks = 0; ks < C::KSTEPS; ++ks) {
+              const int t = t0b + ks;
+              const uint64_t ad = t < 8 ? smem_desc_sw128(sQ + (t >> 2) * BOX128_BYTES + (t & 3) * 32)
+                                        : smem_desc_sw64(sQ + 2 * BOX128_BYTES + (t - 8) * 32);
+              umma_ss(d, ad, smem_desc(kb + ks * 2 * K_CH, K_CH, 128), idesc_qk, ks);
+            }
+            tc_commit(b_srdy + 16 * g + 8 * buf);
           }
-          tc_commit(b_srdy + 16 * g + 8 * buf);
+          __syncwarp();
           X3_TRACE(44);
           jq += NWG;
           if constexpr (!STATS) {
@@ -482,27 +561,119 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
         if constexpr (!STATS) {
           if (jp < jq) {
             X3_TRACE(45);
-            wait_bar<true>(b_prdy + 8 * g, npv & 1, 6);
+            wait_bar_u(b_prdy + 8 * g, npv & 1);
+            if (npv >= 1) wait_bar_u(b_ofree + 8 * g, (npv - 1) & 1);  // the drain warpgroup holds O of the previous item in registers
             X3_TRACE(46);
             ++npv;
             tc_fence_after();
-            const uint32_t vb = s0 + (rec_of(jp) % NSLOT) * RECB + K_HEAD;
+            const int ip = jp >> LOG_HPT;
+            while (ip >= p_next) {
+              ++p_run;
+              p_next += p.n_sl;
+            }
+            const uint32_t vb = s0 + ((p_run * HPT + (jp & (HPT - 1))) % NSLOT) * RECB + K_HEAD;
             const uint64_t vdesc = smem_desc(vb, VT_CH, 128);
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 5; ++kk)
-              umma_ts(tw + O_COL, tw + P_COL + kk * 8, vdesc + static_cast<uint64_t>((kk * 2 * VT_CH) >> 4), idesc_pv, kk);
-            tc_commit(b_ordy + 8 * g);
+              for (int kk = 0; kk < 5; ++kk)
+                umma_ts(tw + O_COL, tw + P_COL + kk * 8, vdesc + static_cast<uint64_t>((kk * 2 * VT_CH) >> 4), idesc_pv, kk);
+              tc_commit(b_ordy + 8 * g);
+            }
+            __syncwarp();
             X3_TRACE(47);
             jp += NWG;
           }
         }
-        (void)idle_spins;
-        (void)idle_t0;
       }
     }
     __syncwarp();
+  } else if (!STATS && warp >= DW0) {
+    // ============================== drain warpgroup (pass 2): O rows out of TMEM ====================
+    // Warp d serves TMEM lanes 32d .. 32d+31 (tile rows) of every consumer warpgroup.  Items in CTA order: wait for P V(J)
+    // (ordy of warpgroup J % NWG), O row -> registers, O columns handed back to the issuer (ofree: P V of the warpgroup's
+    // next item may overwrite them), x 1/rowsum (ones row of V^T: column HD) -> over the row's own Q columns in the ring
+    // stage, stage handed back to the producer (odone).  The consumer warps never touch O: their loop is S -> softmax -> P.
+    if constexpr (!STATS) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_DRAIN));
+      const int row = (warp & 3) * 32 + lane;
+      const uint32_t tl = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + O_COL;
+      auto pack_store = [&](const float* o8, float inv, unsigned char* d) {
+        float t[8];
+        fmul2(t[0], t[1], o8[0], o8[1], inv, inv);
+        fmul2(t[2], t[3], o8[2], o8[3], inv, inv);
+        fmul2(t[4], t[5], o8[4], o8[5], inv, inv);
+        fmul2(t[6], t[7], o8[6], o8[7], inv, inv);
+        uint4 v;
+        v.x = Mma<T>::pack(t[0], t[1]);
+        v.y = Mma<T>::pack(t[2], t[3]);
+        v.z = Mma<T>::pack(t[4], t[5]);
+        v.w = Mma<T>::pack(t[6], t[7]);
+        *reinterpret_cast<uint4*>(d) = v;
+      };
+      int g = 0, k = 0;  // item J = NWG * k + g
+      for (int J = 0; J < n_jobs; ++J) {
+        const int i = J >> LOG_HPT, h = J & (HPT - 1), s = i % NST;
+        const uint32_t tw = tl + g * WG_COLS;
+        unsigned char* st = smem + KV + s * STAGE;
+        // 16-byte chunk c of the head's O row = global chunk G = (HD/8) h + c of the 160-column tile row: the place its Q
+        // columns had (swizzled: 8 consecutive rows hit 8 distinct bank groups)
+        auto dst_of = [&](int c) -> unsigned char* {
+          const int G = h * C::CPH + c;
+          return G < 16 ? st + (G >> 3) * BOX128_BYTES + row * 128 + (((G & 7) ^ (row & 7)) << 4)
+                        : st + 2 * BOX128_BYTES + row * 64 + ((((G - 16) & 3) ^ ((row >> 1) & 3)) << 4);
+        };
+        X3_TRACE(13);
+        wait_bar<false>(b_ordy + 8 * g, k & 1, 7);
+        X3_TRACE(14);
+        tc_fence_after();
+        if constexpr (HD == 40) {
+          float o[40], oz[4];
+          tmem_ld_x16(tw, reinterpret_cast<uint32_t*>(o));
+          tmem_ld_x16(tw + 16, reinterpret_cast<uint32_t*>(o + 16));
+          tmem_ld_x8(tw + 32, reinterpret_cast<uint32_t*>(o + 32));
+          tmem_ld_x4(tw + 40, reinterpret_cast<uint32_t*>(oz));
+          tc_wait_ld();
+          tc_fence_before();
+          mbar_arrive(b_ofree + 8 * g);
+          const float inv = 1.f / oz[0];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) pack_store(o + 8 * c, inv, dst_of(c));
+        } else {
+          // HD = 80 / 160: the row sum (column HD) first, then PIECE columns at a time, the next piece in flight while the
+          // current one is scaled, packed and stored
+          constexpr int PIECE = HD == 160 ? 32 : 16, NP = HD / PIECE;
+          float oz[4], oa[PIECE], ob[PIECE];
+          auto ld_piece = [&](int pc, float* dst) {
+            if constexpr (PIECE == 32) tmem_ld_x32(tw + PIECE * pc, reinterpret_cast<uint32_t*>(dst));
+            else tmem_ld_x16(tw + PIECE * pc, reinterpret_cast<uint32_t*>(dst));
+          };
+          tmem_ld_x4(tw + HD, reinterpret_cast<uint32_t*>(oz));
+          ld_piece(0, oa);
+          tc_wait_ld();
+          const float inv = 1.f / oz[0];
+#pragma unroll
+          for (int pc = 0; pc < NP; ++pc) {
+            float* cur = (pc & 1) ? ob : oa;
+            if (pc + 1 < NP) ld_piece(pc + 1, (pc & 1) ? oa : ob);
+#pragma unroll
+            for (int q = 0; q < PIECE / 8; ++q) pack_store(cur + 8 * q, inv, dst_of((PIECE / 8) * pc + q));
+            if (pc + 1 < NP) tc_wait_ld();
+          }
+          tc_fence_before();
+          mbar_arrive(b_ofree + 8 * g);
+        }
+        fence_proxy_async();  // O rows -> visible to the TMA store
+        mbar_arrive(b_odone + 8 * s);
+        X3_TRACE(15);
+        if (++g == NWG) {
+          g = 0;
+          ++k;
+        }
+      }
+    }
   } else {
     // ============================== consumers: one thread per query row ============================
+    if constexpr (!STATS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_CONSUMER));
     const int g = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t tw = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + g * WG_COLS;
@@ -520,92 +691,24 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     if constexpr (!STATS) sigma_v = p.sigma_dev ? __ldcg(p.sigma_dev) : p.sigma_host;
     double dsum = 0.0, dsq = 0.0;
     uint32_t n_s = 0, n_o = 0;
-    bool pend = false;  // an O row of this thread still sits in TMEM
-    int pend_s = 0, pend_h = 0;
+    bool pend = false;  // P V of this warpgroup's previous item may still be reading P (and the head record's V^T)
     // 3 warpgroups (HD = 40): the exponentials of an item ("M phase": 77 MUFU.EX2 per row, the bottleneck pipe: 4 lanes per
     // clock and SM sub-partition) are SERIALISED per sub-partition in item order: warp (g, quarter) waits until
     // turn[quarter] is within TURNS of its item's sequence number.  Left alone, the three warps of a sub-partition run in
     // lock-step -- they share the MUFU pipe fairly, so they finish their M phases together and then all do their MUFU-free
-    // work (S row out of TMEM, W, row max, O drain, barriers: ~1300 cycles) while the pipe idles
-    // (profiles/r2_x3_trace_lockstep.txt: 3.3k cycles per round of 3 items against 1.85k of MUFU work).  With turns, one or
-    // two warps exponentiate at the full pipe rate while the others do their MUFU-free part.
+    // work (S row out of TMEM, W, row max, barriers) while the pipe idles.  With turns, one or two warps exponentiate at
+    // the full pipe rate while the others do their MUFU-free part.
     volatile uint32_t* my_turn = turn_ptr + (warp & 3);
 
-    // O row of the warpgroup's previous item: TMEM -> x 1/rowsum (ones row of V^T: column HD) -> over the row's own Q
-    // columns in the ring stage, stage handed back
-    auto drain = [&]() {
-      X3_TRACE(13);
-      wait_bar<false>(b_ordy + 8 * g, n_o & 1, 7);
-      X3_TRACE(14);
-      ++n_o;
-      tc_fence_after();
-      unsigned char* st = smem + KV + pend_s * STAGE;
-      // 16-byte chunk c of the head's O row = global chunk G = (HD/8) h + c of the 160-column tile row: the place its Q
-      // columns had (swizzled: 8 consecutive rows hit 8 distinct bank groups)
-      auto dst_of = [&](int c) -> unsigned char* {
-        const int G = pend_h * C::CPH + c;
-        return G < 16 ? st + (G >> 3) * BOX128_BYTES + row * 128 + (((G & 7) ^ (row & 7)) << 4)
-                      : st + 2 * BOX128_BYTES + row * 64 + ((((G - 16) & 3) ^ ((row >> 1) & 3)) << 4);
-      };
-      auto chunk = [&](const float* o8, float inv, unsigned char* d) {
-        float t[8];
-        fmul2(t[0], t[1], o8[0], o8[1], inv, inv);
-        fmul2(t[2], t[3], o8[2], o8[3], inv, inv);
-        fmul2(t[4], t[5], o8[4], o8[5], inv, inv);
-        fmul2(t[6], t[7], o8[6], o8[7], inv, inv);
-        uint4 v;
-        v.x = Mma<T>::pack(t[0], t[1]);
-        v.y = Mma<T>::pack(t[2], t[3]);
-        v.z = Mma<T>::pack(t[4], t[5]);
-        v.w = Mma<T>::pack(t[6], t[7]);
-        *reinterpret_cast<uint4*>(d) = v;
-      };
-      if constexpr (HD == 40) {
-        float oa[16], oz[4];
-        tmem_ld_x16(tw + O_COL, reinterpret_cast<uint32_t*>(oa));
-        tmem_ld_x4(tw + O_COL + 40, reinterpret_cast<uint32_t*>(oz));
-        tc_wait_ld();
-        const float inv = 1.f / oz[0];
-        float ob[16];
-        tmem_ld_x16(tw + O_COL + 16, reinterpret_cast<uint32_t*>(ob));
-        chunk(oa, inv, dst_of(0));
-        chunk(oa + 8, inv, dst_of(1));
-        tc_wait_ld();
-        float oc[8];
-        tmem_ld_x8(tw + O_COL + 32, reinterpret_cast<uint32_t*>(oc));
-        chunk(ob, inv, dst_of(2));
-        chunk(ob + 8, inv, dst_of(3));
-        tc_wait_ld();
-        tc_fence_before();  // the O columns may be overwritten by the next P V once this thread has arrived on odone / prdy
-        chunk(oc, inv, dst_of(4));
-      } else {
-        // HD = 80 / 160: the row sum (column HD) first, then PIECE columns at a time (16 at HD = 80, where the 80 scores of
-        // the current item are live in registers; 32 at HD = 160), the next piece in flight while the current one is
-        // scaled, packed and stored
-        constexpr int PIECE = HD == 160 ? 32 : 16, NP = HD / PIECE;
-        float oz[4], oa[PIECE], ob[PIECE];
-        auto ld_piece = [&](int pc, float* dst) {
-          if constexpr (PIECE == 32) tmem_ld_x32(tw + O_COL + PIECE * pc, reinterpret_cast<uint32_t*>(dst));
-          else tmem_ld_x16(tw + O_COL + PIECE * pc, reinterpret_cast<uint32_t*>(dst));
-        };
-        tmem_ld_x4(tw + O_COL + HD, reinterpret_cast<uint32_t*>(oz));
-        ld_piece(0, oa);
-        tc_wait_ld();
-        const float inv = 1.f / oz[0];
-#pragma unroll
-        for (int pc = 0; pc < NP; ++pc) {
-          float* cur = (pc & 1) ? ob : oa;
-          if (pc + 1 < NP) ld_piece(pc + 1, (pc & 1) ? oa : ob);
-#pragma unroll
-          for (int q = 0; q < PIECE / 8; ++q) chunk(cur + 8 * q, inv, dst_of((PIECE / 8) * pc + q));
-          if (pc + 1 < NP) tc_wait_ld();
-        }
-        tc_fence_before();
+    // P V of the warpgroup's previous item has completed (ordy: its commit): P may be overwritten, the record's V^T released
+    auto pv_done = [&]() {
+      if (pend) {
+        X3_TRACE(13);
+        wait_bar<false>(b_ordy + 8 * g, n_o & 1, 7);
+        X3_TRACE(14);
+        ++n_o;
+        pend = false;
       }
-      fence_proxy_async();  // O rows -> visible to the TMA store
-      mbar_arrive(b_odone + 8 * pend_s);
-      X3_TRACE(15);
-      pend = false;
     };
 
     // Head records are released in record order: this warpgroup arrives on kvfree[record] once it has no item left
@@ -619,12 +722,11 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     };
     int arr_last = n_rec > 0 ? last_job_of(0) : 0x7fffffff;
     {
+      X3_PH_DECL
       for (int j = g; j < n_jobs; j += NWG) {
-        const int i = j >> LOG_HPT, h = j & (HPT - 1), s = i % NST;
+        const int i = j >> LOG_HPT, s = i % NST;
         if (arr_last < j) {
-          if constexpr (!STATS) {
-            if (pend) drain();
-          }
+          if constexpr (!STATS) pv_done();
           do {
             mbar_arrive(b_kvfree + 8 * (arr_next % NSLOT));
             ++arr_next;
@@ -659,9 +761,11 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           dsq += static_cast<double>((fq[0] + fq[1]) + (fq[2] + fq[3]));
         } else {
           X3_TRACE(10);
+          X3_PH(0);
           wait_bar<false>(b_srdy + 16 * g, n_s & 1, 8);
           ++n_s;
           X3_TRACE(11);
+          X3_PH(1);
           tc_fence_after();
           tmem_ld_x64(tw + S_COL, reinterpret_cast<uint32_t*>(sc));
           tmem_ld_x16(tw + S_COL + 64, reinterpret_cast<uint32_t*>(sc) + 64);
@@ -669,6 +773,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           tc_fence_before();
           mbar_arrive(b_sfree + 16 * g);  // the next item's Q K^T may overwrite S
           X3_TRACE(12);
+          X3_PH(2);
           if (!have_beta) {
             X3_TRACE(17);
             pdl_wait_prior_grid();  // pass 1 (same stream, launched just before) has published the std
@@ -702,10 +807,11 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           for (int c = 16; c < 80; ++c) mr[c & 3] = fmaxf(mr[c & 3], sc[c]);
           const float m = fmaxf(fmaxf(fmaxf(my[0], my[1]), fmaxf(my[2], my[3])), ca * fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])));
           const float nb = -ce * m, k2 = ce * ca;
-          // the previous item's O row leaves TMEM while this warp would wait for its turn anyway (its P V was issued when
-          // the previous item published P: long finished after the S read, W and row max above); that also proves
-          // P(previous) has been consumed, so this item's P may go in
-          if (pend) drain();
+          // P V of the previous item was issued when that item published P: long finished after the S read, W and row max
+          // above; its completion proves P(previous) has been consumed, so this item's P may go in
+          X3_PH(3);
+          pv_done();
+          X3_PH(4);
           if constexpr (C::TURNS > 0) {
             const uint32_t seq = static_cast<uint32_t>(j);
             if (lane == 0) {
@@ -720,6 +826,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
             __syncwarp();
           }
           X3_TRACE(19);
+          X3_PH(5);
           uint32_t pw[40];
 #pragma unroll
           for (int c = 0; c < 39; ++c) {
@@ -738,18 +845,16 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
             __syncwarp();
             if (lane == 0) atomicAdd(const_cast<uint32_t*>(my_turn), 1u);  // one more M phase complete: the next warp in line may start
           }
+          X3_PH(6);
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(b_prdy + 8 * g);
           X3_TRACE(16);
+          X3_PH(7);
           pend = true;
-          pend_s = s;
-          pend_h = h;
         }
       }
-      if constexpr (!STATS) {
-        if (pend) drain();
-      }
+      X3_PH_FLUSH;
     }
     if constexpr (STATS) {
       // CTA partial in a fixed order (warp shuffle tree, then the consumer warps serially) -> workspace; the last CTA folds
@@ -923,7 +1028,7 @@ static cudaError_t launch(XattnParams p, cudaStream_t st) {
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(C::THREADS);
+  cfg.blockDim = dim3(C::threads(STATS));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -983,13 +1088,21 @@ cudaError_t run_stats_x3(const XattnParams& p, int D, int dtype, cudaStream_t st
 cudaError_t run_forward_x3(const XattnParams& p, int D, int dtype, cudaStream_t st) { return X3_DISPATCH(x3::launch_forward, p, st); }
 
 #ifdef DSC_TRACE
-extern "C" int dsc_debug_x3_trace(long long* out /*HOST 2*7*1024*2*/, int* counts /*HOST 2*7*/, unsigned long long* cta /*HOST 2*160*2*/) {
+extern "C" int dsc_debug_x3_trace(long long* out /*HOST 2*8*1024*2*/, int* counts /*HOST 2*8*/, unsigned long long* cta /*HOST 2*160*2*/) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, x3::g_x3_trace, sizeof(long long) * 2 * 7 * 1024 * 2);
-  cudaMemcpyFromSymbol(counts, x3::g_x3_trace_n, sizeof(int) * 14);
+  cudaMemcpyFromSymbol(out, x3::g_x3_trace, sizeof(long long) * 2 * 8 * 1024 * 2);
+  cudaMemcpyFromSymbol(counts, x3::g_x3_trace_n, sizeof(int) * 16);
   cudaMemcpyFromSymbol(cta, x3::g_x3_cta, sizeof(unsigned long long) * 2 * 160 * 2);
-  int z[14] = {0};
+  int z[16] = {0};
   cudaMemcpyToSymbol(x3::g_x3_trace_n, z, sizeof(z));
+  return 0;
+}
+#endif
+
+#ifdef DSC_PHASE
+extern "C" int dsc_debug_x3_phase(unsigned int* out /*HOST 4*12*8*/) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, x3::g_x3_phase, sizeof(unsigned int) * 4 * 12 * 8);
   return 0;
 }
 #endif

@@ -33,11 +33,11 @@ for _ in range(3):
     flush[: flush.numel() // 2].view(torch.int64).sum()
     att.region_attention_prepared(view(q), kv, compact, 7.0)
 torch.cuda.synchronize()
-out = np.zeros((2, 7, 1024, 2), dtype=np.int64)
-cnt = np.zeros((2, 7), dtype=np.int32)
+out = np.zeros((2, 8, 1024, 2), dtype=np.int64)
+cnt = np.zeros((2, 8), dtype=np.int32)
 cta = np.zeros((2, 160, 2), dtype=np.uint64)
 _lib.lib.dsc_debug_x3_trace(out.ctypes.data_as(ctypes.c_void_p), cnt.ctypes.data_as(ctypes.c_void_p), cta.ctypes.data_as(ctypes.c_void_p))
-names = ["consumer wg0", "consumer wg1", "consumer wg2", "producer", "issuer 0", "issuer 1", "issuer 2"]
+names = ["consumer wg0", "consumer wg1", "consumer wg2", "producer", "issuer 0", "issuer 1", "issuer 2", "drain warp 0"]
 for ps, pname in ((0, "pass 1 (stats)"), (1, "pass 2 (forward)")):
     c = cta[ps, :148].astype(np.int64)
     t0 = c[:, 0].min()
@@ -50,8 +50,8 @@ for ps, pname in ((0, "pass 1 (stats)"), (1, "pass 2 (forward)")):
         s1 = cta[0, :148].astype(np.int64)
         print(f"      pass 2 first CTA start - pass 1 first CTA start = {int(t0 - s1[:,0].min())} ns; pass 1 last end - pass 1 first start = {int(s1[:,1].max() - s1[:,0].min())} ns; "
               f"pass 2 last end - pass 1 first start = {int(c[:,1].max() - s1[:,0].min())} ns")
-    base = min(out[ps, w, 0, 1] for w in range(7) if cnt[ps, w] > 0)
-    for w in range(7):
+    base = min(out[ps, w, 0, 1] for w in range(8) if cnt[ps, w] > 0)
+    for w in range(8):
         n = cnt[ps, w]
         print(f"--- {names[w]} ({n} events): tag@cycle(+delta)")
         prev = base
