@@ -74,9 +74,9 @@ struct Cfg {
   // re-divided with setmaxnreg (consumers up, drain / service warps down)
   static constexpr int CONSUMERS = NWG * 128;
   static constexpr int threads(bool stats) { return CONSUMERS + (stats ? 128 : 256); }
-  static constexpr int REGS_CONSUMER = HD == 40 ? 128 : HD == 80 ? 184 : 232;  // x CONSUMERS
+  static constexpr int REGS_CONSUMER = HD == 40 ? 120 : HD == 80 ? 184 : 232;  // x CONSUMERS
   static constexpr int REGS_DRAIN = HD == 40 ? 56 : HD == 80 ? 80 : 96;        // x 128
-  static constexpr int REGS_SERVICE = 40;                                      // x 128
+  static constexpr int REGS_SERVICE = HD == 40 ? 64 : 56;                      // x 128
   static constexpr int REGS_LAUNCH = (65536 / threads(false)) / 8 * 8;         // what __launch_bounds__(threads, 1) grants: 96 / 128 / 168
   static_assert(CONSUMERS * REGS_CONSUMER + 128 * (REGS_DRAIN + REGS_SERVICE) <= threads(false) * REGS_LAUNCH, "register pool");
   static constexpr int KSTEPS = HD == 40 ? 3 : HD / 16, NKC = 2 * KSTEPS;
@@ -185,6 +185,30 @@ __device__ __forceinline__ void wait_bar_u(uint32_t bar, uint32_t parity) {
     if (spins > 64 && clock64() - t0 > (1ll << 32)) __trap();  // ~2 s: unreachable unless the barrier protocol is broken
   }
 }
+// explicit shared-space accesses (32-bit addresses derived from the opaque base: no generic-pointer conversion in the loops)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_shared(uint32_t a, uint32_t x) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
+}
+// x, through a shuffle with the caller's own lane: a value ptxas keeps in a register instead of recomputing it
+__device__ __forceinline__ uint32_t opaque(uint32_t x) {
+  uint32_t lane, y;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(y) : "r"(x), "r"(lane));
+  return y;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
@@ -283,7 +307,11 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   constexpr int RECB = STATS ? K_HEAD : C::REC_BYTES;  // bytes of a record this pass needs (pass 1: its K part) = slot pitch
   constexpr int KV = NSLOT * RECB;
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // thread index and shared-memory base are made opaque (a shuffle with the thread's own lane): left alone, ptxas
+  // re-materialises them (S2R SR_TID.X / SR_CgaCtaId + LEA, long-latency special-register reads) in front of every
+  // barrier operation of the role loops
+  const int tid = opaque(threadIdx.x);
+  const int warp = tid >> 5, lane = tid & 31;
   X3_TRACE_DECL
   X3_CTA_TIME(0);
   X3_TRACE(1);
@@ -300,14 +328,14 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     pdl_launch_dependents();  // a following pass 1 (next call) may be placed early; it waits for our completion itself
   }
   X3_TRACE(3);
-  const uint32_t s0 = smem_u32(smem);
+  const uint32_t s0 = opaque(smem_u32(smem));
   const uint32_t sStage = s0 + KV;
   const uint32_t bars = sStage + NST * STAGE;
   // barrier map (8 B each): full[4] | odone[4] | kvfull[4] | kvfree[4] | srdy[3][2] | sfree[3][2] | prdy[3] | ordy[3] | ofree[3]
   const uint32_t b_full = bars, b_odone = bars + 32, b_kvfull = bars + 64, b_kvfree = bars + 96, b_srdy = bars + 128,
                  b_sfree = bars + 176, b_prdy = bars + 224, b_ordy = bars + 248, b_ofree = bars + 272;
   constexpr int N_BARS = 37;
-  volatile uint32_t* turn_ptr = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 320);
+  const uint32_t turn_addr = bars + 320;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 336);
 
   const int begin = static_cast<int>(p.total * blockIdx.x / gridDim.x);
@@ -391,7 +419,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       mbar_init(bars + 8 * idx, cnt);
     }
     fence_mbar_init();
-    if (lane >= 28) turn_ptr[lane - 28] = 0u;  // whose turn it is on each SM sub-partition (pass 2)
+    if (lane >= 28) asm volatile("st.shared.u32 [%0], %1;" ::"r"(turn_addr + 4 * (lane - 28)), "r"(0u) : "memory");  // whose turn it is on each SM sub-partition (pass 2)
   }
   if (warp == SW0 + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
@@ -597,7 +625,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_DRAIN));
       const int row = (warp & 3) * 32 + lane;
       const uint32_t tl = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + O_COL;
-      auto pack_store = [&](const float* o8, float inv, unsigned char* d) {
+      auto pack_store = [&](const float* o8, float inv, uint32_t d) {
         float t[8];
         fmul2(t[0], t[1], o8[0], o8[1], inv, inv);
         fmul2(t[2], t[3], o8[2], o8[3], inv, inv);
@@ -608,16 +636,16 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
         v.y = Mma<T>::pack(t[2], t[3]);
         v.z = Mma<T>::pack(t[4], t[5]);
         v.w = Mma<T>::pack(t[6], t[7]);
-        *reinterpret_cast<uint4*>(d) = v;
+        sts128(d, v);
       };
       int g = 0, k = 0;  // item J = NWG * k + g
       for (int J = 0; J < n_jobs; ++J) {
         const int i = J >> LOG_HPT, h = J & (HPT - 1), s = i % NST;
         const uint32_t tw = tl + g * WG_COLS;
-        unsigned char* st = smem + KV + s * STAGE;
+        const uint32_t st = sStage + s * STAGE;
         // 16-byte chunk c of the head's O row = global chunk G = (HD/8) h + c of the 160-column tile row: the place its Q
         // columns had (swizzled: 8 consecutive rows hit 8 distinct bank groups)
-        auto dst_of = [&](int c) -> unsigned char* {
+        auto dst_of = [&](int c) -> uint32_t {
           const int G = h * C::CPH + c;
           return G < 16 ? st + (G >> 3) * BOX128_BYTES + row * 128 + (((G & 7) ^ (row & 7)) << 4)
                         : st + 2 * BOX128_BYTES + row * 64 + ((((G - 16) & 3) ^ ((row >> 1) & 3)) << 4);
@@ -698,7 +726,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     // lock-step -- they share the MUFU pipe fairly, so they finish their M phases together and then all do their MUFU-free
     // work (S row out of TMEM, W, row max, barriers) while the pipe idles.  With turns, one or two warps exponentiate at
     // the full pipe rate while the others do their MUFU-free part.
-    volatile uint32_t* my_turn = turn_ptr + (warp & 3);
+    const uint32_t my_turn = turn_addr + 4 * (warp & 3);
 
     // P V of the warpgroup's previous item has completed (ordy: its commit): P may be overwritten, the record's V^T released
     auto pv_done = [&]() {
@@ -786,10 +814,10 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
             ce = bpos ? beta_l2 : 1.f;
           }
           wait_bar<false>(b_full + 8 * s, (i / NST) & 1, 9);  // (long complete: the Q K^T needed the stage)
-          const float4* wt4 = reinterpret_cast<const float4*>(smem + KV + s * STAGE + QT_BYTES + row * (DSC_COMPACT_PITCH * 4));
+          const uint32_t wt4 = sStage + s * STAGE + QT_BYTES + row * (DSC_COMPACT_PITCH * 4);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            float4 w = wt4[c];
+            float4 w = lds128(wt4 + 16 * c);
             if (!bpos) {
               fmul2(w.x, w.y, w.x, w.y, cbw, cbw);
               fmul2(w.z, w.w, w.z, w.w, cbw, cbw);
@@ -817,7 +845,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
             if (lane == 0) {
               long long t0 = 0;
               uint32_t spins = 0;
-              while (static_cast<int>(seq - *my_turn) >= C::TURNS) {  // at most TURNS items ahead of the oldest unfinished one
+              while (static_cast<int>(seq - lds32_volatile(my_turn)) >= C::TURNS) {  // at most TURNS items ahead of the oldest unfinished one
                 __nanosleep(20);
                 if (++spins == 256) t0 = clock64();
                 if (spins > 256 && clock64() - t0 > (1ll << 32)) __trap();
@@ -843,7 +871,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           tmem_st_x16(tw + P_COL + 24, pw + 24);  // (volatile, reads pw[24..39]: every exponential above precedes it)
           if constexpr (C::TURNS > 0) {
             __syncwarp();
-            if (lane == 0) atomicAdd(const_cast<uint32_t*>(my_turn), 1u);  // one more M phase complete: the next warp in line may start
+            if (lane == 0) red_add_shared(my_turn, 1u);  // one more M phase complete: the next warp in line may start
           }
           X3_PH(6);
           tc_wait_st();
