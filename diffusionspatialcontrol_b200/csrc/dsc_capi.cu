@@ -123,7 +123,7 @@ static void fill_partition(XattnParams& p, int B, int H, int L, int D, int S) {
 // Long prompts (S > DSC_MAX_KEYS; the reference concatenates 77-token windows, prompt_parser.py:161-194): the keys are
 // processed as chunks of <= 80.  The workspace then also holds the per-chunk outputs and log-sum-exps.
 static int n_chunks(int S) { return (S + DSC_MAX_KEYS - 1) / DSC_MAX_KEYS; }
-static size_t stats_bytes() { return static_cast<size_t>(kWorkspaceHeader) + sizeof(double) * 2 * kMaxPartials; }
+static size_t stats_bytes() { return static_cast<size_t>(kHandoffOffset) + sizeof(double) * 2 * kMaxPartials; }  // header | partials | handoff slots
 static size_t chunk_out_bytes(int B, int H, int L, int D) { return static_cast<size_t>(B) * L * H * D * 2; }
 static size_t chunk_lse_bytes(int B, int H, int L) { return (static_cast<size_t>(B) * H * L * 4 + 15) / 16 * 16; }
 
@@ -403,6 +403,7 @@ int dsc_xattn_call_prepared(const void* q, const int64_t q_str[4], const void* k
   p.scale = scale;
   p.kv_image = kv_image;
   p.ws = static_cast<Workspace*>(workspace);
+  p.handoff = passes == (DSC_PASS_STATS | DSC_PASS_FORWARD) ? 1 : 0;  // one call: pass 2 folds pass 1's partials itself
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
   if (passes & DSC_PASS_STATS) {

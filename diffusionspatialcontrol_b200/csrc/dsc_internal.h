@@ -11,6 +11,11 @@ namespace dsc {
 using Workspace = dsc_xattn_stats_t;
 constexpr int kWorkspaceHeader = 64;
 constexpr int kMaxPartials = 1024;
+// Behind the per-CTA partials: the HANDOFF slots of the prepared-K/V call (xattn_x3.cu), kMaxPartials x {sum, sum of squares} as
+// fp64 bit patterns with bit 0 forced to 1 (0 = "not published yet"; the buffer starts zeroed and the call leaves it zeroed),
+// and in the header, behind the public fields, the count of pass-2 CTAs that have consumed them.
+constexpr int kHandoffOffset = kWorkspaceHeader + 16 * kMaxPartials;
+constexpr int kReadersOffset = 56;
 static_assert(sizeof(Workspace) <= kWorkspaceHeader, "workspace header");
 
 struct XattnParams {
@@ -47,6 +52,7 @@ struct XattnParams {
   int active_cols[16];  // ascending key indices of the compact columns
   unsigned flags;       // 4-warpgroup tcgen05 kernel: launcher-set mode bits (see launch_tc5x4)
   const void* kv_image;  // 3-warpgroup tcgen05 kernels: prepared K / V^T images (dsc_xattn_prepare_kv), one per (batch, head group)
+  int handoff;           // 3-warpgroup tcgen05 kernels, both passes of one call: the std goes from pass 1 to pass 2 through the handoff slots
 };
 
 // Kernel-selection overrides (A/B runs, tests).  Filled ONCE from the environment when the library is loaded

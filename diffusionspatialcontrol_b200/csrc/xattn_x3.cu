@@ -333,8 +333,9 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   const uint32_t bars = sStage + NST * STAGE;
   // barrier map (8 B each): full[4] | odone[4] | kvfull[4] | kvfree[4] | srdy[3][2] | sfree[3][2] | prdy[3] | ordy[3] | ofree[3]
   const uint32_t b_full = bars, b_odone = bars + 32, b_kvfull = bars + 64, b_kvfree = bars + 96, b_srdy = bars + 128,
-                 b_sfree = bars + 176, b_prdy = bars + 224, b_ordy = bars + 248, b_ofree = bars + 272;
-  constexpr int N_BARS = 37;
+                 b_sfree = bars + 176, b_prdy = bars + 224, b_ordy = bars + 248, b_ofree = bars + 272, b_std = bars + 296;
+  constexpr int N_BARS = 38;  // ... | std[1] (pass 2, handoff: the folding warp has put the std at std_addr)
+  const uint32_t std_addr = bars + 344;
   const uint32_t turn_addr = bars + 320;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 336);
 
@@ -415,7 +416,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
       if (idx >= 8 && idx < 12) continue;  // kvfull[]: the producer's
       // odone[]: 128 rows of every head of the tile | kvfree[]: every consumer | srdy, ordy: one commit | sfree, prdy: a warpgroup |
       // ofree[]: the drain warpgroup
-      const uint32_t cnt = idx < 8 ? HPT * 128u : idx < 16 ? static_cast<uint32_t>(CONSUMERS) : idx < 22 ? 1u : idx < 31 ? 128u : idx < 34 ? 1u : 128u;
+      const uint32_t cnt = idx < 8 ? HPT * 128u : idx < 16 ? static_cast<uint32_t>(CONSUMERS) : idx < 22 ? 1u : idx < 31 ? 128u : idx < 34 ? 1u : idx < 37 ? 128u : 1u;
       mbar_init(bars + 8 * idx, cnt);
     }
     fence_mbar_init();
@@ -614,6 +615,10 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
         }
       }
     }
+    if constexpr (!STATS) {
+      // formal ordering: pass 2 complete => pass 1 complete (it is, long ago: returns at once)
+      if (warp == SW0 && p.handoff) pdl_wait_prior_grid();
+    }
     __syncwarp();
   } else if (!STATS && warp >= DW0) {
     // ============================== drain warpgroup (pass 2): O rows out of TMEM ====================
@@ -623,6 +628,66 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     // stage, stage handed back to the producer (odone).  The consumer warps never touch O: their loop is S -> softmax -> P.
     if constexpr (!STATS) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_DRAIN));
+      if (warp == DW0 && p.handoff) {
+        // ------------------------------ first: drain warp 0 folds pass 1's partials (one call) -------
+        // pass 1's CTAs publish {sum, sum of squares} into the handoff slots; this warp polls them (volatile loads: L2),
+        // folds them in the fixed order of finalize_stats and hands the std to the consumers -- no ticket, no fold in pass 1's
+        // last CTA, no wait for pass 1's completion and the memory flush behind it (griddepcontrol.wait).  Every CTA folds
+        // the same values in the same order: bit-identical std everywhere.  The CTA that reads last zeroes the slots again
+        // and fills the public statistics header.
+        const volatile unsigned long long* slots =
+            reinterpret_cast<const volatile unsigned long long*>(reinterpret_cast<const unsigned char*>(p.ws) + kHandoffOffset);
+        const unsigned int n_part = gridDim.x;  // pass 1 runs the same grid (launch())
+        double sa, sb;
+        long long t0 = 0;
+        uint32_t spins = 0;
+        while (true) {
+          bool ok = true;
+          sa = 0.0;
+          sb = 0.0;
+          for (unsigned int c = lane; c < n_part; c += 32) {
+            const unsigned long long va = slots[2 * c], vb = slots[2 * c + 1];
+            ok = ok && va != 0ull && vb != 0ull;
+            sa += __longlong_as_double(static_cast<long long>(va));
+            sb += __longlong_as_double(static_cast<long long>(vb));
+          }
+          if (__all_sync(0xffffffffu, ok)) break;
+          __nanosleep(100);
+          if (++spins == 4096) t0 = clock64();
+          if (spins > 4096 && (spins & 255) == 0 && clock64() - t0 > (1ll << 33)) __trap();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sa += __shfl_xor_sync(0xffffffffu, sa, o);
+          sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        const double scl = static_cast<double>(p.scale);
+        const double n = static_cast<double>(p.B) * p.H * static_cast<double>(p.L) * p.S;
+        const double sum = sa * scl, sumsq = sb * scl * scl, mean = sum / n;
+        double var = (n > 1.0) ? (sumsq - sum * mean) / (n - 1.0) : nan("");
+        if (var < 0.0) var = 0.0;
+        const float std_f = static_cast<float>(sqrt(var));
+        if (lane == 0) {
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(std_addr), "r"(__float_as_uint(std_f)) : "memory");
+          mbar_arrive(b_std);  // (release: the store above is visible to the waiting consumers)
+        }
+        unsigned int last = 0;
+        if (lane == 0) last = atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(p.ws) + kReadersOffset), 1u) == gridDim.x - 1 ? 1u : 0u;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {  // every CTA has read the slots: leave them empty for the next call, publish the statistics
+          unsigned long long* w = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(p.ws) + kHandoffOffset);
+          for (unsigned int c = lane; c < 2 * n_part; c += 32) w[c] = 0ull;
+          if (lane == 0) {
+            p.ws->std_unbiased = std_f;
+            p.ws->mean = static_cast<float>(mean);
+            p.ws->sum = sum;
+            p.ws->sumsq = sumsq;
+            p.ws->n = n;
+            p.ws->n_partials = n_part;
+            *reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(p.ws) + kReadersOffset) = 0u;
+          }
+        }
+      }
       const int row = (warp & 3) * 32 + lane;
       const uint32_t tl = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + O_COL;
       auto pack_store = [&](const float* o8, float inv, uint32_t d) {
@@ -804,9 +869,16 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           X3_PH(2);
           if (!have_beta) {
             X3_TRACE(17);
-            pdl_wait_prior_grid();  // pass 1 (same stream, launched just before) has published the std
+            float std_v;
+            if (p.handoff) {  // the folding warp of this CTA has summed pass 1's per-CTA partials
+              wait_bar<false>(b_std, 0, 11);
+              std_v = __uint_as_float(lds32_volatile(std_addr));
+            } else {
+              pdl_wait_prior_grid();  // pass 1 (same stream, launched just before) has published the std
+              std_v = __ldcg(&p.ws->std_unbiased);
+            }
             X3_TRACE(18);
-            beta_l2 = sigma_v * __ldcg(&p.ws->std_unbiased) * kLog2e;
+            beta_l2 = sigma_v * std_v * kLog2e;
             have_beta = true;
             bpos = beta_l2 > 1e-20f;
             ca = bpos ? scale_l2 / beta_l2 : scale_l2;
@@ -907,10 +979,18 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
             a += red[w];
             b += red[4 * NWG + w];
           }
-          partials[2 * blockIdx.x] = a;
-          partials[2 * blockIdx.x + 1] = b;
-          __threadfence();
-          last = atomicAdd(&p.ws->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+          if (p.handoff) {
+            // the value IS the message: two 8-byte stores (atomic each), bit 0 set so that a published value is never the
+            // all-zero "empty" pattern (1 ulp of fp64); no fence, no ticket -- pass 2 polls the slots and folds them
+            unsigned long long* slots = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(p.ws) + kHandoffOffset);
+            __stcg(slots + 2 * blockIdx.x, static_cast<unsigned long long>(__double_as_longlong(a)) | 1ull);
+            __stcg(slots + 2 * blockIdx.x + 1, static_cast<unsigned long long>(__double_as_longlong(b)) | 1ull);
+          } else {
+            partials[2 * blockIdx.x] = a;
+            partials[2 * blockIdx.x + 1] = b;
+            __threadfence();
+            last = atomicAdd(&p.ws->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+          }
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {

@@ -62,7 +62,8 @@ int dsc_sm_count(void);
 
 /* Bytes of device workspace one attention call needs (stats + per-CTA partials + ticket; for
  * S > DSC_MAX_KEYS also the per-key-chunk outputs and log-sum-exps that dsc_xattn_forward merges).
- * The first 64 + 16384 bytes must be zero-filled ONCE after allocation; calls leave it reusable. */
+ * The first 64 + 2 * 16384 bytes (header | per-CTA partials | handoff slots of dsc_xattn_call_prepared) must be zero-filled
+ * ONCE after allocation; calls leave it reusable.  A workspace serves one call at a time (one stream). */
 int dsc_xattn_workspace_bytes(int B, int H, int L, int D, int S, size_t* out /*HOST*/);
 
 /* Pass 1.  a = scale * Q K^T over the whole call; writes to `workspace`
