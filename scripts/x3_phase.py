@@ -13,7 +13,7 @@ from diffusionspatialcontrol_b200 import _lib, attention as att  # noqa: E402
 
 B, L = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (16, 4096)
 D = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-H, S = 320 // D, 77
+H, S = 8, 77
 dev = torch.device("cuda")
 q = torch.randn(B, L, H * D, device=dev).half()
 k = torch.randn(B, S, H * D, device=dev).half()
