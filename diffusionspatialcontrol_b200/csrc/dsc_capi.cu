@@ -409,8 +409,6 @@ int dsc_xattn_call_prepared(const void* q, const int64_t q_str[4], const void* k
   if (passes & DSC_PASS_STATS) {
     if (stats_grid(static_cast<long long>(B) * (H * D / 160) * ((L + 127) / 128)) > kMaxPartials)
       return fail(DSC_ERR_UNSUPPORTED, "grid exceeds the workspace's partial slots");
-    e = run_stats_x3(p, D, dtype, st);
-    if (e != cudaSuccess) return cuda_fail(e, "dsc_xattn_call_prepared (pass 1)");
   }
   if (passes & DSC_PASS_FORWARD) {
     if (!Wc || !aligned16(Wc) || !out || !o_str) return fail(DSC_ERR_INVALID_ARGUMENT, "pass 2 needs Wc (16-byte aligned) and out");
@@ -426,6 +424,20 @@ int dsc_xattn_call_prepared(const void* q, const int64_t q_str[4], const void* k
     p.Bw = Bw;
     p.sigma_dev = sigma_dev_or_null;
     p.sigma_host = sigma_host;
+  }
+  if (p.handoff && !config().no_fused) {
+    // one call: both passes in ONE cooperative launch; if the device cannot hold the grid (it is sized to the SM count: only
+    // when another context occupies SMs), fall back to pass 1 + pass 2 as two launches
+    e = run_fused_x3(p, D, dtype, st);
+    if (e == cudaSuccess) return DSC_OK;
+    if (e != cudaErrorCooperativeLaunchTooLarge) return cuda_fail(e, "dsc_xattn_call_prepared (single launch)");
+    (void)cudaGetLastError();
+  }
+  if (passes & DSC_PASS_STATS) {
+    e = run_stats_x3(p, D, dtype, st);
+    if (e != cudaSuccess) return cuda_fail(e, "dsc_xattn_call_prepared (pass 1)");
+  }
+  if (passes & DSC_PASS_FORWARD) {
     e = run_forward_x3(p, D, dtype, st);
     if (e != cudaSuccess) return cuda_fail(e, "dsc_xattn_call_prepared (pass 2)");
   }

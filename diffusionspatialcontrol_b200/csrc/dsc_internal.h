@@ -18,6 +18,28 @@ constexpr int kHandoffOffset = kWorkspaceHeader + 16 * kMaxPartials;
 constexpr int kReadersOffset = 56;
 static_assert(sizeof(Workspace) <= kWorkspaceHeader, "workspace header");
 
+// Division by a launch-invariant divisor without the ~100-cycle integer-division sequence (role prologues, tile decode):
+// q = x / d for every 32-bit x.  d >= 1.  (round-up magic number, 33-bit form: umulhi + shift-add)
+struct FastDiv {
+  uint32_t m, l, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{0u, 0u, d};
+  if (d <= 1u) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;  // ceil(log2 d)
+  f.l = l;
+  f.m = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1ull);
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fastdiv(uint32_t x, const FastDiv& f) {
+  if (f.d <= 1u) return x;
+  const uint32_t q = __umulhi(x, f.m);
+  return (((x - q) >> 1) + q) >> (f.l - 1u);
+}
+#endif
+
 struct XattnParams {
   const void* q;
   const void* k;
@@ -52,6 +74,10 @@ struct XattnParams {
   int active_cols[16];  // ascending key indices of the compact columns
   unsigned flags;       // 4-warpgroup tcgen05 kernel: launcher-set mode bits (see launch_tc5x4)
   const void* kv_image;  // 3-warpgroup tcgen05 kernels: prepared K / V^T images (dsc_xattn_prepare_kv), one per (batch, head group)
+  // 3-warpgroup tcgen05 kernels: tile ranges and tile decode without divisions (set by the launcher): CTA b owns tiles
+  // [b * tiles_q + min(b, tiles_r), +tiles_q + (b < tiles_r))
+  uint32_t tiles_q, tiles_r;
+  FastDiv div_nsl, div_nhg;
   int handoff;           // 3-warpgroup tcgen05 kernels, both passes of one call: the std goes from pass 1 to pass 2 through the handoff slots
 };
 
@@ -100,6 +126,7 @@ cudaError_t run_prepare_kv_x3(const void* k, const void* v, long long k_sb, long
                               int H, int D, int S, int n_active, const int* cols, int dtype, void* image, cudaStream_t st);
 cudaError_t run_stats_x3(const XattnParams& p, int D, int dtype, cudaStream_t st);
 cudaError_t run_forward_x3(const XattnParams& p, int D, int dtype, cudaStream_t st);
+cudaError_t run_fused_x3(const XattnParams& p, int D, int dtype, cudaStream_t st);  // both passes, one cooperative launch
 
 cudaError_t run_region_downsample(const uint8_t* maps, int R, int Hpx, int Wpx, int w_r, int h_r, uint8_t* ds,
                                   uint32_t* any_set, cudaStream_t st);

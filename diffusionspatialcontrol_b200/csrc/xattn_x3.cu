@@ -108,9 +108,9 @@ struct Tile {
 };
 __device__ __forceinline__ Tile decode(int idx, const XattnParams& p) {
   Tile t;
-  const int seg = idx / p.n_sl;
+  const int seg = static_cast<int>(fastdiv(static_cast<uint32_t>(idx), p.div_nsl));
   t.tile = idx - seg * p.n_sl;
-  t.b = seg / p.n_hg;
+  t.b = static_cast<int>(fastdiv(static_cast<uint32_t>(seg), p.div_nhg));
   t.hg = seg - t.b * p.n_hg;
   t.l0 = t.tile * ROWS;
   return t;
@@ -257,7 +257,7 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 }
 #define X3_TRACE_DECL                                                                                   \
   int tr_n = 0;                                                                                         \
-  const int tr_c = Cfg<HD>::CONSUMERS, tr_s = tr_c + (STATS ? 0 : 128);                                 \
+  const int tr_c = Cfg<HD>::CONSUMERS, tr_s = tr_c + ((STATS && !FUSED) ? 0 : 128);                                 \
   const int tr_k = blockIdx.x != 0 ? -1                                                                 \
                    : (threadIdx.x & 127) == 0 && (int)threadIdx.x < tr_c ? (int)(threadIdx.x >> 7)      \
                    : (int)threadIdx.x == tr_s ? 3                                                       \
@@ -292,16 +292,19 @@ __device__ unsigned int g_x3_phase[4][12][8];
 #define X3_PH_FLUSH do {} while (0)
 #endif
 
-template <typename T, int HD, bool STATS>
-__global__ void __launch_bounds__(Cfg<HD>::threads(STATS), 1)
-xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, const __grid_constant__ CUtensorMap tm_qb,
-                const __grid_constant__ CUtensorMap tm_qp, const __grid_constant__ CUtensorMap tm_oa,
-                const __grid_constant__ CUtensorMap tm_ob) {
+// One pass over the CTA's tile range.  FUSED: both passes run in ONE (cooperative) launch, x3_phase<STATS> then
+// x3_phase<!STATS> with the pass-2 thread layout (the drain warpgroup idles through pass 1), TMEM allocated once (returned by
+// pass 1, handed to pass 2), pass 1's barriers invalidated before pass 2 lays out its own; the std goes through the handoff
+// slots.  Returns the TMEM base address.
+template <typename T, int HD, bool STATS, bool FUSED>
+__device__ __forceinline__ uint32_t x3_phase(const XattnParams& p, const CUtensorMap& tm_qa, const CUtensorMap& tm_qb,
+                                             const CUtensorMap& tm_qp, const CUtensorMap& tm_oa, const CUtensorMap& tm_ob,
+                                             uint32_t tmem_in) {
   using C = Cfg<HD>;
   constexpr int D = C::D, HPT = C::HPT, LOG_HPT = C::LOG_HPT, NWG = C::NWG, CONSUMERS = C::CONSUMERS, WG_COLS = C::WG_COLS;
   constexpr int K_HEAD = C::K_HEAD, VT_CH = C::VT_CH, IMG_BYTES = C::IMG_BYTES, NSLOT = C::NSLOT;
   constexpr int DW0 = 4 * NWG;                    // pass 2: first warp of the drain warpgroup
-  constexpr int SW0 = STATS ? 4 * NWG : 4 * NWG + 4;  // first service warp
+  constexpr int SW0 = (STATS && !FUSED) ? 4 * NWG : 4 * NWG + 4;  // first service warp
   constexpr int NST = STATS ? STATS_NST : C::FWD_NST;
   constexpr int STAGE = STATS ? STATS_STAGE : FWD_STAGE;
   constexpr int RECB = STATS ? K_HEAD : C::REC_BYTES;  // bytes of a record this pass needs (pass 1: its K part) = slot pitch
@@ -324,7 +327,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     // before that kernel has completed; pass 2 may be placed as SMs free up
     pdl_wait_prior_grid();
     pdl_launch_dependents();
-  } else {
+  } else if constexpr (!FUSED) {
     pdl_launch_dependents();  // a following pass 1 (next call) may be placed early; it waits for our completion itself
   }
   X3_TRACE(3);
@@ -339,11 +342,11 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   const uint32_t turn_addr = bars + 320;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 336);
 
-  const int begin = static_cast<int>(p.total * blockIdx.x / gridDim.x);
-  const int n_items = static_cast<int>(p.total * (blockIdx.x + 1) / gridDim.x) - begin;
+  const int begin = static_cast<int>(blockIdx.x * p.tiles_q + min(blockIdx.x, p.tiles_r));
+  const int n_items = static_cast<int>(p.tiles_q + (blockIdx.x < p.tiles_r ? 1u : 0u));
   // the CTA's tiles span the (batch, head group) segments seg0 .. seg0 + n_runs - 1 ("runs"); records = n_runs * HPT
-  const int seg0 = begin / p.n_sl;
-  const int n_rec = n_items > 0 ? ((begin + n_items - 1) / p.n_sl - seg0 + 1) * HPT : 0;
+  const int seg0 = static_cast<int>(fastdiv(static_cast<uint32_t>(begin), p.div_nsl));
+  const int n_rec = n_items > 0 ? (static_cast<int>(fastdiv(static_cast<uint32_t>(begin + n_items - 1), p.div_nsl)) - seg0 + 1) * HPT : 0;
   const uint64_t pol_q = STATS ? policy_evict_last() : policy_evict_first();  // pass 2 reads Q again: keep it in L2
   const unsigned char* img = reinterpret_cast<const unsigned char*>(p.kv_image);
 
@@ -422,7 +425,8 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     fence_mbar_init();
     if (lane >= 28) asm volatile("st.shared.u32 [%0], %1;" ::"r"(turn_addr + 4 * (lane - 28)), "r"(0u) : "memory");  // whose turn it is on each SM sub-partition (pass 2)
   }
-  if (warp == SW0 + 1) {
+  constexpr bool kAllocTmem = STATS || !FUSED;  // fused pass 2 inherits pass 1's allocation
+  if (kAllocTmem && warp == SW0 + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
                      smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)))
                  : "memory");
@@ -432,7 +436,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = kAllocTmem ? *tmem_ptr_smem : tmem_in;
   X3_TRACE(2);
 
   const int n_jobs = n_items * HPT;  // (tile, head) work items of this CTA, in order; item J -> warpgroup J % NWG
@@ -617,9 +621,11 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     }
     if constexpr (!STATS) {
       // formal ordering: pass 2 complete => pass 1 complete (it is, long ago: returns at once)
-      if (warp == SW0 && p.handoff) pdl_wait_prior_grid();
+      if (!FUSED && warp == SW0 && p.handoff) pdl_wait_prior_grid();
     }
     __syncwarp();
+  } else if (STATS && warp >= DW0) {
+    // (fused launch, pass 1: the drain warpgroup has nothing to do)
   } else if (!STATS && warp >= DW0) {
     // ============================== drain warpgroup (pass 2): O rows out of TMEM ====================
     // Warp d serves TMEM lanes 32d .. 32d+31 (tile rows) of every consumer warpgroup.  Items in CTA order: wait for P V(J)
@@ -628,7 +634,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
     // stage, stage handed back to the producer (odone).  The consumer warps never touch O: their loop is S -> softmax -> P.
     if constexpr (!STATS) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_DRAIN));
-      if (warp == DW0 && p.handoff) {
+      if (warp == DW0 && (FUSED || p.handoff)) {
         // ------------------------------ first: drain warp 0 folds pass 1's partials (one call) -------
         // pass 1's CTAs publish {sum, sum of squares} into the handoff slots; this warp polls them (volatile loads: L2),
         // folds them in the fixed order of finalize_stats and hands the std to the consumers -- no ticket, no fold in pass 1's
@@ -870,7 +876,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
           if (!have_beta) {
             X3_TRACE(17);
             float std_v;
-            if (p.handoff) {  // the folding warp of this CTA has summed pass 1's per-CTA partials
+            if (FUSED || p.handoff) {  // the folding warp of this CTA has summed pass 1's per-CTA partials
               wait_bar<false>(b_std, 0, 11);
               std_v = __uint_as_float(lds32_volatile(std_addr));
             } else {
@@ -979,7 +985,7 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
             a += red[w];
             b += red[4 * NWG + w];
           }
-          if (p.handoff) {
+          if (FUSED || p.handoff) {
             // the value IS the message: two 8-byte stores (atomic each), bit 0 set so that a published value is never the
             // all-zero "empty" pattern (1 ulp of fp64); no fence, no ticket -- pass 2 polls the slots and folds them
             unsigned long long* slots = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(p.ws) + kHandoffOffset);
@@ -1006,9 +1012,38 @@ xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, 
   __syncthreads();
   tc_fence_after();
   X3_CTA_TIME(1);
-  if (warp == SW0 + 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  if constexpr (FUSED && STATS) {
+    // pass 2 re-uses this shared memory with another layout: the barrier objects must be invalidated before their bytes
+    // become tile data (pass 2 writes there only after its own CTA-wide barrier, i.e. after this warp is done)
+    if (warp == SW0 + 2) {
+      for (int idx = lane; idx < N_BARS; idx += 32) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + 8 * idx) : "memory");
+    }
+  } else {
+    if (warp == SW0 + 1) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
   }
+  return tmem_base;
+}
+
+template <typename T, int HD, bool STATS>
+__global__ void __launch_bounds__(Cfg<HD>::threads(STATS), 1)
+xattn_x3_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, const __grid_constant__ CUtensorMap tm_qb,
+                const __grid_constant__ CUtensorMap tm_qp, const __grid_constant__ CUtensorMap tm_oa,
+                const __grid_constant__ CUtensorMap tm_ob) {
+  x3_phase<T, HD, STATS, false>(p, tm_qa, tm_qb, tm_qp, tm_oa, tm_ob, 0u);
+}
+
+// Both passes of one call in ONE cooperative launch (every CTA resident: pass 2 polls the handoff slots that all pass-1 phases
+// fill): no second launch, no second prologue (TMEM allocation, descriptor fetches), pass 2's first loads leave the moment
+// the CTA's own pass 1 is done while the other CTAs are still streaming.
+template <typename T, int HD>
+__global__ void __launch_bounds__(Cfg<HD>::threads(false), 1)
+xattn_x3_fused_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_qa, const __grid_constant__ CUtensorMap tm_qb,
+                      const __grid_constant__ CUtensorMap tm_qp, const __grid_constant__ CUtensorMap tm_oa,
+                      const __grid_constant__ CUtensorMap tm_ob) {
+  const uint32_t tmem = x3_phase<T, HD, true, true>(p, tm_qa, tm_qb, tm_qp, tm_qa, tm_qb, 0u);
+  x3_phase<T, HD, false, true>(p, tm_qa, tm_qb, tm_qp, tm_oa, tm_ob, tmem);
 }
 
 // ---- K / V^T image ------------------------------------------------------------------------------
@@ -1134,6 +1169,10 @@ static cudaError_t launch(XattnParams p, cudaStream_t st) {
   if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
   const int sms = sm_count_cached();
   const int grid = static_cast<int>(p.total < sms ? p.total : sms);
+  p.tiles_q = static_cast<uint32_t>(p.total / grid);
+  p.tiles_r = static_cast<uint32_t>(p.total % grid);
+  p.div_nsl = make_fastdiv(static_cast<uint32_t>(p.n_sl));
+  p.div_nhg = make_fastdiv(static_cast<uint32_t>(p.n_hg));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(C::threads(STATS));
@@ -1145,6 +1184,55 @@ static cudaError_t launch(XattnParams p, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = config().no_pdl ? 0 : 1;  // pass 2 may overlap the tail of pass 1 (and pass 1 its predecessor's)
   return cudaLaunchKernelEx(&cfg, xattn_x3_kernel<T, HD, STATS>, p, tm_qa, tm_qb, tm_qp, tm_oa, tm_ob);
+}
+
+template <typename T, int HD>
+static cudaError_t launch_fused(XattnParams p, cudaStream_t st) {
+  using C = Cfg<HD>;
+  constexpr int smem = C::FWD_SMEM > C::STATS_SMEM ? C::FWD_SMEM : C::STATS_SMEM;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_x3_fused_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  CUtensorMap tm_qa, tm_qb, tm_qp, tm_oa, tm_ob;
+  if (!make_map_sw(&tm_qa, p.q, p.H * HD, p.L, p.B, p.q_sl, p.q_sb, 64)) return cudaErrorInvalidValue;
+  if (!make_map_sw(&tm_qb, p.q, p.H * HD, p.L, p.B, p.q_sl, p.q_sb, 32)) return cudaErrorInvalidValue;
+  if (!make_map_plain(&tm_qp, p.q, p.H * HD, p.L, p.B, p.q_sl, p.q_sb, GW)) return cudaErrorInvalidValue;  // L2 prefetch only
+  if (!make_map_sw(&tm_oa, p.out, p.H * HD, p.L, p.B, p.o_sl, p.o_sb, 64)) return cudaErrorInvalidValue;
+  if (!make_map_sw(&tm_ob, p.out, p.H * HD, p.L, p.B, p.o_sl, p.o_sb, 32)) return cudaErrorInvalidValue;
+  p.n_hg = p.H / C::HPT;
+  p.n_sl = (p.L + ROWS - 1) / ROWS;
+  p.total = static_cast<long long>(p.B) * p.n_hg * p.n_sl;
+  if (p.total >= (1ll << 31)) return cudaErrorInvalidValue;
+  const int sms = sm_count_cached();
+  const int grid = static_cast<int>(p.total < sms ? p.total : sms);
+  p.tiles_q = static_cast<uint32_t>(p.total / grid);
+  p.tiles_r = static_cast<uint32_t>(p.total % grid);
+  p.div_nsl = make_fastdiv(static_cast<uint32_t>(p.n_sl));
+  p.div_nhg = make_fastdiv(static_cast<uint32_t>(p.n_hg));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(C::threads(false));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;  // pass 2 waits for values every pass-1 phase publishes: all CTAs resident
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = config().no_pdl ? 1 : 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, xattn_x3_fused_kernel<T, HD>, p, tm_qa, tm_qb, tm_qp, tm_oa, tm_ob);
+  if (e != cudaSuccess && cfg.numAttrs == 2) {  // a driver that refuses the combination: cooperative only
+    (void)cudaGetLastError();
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, xattn_x3_fused_kernel<T, HD>, p, tm_qa, tm_qb, tm_qp, tm_oa, tm_ob);
+  }
+  return e;
 }
 
 template <typename T, int HD>
@@ -1193,6 +1281,7 @@ static cudaError_t launch_forward(const XattnParams& p, cudaStream_t st) { retur
 }  // namespace x3
 
 cudaError_t run_stats_x3(const XattnParams& p, int D, int dtype, cudaStream_t st) { return X3_DISPATCH(x3::launch_stats, p, st); }
+cudaError_t run_fused_x3(const XattnParams& p, int D, int dtype, cudaStream_t st) { return X3_DISPATCH(x3::launch_fused, p, st); }
 cudaError_t run_forward_x3(const XattnParams& p, int D, int dtype, cudaStream_t st) { return X3_DISPATCH(x3::launch_forward, p, st); }
 
 #ifdef DSC_TRACE
