@@ -45,6 +45,10 @@ namespace dsc {
 #define X3_L2_PREFETCH 1  // tile i + NST is pulled towards L2 when tile i is loaded
 #endif
 
+#ifndef X3_POLY
+#define X3_POLY 0  // pass 2: every X3_POLY-th pair of exponentials on the FMA / ALU pipes (0 = all on the MUFU pipe; measured slower: see DESIGN.md)
+#endif
+
 namespace x3 {
 constexpr int X3_TURNS_DEFAULT = X3_TURNS;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -74,9 +78,9 @@ struct Cfg {
   // re-divided with setmaxnreg (consumers up, drain / service warps down)
   static constexpr int CONSUMERS = NWG * 128;
   static constexpr int threads(bool stats) { return CONSUMERS + (stats ? 128 : 256); }
-  static constexpr int REGS_CONSUMER = HD == 40 ? 120 : HD == 80 ? 184 : 232;  // x CONSUMERS
+  static constexpr int REGS_CONSUMER = HD == 40 ? 128 : HD == 80 ? 184 : 232;  // x CONSUMERS
   static constexpr int REGS_DRAIN = HD == 40 ? 56 : HD == 80 ? 80 : 96;        // x 128
-  static constexpr int REGS_SERVICE = HD == 40 ? 64 : 56;                      // x 128
+  static constexpr int REGS_SERVICE = HD == 40 ? 40 : 56;                      // x 128
   static constexpr int REGS_LAUNCH = (65536 / threads(false)) / 8 * 8;         // what __launch_bounds__(threads, 1) grants: 96 / 128 / 168
   static_assert(CONSUMERS * REGS_CONSUMER + 128 * (REGS_DRAIN + REGS_SERVICE) <= threads(false) * REGS_LAUNCH, "register pool");
   static constexpr int KSTEPS = HD == 40 ? 3 : HD / 16, NKC = 2 * KSTEPS;
@@ -173,17 +177,23 @@ __device__ __forceinline__ void idle_or_trap(bool progress, uint32_t& spins, lon
 // warp-converged variants (tensor-core issuer warps): every lane probes, the vote makes the answer warp-uniform
 __device__ __forceinline__ bool test_bar_u(uint32_t bar, uint32_t parity) { return __all_sync(0xffffffffu, test_bar(bar, parity)); }
 __device__ __forceinline__ void wait_bar_u(uint32_t bar, uint32_t parity) {
-  long long t0 = 0;
-  uint32_t spins = 0;
-  while (true) {
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (__all_sync(0xffffffffu, ok != 0)) return;
-    __nanosleep(40);
-    if (++spins == 64) t0 = clock64();
-    if (spins > 64 && clock64() - t0 > (1ll << 32)) __trap();  // ~2 s: unreachable unless the barrier protocol is broken
-  }
+  // one asm block (see wait_bar): nothing lane-dependent leaves it, so the caller's control flow stays warp-uniform
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 n;\n"
+      "mov.u32 n, 0;\n"
+      "X3_WAIT_U:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra X3_DONE_U;\n"
+      "nanosleep.u32 40;\n"
+      "add.u32 n, n, 1;\n"
+      "setp.lt.u32 p, n, 0x400000;\n"
+      "@p bra X3_WAIT_U;\n"
+      "trap;\n"  // unreachable unless the barrier protocol is broken: never hang the GPU
+      "X3_DONE_U:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
 }
 // explicit shared-space accesses (32-bit addresses derived from the opaque base: no generic-pointer conversion in the loops)
 __device__ __forceinline__ float4 lds128(uint32_t a) {
@@ -202,6 +212,24 @@ __device__ __forceinline__ uint32_t lds32_volatile(uint32_t a) {
 __device__ __forceinline__ void red_add_shared(uint32_t a, uint32_t x) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
 }
+// 2^t for two arguments t <= 0 WITHOUT the MUFU pipe (the softmax's bottleneck: 16 exponentials per clock and SM): Cody-Waite
+// split t = n + f with n = floor(t) through the round-down add of 1.5 * 2^23 (the integer lands in the low mantissa bits),
+// 2^f on [0, 1) as a cubic (max relative error 7.5e-5, a sixth of the half-ulp of the fp16 the result is rounded to), n added
+// to the exponent field.  Arguments below -126 are clamped (the result is < 2^-126 either way: it rounds to zero in P).
+__device__ __forceinline__ void exp2_fma2(float& p0, float& p1, float t0, float t1) {
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23
+  t0 = fmaxf(t0, -126.f);
+  t1 = fmaxf(t1, -126.f);
+  const float r0 = __fadd_rd(t0, kMagic), r1 = __fadd_rd(t1, kMagic);
+  float n0, n1, f0, f1, q0, q1;
+  fadd2(n0, n1, r0, r1, -kMagic, -kMagic);  // floor(t), exact
+  ffma2(f0, f1, n0, n1, -1.f, -1.f, t0, t1);  // t - floor(t), exact
+  ffma2(q0, q1, f0, f1, 0.07802421599626541f, 0.07802421599626541f, 0.22606723010540009f, 0.22606723010540009f);
+  ffma2(q0, q1, q0, q1, f0, f1, 0.6958337426185608f, 0.6958337426185608f);
+  ffma2(q0, q1, q0, q1, f0, f1, 0.9999251961708069f, 0.9999251961708069f);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
+}
 // x, through a shuffle with the caller's own lane: a value ptxas keeps in a register instead of recomputing it
 __device__ __forceinline__ uint32_t opaque(uint32_t x) {
   uint32_t lane, y;
@@ -214,8 +242,13 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
   return pred != 0;
 }
+// Blocking wait on a barrier phase.  The whole loop is ONE asm block: the satisfied case is try_wait + one short forward
+// branch.  (Written in C++, with the time-out logic inline, the compiler wraps every wait in BSSY / BSYNC, three register
+// clears and a far taken branch over the slow path -- ~10 instructions and an instruction-fetch bubble per wait, six waits
+// per item.)  A wait that polls 2^22 times traps: a protocol error must end in an error the host sees, never in a hung GPU.
 template <bool RELAXED>
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t tag) {
+#ifdef DSC_WATCHDOG
   long long t0 = 0;
   uint32_t spins = 0;
   while (true) {
@@ -226,7 +259,6 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t
     if (RELAXED) __nanosleep(40);
     if (++spins == 64) t0 = clock64();
     if (spins > 64) {
-#ifdef DSC_WATCHDOG
       if (*reinterpret_cast<volatile unsigned int*>(&g_x3_abort)) return;
       if (clock64() - t0 > (1ll << 30)) {
         if (atomicCAS(&g_x3_abort, 0u, 1u) == 0u) {
@@ -237,11 +269,45 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t
         }
         return;
       }
-#else
-      if (clock64() - t0 > (1ll << 32)) __trap();  // ~2 s: unreachable unless the barrier protocol is broken
-#endif
     }
   }
+#else
+  (void)tag;
+  if constexpr (RELAXED) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "X3_WAIT_R:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra X3_DONE_R;\n"
+        "nanosleep.u32 40;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 p, n, 0x400000;\n"
+        "@p bra X3_WAIT_R;\n"
+        "trap;\n"
+        "X3_DONE_R:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "X3_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra X3_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 p, n, 0x400000;\n"
+        "@p bra X3_WAIT;\n"
+        "trap;\n"
+        "X3_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+  }
+#endif
 }
 
 #ifdef DSC_TRACE
@@ -272,6 +338,18 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
       g_x3_trace_n[STATS ? 0 : 1][tr_k] = ++tr_n;                \
     }                                                            \
   } while (0)
+#define X3_CTA_TIME(k) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_x3_cta[STATS ? 0 : 1][blockIdx.x][k] = gtimer_ns(); } while (0)
+#elif defined(DSC_CTATIME)
+// Debug build only: globaltimer at the start / end of every CTA and pass, nothing else (the in-kernel span of a call without
+// the event-timer quantisation and the launch overhead: scripts/x3_span.py)
+__device__ unsigned long long g_x3_cta[2][160][2];
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define X3_TRACE_DECL
+#define X3_TRACE(tag) do {} while (0)
 #define X3_CTA_TIME(k) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_x3_cta[STATS ? 0 : 1][blockIdx.x][k] = gtimer_ns(); } while (0)
 #else
 #define X3_TRACE_DECL
@@ -506,7 +584,21 @@ __device__ __forceinline__ uint32_t x3_phase(const XattnParams& p, const CUtenso
         ++dn;
       }
       if constexpr (!STATS) {
-        if (elect_one()) bulk_wait0();
+        // the CTA must outlive the stores' READS of shared memory; their global writes complete with the grid
+        if (elect_one()) bulk_wait_read0();
+        __syncwarp();
+      } else if constexpr (FUSED) {
+        // single launch: the Q tiles are on their way; pull towards L2 what pass 2's first tiles need and pass 1 never
+        // touched (the compact W rows, the V^T halves of the first image) while the consumers finish pass 1
+        const int npre = min(n_items, C::FWD_NST);
+        for (int i = 0; i < npre; ++i) {
+          const Tile t = decode(begin + i, p);
+          const float* w = p.wc + (static_cast<size_t>(t.b / (p.B / p.Bw)) * p.L + t.l0) * DSC_COMPACT_PITCH;
+          const uint32_t wb = static_cast<uint32_t>(min(ROWS, p.L - t.l0)) * (DSC_COMPACT_PITCH * 4);
+          if (elect_one()) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(w), "r"(wb) : "memory");
+        }
+        if (n_items > 0 && elect_one())
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(img + static_cast<size_t>(seg0) * IMG_BYTES), "r"(IMG_BYTES) : "memory");
         __syncwarp();
       }
     } else if (warp > SW0 && warp - SW0 - 1 < NWG) {
@@ -939,7 +1031,13 @@ __device__ __forceinline__ uint32_t x3_phase(const XattnParams& p, const CUtenso
             float e0, e1;
             if (c < 8) ffma2(e0, e1, sc[2 * c], sc[2 * c + 1], ce, ce, nb, nb);
             else ffma2(e0, e1, sc[2 * c], sc[2 * c + 1], k2, k2, nb, nb);
-            pw[c] = c < 38 ? Mma<T>::pack(ex2_approx(e0), ex2_approx(e1)) : Mma<T>::pack(ex2_approx(e0), 0.f);
+            if (X3_POLY > 0 && c % (X3_POLY > 0 ? X3_POLY : 1) == X3_POLY - 1 && c < 38) {
+              float p0, p1;
+              exp2_fma2(p0, p1, e0, e1);  // this pair on the FMA / ALU pipes instead of the MUFU pipe
+              pw[c] = Mma<T>::pack(p0, p1);
+            } else {
+              pw[c] = c < 38 ? Mma<T>::pack(ex2_approx(e0), ex2_approx(e1)) : Mma<T>::pack(ex2_approx(e0), 0.f);
+            }
             if (c == 23) {  // keys 0..47 are done: first part of P
               tmem_st_x16(tw + P_COL, pw);
               tmem_st_x8(tw + P_COL + 16, pw + 16);
@@ -1292,6 +1390,14 @@ extern "C" int dsc_debug_x3_trace(long long* out /*HOST 2*8*1024*2*/, int* count
   cudaMemcpyFromSymbol(cta, x3::g_x3_cta, sizeof(unsigned long long) * 2 * 160 * 2);
   int z[16] = {0};
   cudaMemcpyToSymbol(x3::g_x3_trace_n, z, sizeof(z));
+  return 0;
+}
+#endif
+
+#ifdef DSC_CTATIME
+extern "C" int dsc_debug_x3_cta(unsigned long long* cta /*HOST 2*160*2*/) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(cta, x3::g_x3_cta, sizeof(unsigned long long) * 2 * 160 * 2);
   return 0;
 }
 #endif
