@@ -96,12 +96,18 @@ struct Cfg {
   static constexpr int VT_CH = ON * 16, VT_HEAD = 10 * VT_CH;
   static constexpr int REC_BYTES = K_HEAD + VT_HEAD;                   // 15360 / 28160 / 53760
   static constexpr int IMG_BYTES = HPT * REC_BYTES;                    // 61440 / 56320 / 53760
-  static constexpr int NSLOT = HD == 40 ? 4 : 2;
+#ifndef X3_NSLOT40
+#define X3_NSLOT40 5
+#endif
+  // HD = 40: one slot more than a (batch, head group) has heads -- at a run boundary the first record of the next run is
+  // loaded while all four heads of the old run are still in use (a CTA whose tiles cross a boundary pays ~1.4 us for the
+  // drained pipeline with 4 slots: profiles/r2_x3_span_detail*.txt)
+  static constexpr int NSLOT = HD == 40 ? X3_NSLOT40 : 2;
   static constexpr int FWD_NST = HD == 160 ? 2 : 3;
-  static constexpr int FWD_SMEM = NSLOT * REC_BYTES + FWD_NST * FWD_STAGE + BAR_BYTES;
-  static constexpr int STATS_SMEM = NSLOT * K_HEAD + STATS_NST * STATS_STAGE + BAR_BYTES;
+  static constexpr int FWD_SMEM = round_1k(NSLOT * REC_BYTES) + FWD_NST * FWD_STAGE + BAR_BYTES;
+  static constexpr int STATS_SMEM = round_1k(NSLOT * K_HEAD) + STATS_NST * STATS_STAGE + BAR_BYTES;
   static constexpr int TURNS = NWG == 3 ? X3_TURNS_DEFAULT : 0;
-  static_assert((NSLOT * REC_BYTES) % 1024 == 0 && (NSLOT * K_HEAD) % 1024 == 0 && FWD_STAGE % 1024 == 0 && STATS_STAGE % 1024 == 0 &&
+  static_assert(FWD_STAGE % 1024 == 0 && STATS_STAGE % 1024 == 0 &&
                     REC_BYTES % 16 == 0 && K_HEAD % 16 == 0, "alignment");
   static_assert(FWD_SMEM <= 227 * 1024 && STATS_SMEM <= 227 * 1024, "shared memory budget");
   static_assert(NWG * WG_COLS <= 512 && 2 * S1_COL * NWG <= 512, "TMEM budget");
@@ -386,7 +392,7 @@ __device__ __forceinline__ uint32_t x3_phase(const XattnParams& p, const CUtenso
   constexpr int NST = STATS ? STATS_NST : C::FWD_NST;
   constexpr int STAGE = STATS ? STATS_STAGE : FWD_STAGE;
   constexpr int RECB = STATS ? K_HEAD : C::REC_BYTES;  // bytes of a record this pass needs (pass 1: its K part) = slot pitch
-  constexpr int KV = NSLOT * RECB;
+  constexpr int KV = (NSLOT * RECB + 1023) / 1024 * 1024;  // the ring stages behind it hold swizzled boxes: 1024-byte aligned
   extern __shared__ __align__(1024) unsigned char smem[];
   // thread index and shared-memory base are made opaque (a shuffle with the thread's own lane): left alone, ptxas
   // re-materialises them (S2R SR_TID.X / SR_CgaCtaId + LEA, long-latency special-register reads) in front of every
@@ -412,13 +418,15 @@ __device__ __forceinline__ uint32_t x3_phase(const XattnParams& p, const CUtenso
   const uint32_t s0 = opaque(smem_u32(smem));
   const uint32_t sStage = s0 + KV;
   const uint32_t bars = sStage + NST * STAGE;
-  // barrier map (8 B each): full[4] | odone[4] | kvfull[4] | kvfree[4] | srdy[3][2] | sfree[3][2] | prdy[3] | ordy[3] | ofree[3]
-  const uint32_t b_full = bars, b_odone = bars + 32, b_kvfull = bars + 64, b_kvfree = bars + 96, b_srdy = bars + 128,
-                 b_sfree = bars + 176, b_prdy = bars + 224, b_ordy = bars + 248, b_ofree = bars + 272, b_std = bars + 296;
-  constexpr int N_BARS = 38;  // ... | std[1] (pass 2, handoff: the folding warp has put the std at std_addr)
-  const uint32_t std_addr = bars + 344;
-  const uint32_t turn_addr = bars + 320;
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 336);
+  // barrier map (8 B each): full[4] | odone[4] | kvfull[8] | kvfree[8] | srdy[3][2] | sfree[3][2] | prdy[3] | ordy[3] | ofree[3] |
+  // std[1] (pass 2, handoff: the folding warp has put the std at std_addr)
+  const uint32_t b_full = bars, b_odone = bars + 32, b_kvfull = bars + 64, b_kvfree = bars + 128, b_srdy = bars + 192,
+                 b_sfree = bars + 240, b_prdy = bars + 288, b_ordy = bars + 312, b_ofree = bars + 336, b_std = bars + 360;
+  constexpr int N_BARS = 46;
+  static_assert(NSLOT <= 8, "kvfull / kvfree barrier arrays");
+  const uint32_t turn_addr = bars + 384;
+  const uint32_t std_addr = bars + 408;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + KV + NST * STAGE + 400);
 
   const int begin = static_cast<int>(blockIdx.x * p.tiles_q + min(blockIdx.x, p.tiles_r));
   const int n_items = static_cast<int>(p.tiles_q + (blockIdx.x < p.tiles_r ? 1u : 0u));
@@ -482,7 +490,7 @@ __device__ __forceinline__ uint32_t x3_phase(const XattnParams& p, const CUtenso
   // barrier init is spread over the service warps so that the first loads leave as early as possible: the producer
   // warp initialises only what those loads signal (full[], kvfull[]), service warp 2 the rest
   if (warp == SW0) {
-    if (lane < 8) mbar_init((lane < 4 ? b_full : b_kvfull - 32) + 8 * lane, 1);
+    if (lane < 12) mbar_init((lane < 4 ? b_full : b_kvfull - 32) + 8 * lane, 1);  // full[4], kvfull[8]
     fence_mbar_init();
     __syncwarp();
     X3_TRACE(4);
@@ -494,10 +502,10 @@ __device__ __forceinline__ uint32_t x3_phase(const XattnParams& p, const CUtenso
   }
   if (warp == SW0 + 2) {
     for (int idx = 4 + lane; idx < N_BARS; idx += 32) {
-      if (idx >= 8 && idx < 12) continue;  // kvfull[]: the producer's
+      if (idx >= 8 && idx < 16) continue;  // kvfull[]: the producer's
       // odone[]: 128 rows of every head of the tile | kvfree[]: every consumer | srdy, ordy: one commit | sfree, prdy: a warpgroup |
       // ofree[]: the drain warpgroup
-      const uint32_t cnt = idx < 8 ? HPT * 128u : idx < 16 ? static_cast<uint32_t>(CONSUMERS) : idx < 22 ? 1u : idx < 31 ? 128u : idx < 34 ? 1u : idx < 37 ? 128u : 1u;
+      const uint32_t cnt = idx < 8 ? HPT * 128u : idx < 24 ? static_cast<uint32_t>(CONSUMERS) : idx < 30 ? 1u : idx < 39 ? 128u : idx < 42 ? 1u : idx < 45 ? 128u : 1u;
       mbar_init(bars + 8 * idx, cnt);
     }
     fence_mbar_init();
