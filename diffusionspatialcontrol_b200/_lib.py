@@ -54,6 +54,7 @@ SIGNATURES = {
         [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_int, POINTER(ctypes.c_int32)]
         + [c_int] * 5 + [c_void_p, c_void_p],
     ),
+    "dsc_xattn_call_prepared_launches": (c_int, [c_int] * 5),
     "dsc_xattn_call_prepared": (
         c_int,
         [c_void_p, POINTER(c_int64), c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,

@@ -382,6 +382,11 @@ int dsc_xattn_prepare_kv(const void* k, const void* v, const int64_t k_str[4], c
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_prepare_kv");
 }
 
+int dsc_xattn_call_prepared_launches(int B, int H, int L, int D, int S) {
+  if (B <= 0 || H <= 0 || L <= 0 || !x3_supports(H, D, S)) return -1;
+  return config().no_fused ? 2 : 1;
+}
+
 int dsc_xattn_call_prepared(const void* q, const int64_t q_str[4], const void* kv_image, const float* Wc, int Bw, int n_active,
                             const float* sigma_dev_or_null, float sigma_host, void* workspace, void* out, const int64_t o_str[3],
                             int B, int H, int L, int D, int S, float scale, int dtype, int passes, void* stream) {

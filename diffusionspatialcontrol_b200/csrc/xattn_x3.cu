@@ -1098,8 +1098,9 @@ __device__ __forceinline__ uint32_t x3_phase(const XattnParams& p, const CUtenso
             __stcg(slots + 2 * blockIdx.x, static_cast<unsigned long long>(__double_as_longlong(a)) | 1ull);
             __stcg(slots + 2 * blockIdx.x + 1, static_cast<unsigned long long>(__double_as_longlong(b)) | 1ull);
           } else {
-            partials[2 * blockIdx.x] = a;
-            partials[2 * blockIdx.x + 1] = b;
+            // (same bit 0 as the handoff form: both protocols fold the same values in the same order -> the same std)
+            partials[2 * blockIdx.x] = __longlong_as_double(__double_as_longlong(a) | 1ll);
+            partials[2 * blockIdx.x + 1] = __longlong_as_double(__double_as_longlong(b) | 1ll);
             __threadfence();
             last = atomicAdd(&p.ws->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
           }

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSC_VERSION 106 /* major*10000 + minor*100 + patch */
+#define DSC_VERSION 107 /* major*10000 + minor*100 + patch */
 
 #define DSC_DTYPE_F16 0
 #define DSC_DTYPE_BF16 1
@@ -133,8 +133,8 @@ int dsc_xattn_call_cw(const void* q, const void* k, const void* v, const int64_t
  * them out ONCE as the shared-memory image the tcgen05 kernels multiply from (UMMA K-major chunks of K, V^T with a ones
  * row, keys permuted so that the active columns of the compact region map come first); dsc_xattn_call_prepared then
  * runs pass 1 and pass 2 on that image: each CTA fetches K / V^T with one bulk copy instead of re-gathering them.
- * Supported (dsc_xattn_prepared_supported != 0): D == 40, S == 77, H a multiple of 4, 1 <= n_active <= 16.
- * The image depends on k, v AND the active column list: prepare again when any of them changes. */
+ * Supported (dsc_xattn_prepared_supported != 0): D in {40, 80, 160} with H * D a multiple of 160, S == 77,
+ * 1 <= n_active <= 16.  The image depends on k, v AND the active column list: prepare again when any of them changes. */
 int dsc_xattn_prepared_supported(int H, int D, int S);
 int dsc_xattn_kv_image_bytes(int B, int H, int D, int S, size_t* out /*HOST*/);
 int dsc_xattn_prepare_kv(const void* k, const void* v, const int64_t k_str[4] /*HOST*/, const int64_t v_str[4] /*HOST*/,
@@ -142,9 +142,16 @@ int dsc_xattn_prepare_kv(const void* k, const void* v, const int64_t k_str[4] /*
                          void* kv_image, void* stream);
 /* passes: 1 = pass 1 only (std -> workspace), 2 = pass 2 only (std read from the workspace), 3 = the whole call.
  * Wc / n_active / Bw as in dsc_xattn_call_cw (the column list itself is baked into the image); same result as
- * dsc_xattn_call_cw on the k, v the image was prepared from. */
+ * dsc_xattn_call_cw on the k, v the image was prepared from.
+ * passes == 3 is ONE cooperative launch (pass 1 and pass 2 as two phases of the same persistent CTAs; the std goes from
+ * one to the other through per-CTA slots in the workspace that pass 2 polls and folds in a fixed order); when the device
+ * cannot hold the grid (another context occupies SMs) or after dsc_config_set("no_fused", "1") it is two launches, pass 2
+ * a programmatic dependent launch of pass 1.  The statistics header of the workspace is filled either way. */
 #define DSC_PASS_STATS 1
 #define DSC_PASS_FORWARD 2
+/* Number of kernel launches dsc_xattn_call_prepared(passes = 3) issues under the current configuration: 1 or 2; -1 for an
+ * unsupported shape.  Introspection only. */
+int dsc_xattn_call_prepared_launches(int B, int H, int L, int D, int S);
 int dsc_xattn_call_prepared(const void* q, const int64_t q_str[4] /*HOST*/, const void* kv_image, const float* Wc, int Bw,
                             int n_active, const float* sigma_dev_or_null, float sigma_host, void* workspace, void* out,
                             const int64_t o_str[3] /*HOST*/, int B, int H, int L, int D, int S, float scale, int dtype,

@@ -31,7 +31,7 @@ def test_version_and_workspace_size():
     from diffusionspatialcontrol_b200 import _lib
     from diffusionspatialcontrol_b200.attention import workspace_bytes
 
-    assert _lib.lib.dsc_version() == 106
+    assert _lib.lib.dsc_version() == 107
     assert workspace_bytes(16, 8, 4096, 40, 77) >= 64 + 16 * 148
     n = ctypes.c_size_t(0)
     assert _lib.lib.dsc_xattn_workspace_bytes(0, 8, 64, 40, 77, ctypes.byref(n)) == _lib.ERR_INVALID_ARGUMENT
