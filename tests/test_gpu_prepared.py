@@ -259,3 +259,65 @@ def test_processor_prepared_path_matches_reference_processor_restatement():
         want = oa.processor_forward(attn32, hs.float(), ehs.float(), {**rp, "region_state": {4096: W.cuda()}})
     assert len(proc._img_cache) == 1  # the call went through the prepared path
     assert rel_l2(got.float(), want) <= 4e-3
+
+
+@pytest.mark.parametrize("B,L,D", [(2, 37, 80), (2, 144, 160), (2, 100, 40), (1, 64, 160), (3, 129, 40), (16, 4096, 40)])
+def test_guard_bands_around_every_buffer_stay_untouched(B, L, D):
+    """Our own bounds check (compute-sanitizer is closed on the GPU pool: profiles/r2_sanitizer_memcheck_closed.log): the
+    output, the K/V^T image and the workspace sit inside larger buffers whose guard bands carry a pattern; ragged tails
+    (L not a multiple of the 128-row tile), the single launch and the two-launch form must leave every guard byte alone
+    and agree bit for bit."""
+    att = _att()
+    H, S, G = 8, 77, 1 << 16
+    q, k, v = make_qkv(B, H, L, D, S, seed=11, device="cuda")
+    W = synthetic_w(B, L, S).cuda()
+    Wp = att.padded_region_map(W)
+    compact = att.compact_region_map(Wp)
+
+    def guarded(nbytes, align=1024):
+        n = (nbytes + align - 1) // align * align
+        buf = torch.full((G + n + G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return buf, buf[G:G + nbytes]
+
+    kv_buf, kv_mem = guarded(att.kv_image_bytes(B, H, D, S))
+    kv = att.prepare_kv(k, v, compact[1], out=kv_mem)
+    ws_buf, ws_mem = guarded(att.workspace_bytes(B, H, L, D, S))
+    ws_mem.zero_()
+    o_buf, o_mem = guarded(B * L * H * D * 2)
+    out = o_mem.view(torch.float16).view(B, L, H * D)
+    a = att.region_attention_prepared(q, kv, compact, 7.0, workspace=ws_mem, out=out).clone()
+    att.region_attention_prepared(q, kv, compact, 7.0, workspace=ws_mem, out=out, passes=1)
+    b = att.region_attention_prepared(q, kv, compact, 7.0, workspace=ws_mem, out=out, passes=2).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert rel_l2(a, _oracle(q, k, v, W, 7.0)) < TOL
+    for name, buf, mem in (("kv image", kv_buf, kv_mem), ("workspace", ws_buf, ws_mem), ("output", o_buf, o_mem)):
+        n = mem.numel()
+        assert bool((buf[:G] == 0xA5).all()) and bool((buf[G + n:] == 0xA5).all()), f"guard band of the {name} was written"
+    # the workspace is left reusable: handoff slots empty again, reader count back to zero
+    from diffusionspatialcontrol_b200 import _lib  # noqa: F401
+    hdr = ws_mem[:64].cpu().numpy().view(np.uint32)
+    assert hdr[0] == 0 and hdr[14] == 0
+    assert not bool(ws_mem[64 + 16 * 1024:64 + 32 * 1024].any())
+
+
+def test_two_launch_fallback_equals_the_single_launch():
+    """dsc_config_set("no_fused", "1") sends the whole call through pass 1 + pass 2 as two launches (the form taken when a
+    cooperative launch cannot be placed): same bits, and dsc_xattn_call_prepared_launches reports it."""
+    from diffusionspatialcontrol_b200 import _lib
+
+    att = _att()
+    B, H, L, D, S = 4, 8, 1024, 80, 77
+    q, k, v = make_qkv(B, H, L, D, S, seed=5, device="cuda")
+    W = synthetic_w(B, L, S).cuda()
+    a, kv, compact = _run(att, q, k, v, W, 7.0)
+    a = a.clone()
+    assert _lib.lib.dsc_xattn_call_prepared_launches(B, H, L, D, S) == 1
+    try:
+        assert _lib.lib.dsc_config_set(b"no_fused", b"1") == 0
+        assert _lib.lib.dsc_xattn_call_prepared_launches(B, H, L, D, S) == 2
+        b = att.region_attention_prepared(q, kv, compact, 7.0).clone()
+    finally:
+        _lib.lib.dsc_config_set(b"no_fused", None)
+    assert _lib.lib.dsc_xattn_call_prepared_launches(B, H, L, D, S) == 1
+    assert torch.equal(a, b)
