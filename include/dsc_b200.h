@@ -75,8 +75,10 @@ int dsc_xattn_workspace_bytes(int B, int H, int L, int D, int S, size_t* out /*H
  * multiples of 8 elements, base pointers 16-byte aligned -- i.e. the [B, L, H*D] projection output
  * viewed as heads, which is exactly what the reference processor produces
  * (attention_modify.py:471-474).  D in {40,64,80,128,160}; 1 <= S <= DSC_MAX_KEYS_TOTAL.
- * mask_or_null: additive attention mask; only NULL is implemented (DSC_ERR_UNSUPPORTED otherwise;
- * SD-1.5 never passes one). */
+ * mask_or_null: additive attention mask (attention_modify.py:84-89); only NULL is accepted, anything else is refused
+ * with DSC_ERR_UNSUPPORTED on every entry point of the region path.  Decision, not omission: SD-1.5 never passes one,
+ * and the reference's own behaviour with one is not worth reproducing (a -inf mask makes qk.std() NaN and the
+ * beta-term poisons every row; a finite mask changes the std of the masked scores in both passes). */
 int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4] /*HOST*/, const int64_t k_str[4] /*HOST*/,
                     const void* mask_or_null, int B, int H, int L, int D, int S, float scale, int dtype,
                     void* workspace, void* stream);
