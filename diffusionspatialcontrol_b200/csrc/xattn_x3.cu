@@ -35,6 +35,7 @@
 #include "tc5_tmem.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace dsc {
 
@@ -1333,6 +1334,13 @@ static cudaError_t launch_fused(XattnParams p, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = config().no_pdl ? 1 : 2;
+#ifdef DSC_CTATIME  // measurement builds only: DSC_X3_NOCOOP=1 drops the cooperative attribute (what does it cost per launch?)
+  static const bool nocoop = getenv("DSC_X3_NOCOOP") != nullptr;
+  if (nocoop) {
+    cfg.attrs = attr + 1;
+    cfg.numAttrs = 1;
+  }
+#endif
   cudaError_t e = cudaLaunchKernelEx(&cfg, xattn_x3_fused_kernel<T, HD>, p, tm_qa, tm_qb, tm_qp, tm_oa, tm_ob);
   if (e != cudaSuccess && cfg.numAttrs == 2) {  // a driver that refuses the combination: cooperative only
     (void)cudaGetLastError();
