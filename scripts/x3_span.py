@@ -33,9 +33,12 @@ for sh in shapes.split(","):
     out = torch.empty(B, L, H * D, device=dev, dtype=torch.float16)
     grid = min(148, B * (H * D // 160) * ((L + 127) // 128))
     rows = []
+    q_src = q.clone()
     for it in range(n + 3):
         flush.zero_()
         flush[: flush.numel() // 2].view(torch.int64).sum()
+        if os.environ.get("X3_SPAN_FRESH_Q"):  # as in the UNet: Q has just been written by the projection (L2-resident)
+            q.copy_(q_src)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         att.region_attention_prepared(view(q), kv, compact, 7.0, out=out)
