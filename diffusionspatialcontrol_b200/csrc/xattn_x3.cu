@@ -1,36 +1,44 @@
-// Region-masked cross-attention, tcgen05 + TMEM, THREE decoupled consumer warpgroups ("x3"), D = 40, S = 77.
+// Region-masked cross-attention on a prepared K / V^T image: warp-specialised tcgen05 + TMEM + TMA kernels ("x3"),
+// head dims 40 / 80 / 160, S = 77.  What RegionAttnProcessor runs for every SD-1.5 cross-attention layer.
 //
 // Same two passes as xattn_tc5.cu (pass 1: std of scale*QK^T over the whole call; pass 2: softmax(scale*QK^T + beta*W) V;
-// reference source/modules/attention_modify.py:74-103 with the weight_func of source/app.py:1004), reorganised so that no
-// thread ever waits for a tensor-core round trip it has just started:
+// reference source/modules/attention_modify.py:74-103 with the weight_func of source/app.py:1004), organised so that no
+// thread ever waits for a tensor-core round trip it has just started, and -- for the whole call -- as ONE cooperative
+// launch (xattn_x3_fused_kernel: x3_phase<pass 1> then x3_phase<pass 2> in the same persistent CTAs):
 //
-//   * Work item = (128-row tile, head).  Items of a CTA's tile range are dealt round-robin to 3 consumer warpgroups
-//     (one thread per query row; TMEM lane = row).  A warpgroup owns 168 TMEM columns: S (80 fp32) | P (40, 16-bit pairs)
-//     | O (48 fp32) -- S, P and O are SEPARATE regions (3 x 168 = 504 <= 512 columns), so
+//   * Work item = (128-row tile, head).  Items of a CTA's tile range are dealt round-robin to 3 / 2 / 1 consumer
+//     warpgroups (one thread per query row; TMEM lane = row).  A warpgroup owns S (80 fp32 columns) | P (40, 16-bit pairs)
+//     | O (48 / 96 / 176 fp32) as SEPARATE TMEM regions (3 x 168 = 504 <= 512 columns at D = 40), so
 //         Q K^T of item n+1 is issued the moment S(n) has been read into registers,
-//         P V   of item n   runs while the warpgroup already exponentiates item n+1,
-//         O(n) is drained (x 1/rowsum -> shared memory) in the middle of item n+1's softmax, when P V(n) has long
-//         finished.
+//         P V   of item n   runs while the warpgroup already exponentiates item n+1.
 //     The x4 kernel (xattn_tc5.cu) aliases P on S and the Q operand on O: its four warpgroups sit through the serial chain
 //     O -> Q rows to TMEM -> QK^T -> S -> softmax -> P -> PV together (2.8k of 5.7k cycles per tile idle, profiles/r1_*).
+//   * The consumers never touch O: a DRAIN warpgroup (pass 2; warp d <-> TMEM lanes 32d..32d+31 of every consumer
+//     warpgroup) takes the O rows out of TMEM, scales them by 1 / rowsum (ones row of V^T), and stores them over the rows'
+//     own Q columns of the ring stage; the register file is re-divided with setmaxnreg (consumers up, drain / service down).
 //   * Q is the A operand STRAIGHT FROM SHARED MEMORY (no smem -> registers -> TMEM hop, no consumer thread involved).
-//     The TMA engine costs about one cycle per box ROW whatever its width (profiles/r1_tma_copy_rate.jsonl,
-//     profiles/r2_x3_trace_*.txt), so the 160-column tile arrives as just three boxes: columns [0,64) and [64,128) with
-//     SWIZZLE_128B and [128,160) with SWIZZLE_64B (384 rows) -- the UMMA K-major canonical layouts.  A k16 step must lie
-//     inside one swizzle row, and head h starts at column 40h, so the contraction of head h runs over the three
-//     16-column blocks (32-byte aligned in the row) that cover its 40 columns, and the K image holds ZEROS where a block's
-//     columns belong to a neighbouring head (h = 0: blocks 0-2, h = 1: 2-4, h = 2: 5-7, h = 3: 7-9): 3 MMAs per head,
-//     as many as 40 columns need anyway.  Finished O rows overwrite their own columns in the same boxes and leave through
-//     the same three box shapes; the compact W tile (128 rows x 80 B, contiguous in global memory) is ONE bulk copy.
-//   * K and V^T|1 of a (batch, 4-head group) arrive as ONE bulk copy of a prepared 60 KB image (dsc_xattn_prepare_kv:
-//     UMMA K-major chunks, keys permuted so that the weighted columns of the compact region map are slots 0..15, ones
-//     row appended to V^T so that column 40 of O is the softmax row sum).  K/V never change during a generation
-//     (attention_modify.py:465-466 recomputes the same projections on each of the 25 steps), so the image is built once.
-//   * 512 threads: warps 0-11 consumers, warp 12 lane 0 = TMA producer, lane 0 of warps 13-15 = tensor-core issuers of
-//     warpgroups 0-2 -> 128 registers per thread (the 640-thread x4 kernel has 96).
-//   * pass 1 (STATS): same skeleton, S double-buffered in TMEM (2 x 80 columns per warpgroup), 4-stage Q ring, every
-//     thread accumulates sum / sum of squares of its S rows; fold as in xattn_tc5.cu (deterministic).
-// Pass 2 is a programmatic dependent launch of pass 1, as before.
+//     The TMA engine costs about one cycle per box ROW whatever its width (profiles/r1_tma_copy_rate.jsonl), so the
+//     160-column tile arrives as just three boxes: columns [0,64) and [64,128) with SWIZZLE_128B and [128,160) with
+//     SWIZZLE_64B -- the UMMA K-major canonical layouts.  A k16 step must lie inside one swizzle row, and head h starts
+//     at column 40h, so the contraction of head h runs over the three 16-column blocks (32-byte aligned in the row) that
+//     cover its 40 columns, and the K image holds ZEROS where a block's columns belong to a neighbouring head (h = 0:
+//     blocks 0-2, h = 1: 2-4, h = 2: 5-7, h = 3: 7-9): 3 MMAs per head, as many as 40 columns need anyway.  Finished O
+//     rows leave through the same three box shapes; the compact W tile (128 rows x 80 B, contiguous) is ONE bulk copy.
+//   * K and V^T|1 of a (batch, head group) arrive as bulk copies of head RECORDS of the prepared image
+//     (dsc_xattn_prepare_kv: UMMA K-major chunks, keys permuted so that the weighted columns of the compact region map are
+//     slots 0..15, ones row appended to V^T so that column D of O is the softmax row sum) into a ring of record slots
+//     (5 for 4 heads at D = 40: the next group's first record loads while all heads of the old one are in use).  K / V never
+//     change during a generation (attention_modify.py:465-466 recomputes the same projections on each of the 25 steps).
+//   * Producer warp and tensor-core issuer warps run CONVERGED: every TMA / MMA operand is warp-uniform to the compiler and
+//     lives in uniform registers; the instruction is issued by the elected lane.
+//   * pass 1 (STATS): same skeleton without the drain warpgroup, S double-buffered in TMEM (2 x 80 columns per
+//     warpgroup), 4-stage Q ring, every thread accumulates sum / sum of squares of its S rows; the CTA's partial goes
+//     to the workspace: ticket + deterministic fold by the last CTA (pass 1 on its own), or -- whole call -- two 8-byte
+//     stores into the HANDOFF slots that drain warp 0 of every pass-2 CTA polls and folds in the same fixed order.
+// Launch forms: the whole call = one cooperative launch (fallback: two launches, pass 2 a programmatic dependent launch of
+// pass 1 that never waits for pass 1's completion); pass 1 / pass 2 on their own = xattn_x3_kernel<.., STATS>.
+// Debug builds: -DDSC_TRACE (clock64 timelines), -DDSC_PHASE (cycles per consumer phase), -DDSC_CTATIME (globaltimer span
+// of every CTA and pass), -DDSC_WATCHDOG (who waited on what); A/B switches X3_TURNS, X3_POLY, X3_NSLOT40.
 #include "tc5_common.cuh"
 #include "tc5_tmem.cuh"
 
