@@ -203,7 +203,7 @@ __device__ __forceinline__ void wait_bar_u(uint32_t bar, uint32_t parity) {
       "@p bra X3_DONE_U;\n"
       "nanosleep.u32 40;\n"
       "add.u32 n, n, 1;\n"
-      "setp.lt.u32 p, n, 0x400000;\n"
+      "setp.lt.u32 p, n, 0x4000000;\n"
       "@p bra X3_WAIT_U;\n"
       "trap;\n"  // unreachable unless the barrier protocol is broken: never hang the GPU
       "X3_DONE_U:\n"
@@ -260,7 +260,7 @@ __device__ __forceinline__ bool elect_one() {
 // Blocking wait on a barrier phase.  The whole loop is ONE asm block: the satisfied case is try_wait + one short forward
 // branch.  (Written in C++, with the time-out logic inline, the compiler wraps every wait in BSSY / BSYNC, three register
 // clears and a far taken branch over the slow path -- ~10 instructions and an instruction-fetch bubble per wait, six waits
-// per item.)  A wait that polls 2^22 times traps: a protocol error must end in an error the host sees, never in a hung GPU.
+// per item.)  A wait that polls 2^26 times (>= 1 s) traps: a protocol error must end in an error the host sees, never in a hung GPU.
 template <bool RELAXED>
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t tag) {
 #ifdef DSC_WATCHDOG
@@ -299,7 +299,7 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t
         "@p bra X3_DONE_R;\n"
         "nanosleep.u32 40;\n"
         "add.u32 n, n, 1;\n"
-        "setp.lt.u32 p, n, 0x400000;\n"
+        "setp.lt.u32 p, n, 0x4000000;\n"
         "@p bra X3_WAIT_R;\n"
         "trap;\n"
         "X3_DONE_R:\n"
@@ -315,7 +315,7 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, uint32_t
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra X3_DONE;\n"
         "add.u32 n, n, 1;\n"
-        "setp.lt.u32 p, n, 0x400000;\n"
+        "setp.lt.u32 p, n, 0x4000000;\n"
         "@p bra X3_WAIT;\n"
         "trap;\n"
         "X3_DONE:\n"

@@ -14,6 +14,7 @@ weights are random-init (no checkpoints are available offline).
 from __future__ import annotations
 
 import inspect
+import os
 import math
 from typing import Dict, Optional, Union
 
@@ -94,7 +95,19 @@ class GEGLU(nn.Module):
         super().__init__()
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
+    # DSC_GEGLU_SPLIT=0 restores the single projection + chunk (A/B runs)
+    SPLIT = os.environ.get("DSC_GEGLU_SPLIT", "1") != "0"
+
     def forward(self, x):
+        if self.SPLIT and x.is_cuda:
+            # two projections on row slices of the same weight (same parameters, same state-dict keys): value and gate come
+            # out CONTIGUOUS, so gelu and the product run as vectorised elementwise kernels; chunk() of one [.., 2 * inner]
+            # output hands strided halves to both (non-vectorised generic kernels: 4 ms of a 32 ms UNet step at batch 16,
+            # profiles/r2_unet_host_groupnorm_nhwc.log).  Plain PyTorch ops: the UNet host is not part of the hot path.
+            inner = self.proj.out_features // 2
+            w, b = self.proj.weight, self.proj.bias
+            gate = F.gelu(F.linear(x, w[inner:], None if b is None else b[inner:]))
+            return F.linear(x, w[:inner], None if b is None else b[:inner]).mul_(gate)
         x, gate = self.proj(x).chunk(2, dim=-1)
         return x * F.gelu(gate)
 
