@@ -152,6 +152,8 @@ class GroupNorm(nn.GroupNorm):
     UNet host is not part of the hot path (BASELINE north_star: "the rest of the UNet stays on PyTorch GPU ops").
     Any other input takes ``F.group_norm``."""
 
+    ONE_PASS_STATS = os.environ.get("DSC_GN_ONE_PASS", "1") != "0"  # A/B switch
+
     def forward(self, x: torch.Tensor, silu: bool = False) -> torch.Tensor:
         if (x.is_cuda and x.dim() == 4 and x.dtype != torch.float32 and not x.is_contiguous()
                 and x.is_contiguous(memory_format=torch.channels_last)):
@@ -160,10 +162,18 @@ class GroupNorm(nn.GroupNorm):
             Cg = C // G
             xl = x.permute(0, 2, 3, 1)                      # [N, H, W, C] view of the same memory, contiguous
             xv = xl.reshape(N, H * W, G, Cg)
-            n = float(H * W * Cg)
-            mean = xv.sum(dim=(1, 3), dtype=torch.float32) / n                              # [N, G]
-            ex2 = torch.linalg.vector_norm(xv, dim=(1, 3), dtype=torch.float32).square() / n
-            rstd = torch.rsqrt((ex2 - mean * mean).clamp_min(0.0) + self.eps)
+            if self.ONE_PASS_STATS:
+                # ONE reduction over the activation (Welford, fp32 accumulation inside the kernel; the results come back in
+                # the activation's 16-bit type: the mean is off by <= 2^-11 |mean|, below the activation's own rounding
+                # for any |mean| / std a UNet produces) instead of a sum and a norm pass
+                var, mean = torch.var_mean(xv, dim=(1, 3), correction=0)
+                mean = mean.float()
+                rstd = torch.rsqrt(var.float() + self.eps)
+            else:
+                n = float(H * W * Cg)
+                mean = xv.sum(dim=(1, 3), dtype=torch.float32) / n                              # [N, G]
+                ex2 = torch.linalg.vector_norm(xv, dim=(1, 3), dtype=torch.float32).square() / n
+                rstd = torch.rsqrt((ex2 - mean * mean).clamp_min(0.0) + self.eps)
             scale = rstd[:, :, None] * self.weight.float().view(1, G, Cg)                   # [N, G, Cg]
             shift = self.bias.float().view(1, G, Cg) - mean[:, :, None] * scale
             y = torch.addcmul(shift.to(x.dtype).view(N, 1, 1, C), xl, scale.to(x.dtype).view(N, 1, 1, C))
