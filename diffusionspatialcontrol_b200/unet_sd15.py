@@ -214,8 +214,11 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
-        h = self.conv1(self.norm1(x, silu=True))
-        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        # conv1's bias rides on the time-embedding add: one per-(sample, channel) broadcast pass over h instead of two
+        c1 = self.conv1
+        h = F.conv2d(self.norm1(x, silu=True), c1.weight, None, c1.stride, c1.padding, c1.dilation, c1.groups)
+        t = self.time_emb_proj(F.silu(temb))
+        h = h + (t if c1.bias is None else t + c1.bias)[:, :, None, None]
         h = self.conv2(self.norm2(h, silu=True))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
