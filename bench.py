@@ -568,7 +568,7 @@ def main():
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # (NCCL_DEBUG is left alone: even WARN prints a version banner on stdout in front of the one JSON line)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # (NCCL prints its one-line version banner on stdout; the JSON line is the last line)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
