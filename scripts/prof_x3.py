@@ -1,4 +1,4 @@
-"""One flushed call of the prepared-K/V path (pass 1 + pass 2) for ncu.  Usage: python scripts/prof_x3.py [B L reps]"""
+"""One flushed call of the prepared-K/V path (the single cooperative launch) for ncu.  Usage: python scripts/prof_x3.py [B L reps [D]]"""
 import os
 import sys
 
@@ -10,7 +10,8 @@ from diffusionspatialcontrol_b200 import attention as att  # noqa: E402
 
 B, L = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (16, 4096)
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-H, D, S = 8, 40, 77
+H, S = 8, 77
+D = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 dev = torch.device("cuda")
 q = torch.randn(B, L, H * D, device=dev).half()
 k = torch.randn(B, S, H * D, device=dev).half()
