@@ -5,6 +5,7 @@ There is deliberately no fallback: if the library is missing the import fails lo
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 from .build import LIB_PATH
@@ -106,3 +107,31 @@ def config_set(key: str, value=None) -> None:
 def check(code: int) -> None:
     if code != 0:
         raise DscError(code, lib.dsc_last_error().decode("utf-8", "replace"))
+
+
+# ---- optional NVTX ranges around the kernels (K1/K2 attention, K3 region maps, K4 sampler step) --------
+NVTX = os.environ.get("DSC_NVTX", "") not in ("", "0")
+
+
+def nvtx(name: str):
+    """Decorator: wraps the call in an NVTX range ``dsc:<name>`` when DSC_NVTX=1 (for ncu --nvtx / nsys); otherwise returns
+    the function unchanged (no overhead)."""
+
+    def deco(fn):
+        if not NVTX:
+            return fn
+        import functools
+
+        import torch
+
+        @functools.wraps(fn)
+        def wrapped(*a, **kw):
+            torch.cuda.nvtx.range_push("dsc:" + name)
+            try:
+                return fn(*a, **kw)
+            finally:
+                torch.cuda.nvtx.range_pop()
+
+        return wrapped
+
+    return deco

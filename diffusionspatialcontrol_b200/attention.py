@@ -97,6 +97,7 @@ def _check_inputs(query, key):
         raise TypeError("query/key/value must share one dtype")
 
 
+@_lib.nvtx("xattn_stats")
 def score_stats(query: torch.Tensor, key: torch.Tensor, scale: Optional[float] = None,
                 workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Pass 1 alone.  Returns the workspace (uint8); bytes 8..12 hold the fp32 unbiased std of
@@ -178,6 +179,7 @@ def compact_region_map(W: torch.Tensor):
     return Wc, cols
 
 
+@_lib.nvtx("xattn_call")
 def region_attention(
     query: torch.Tensor,  # [B, H, L, D]
     key: torch.Tensor,  # [B, H, S, D]
@@ -254,6 +256,7 @@ def kv_image_bytes(B: int, H: int, D: int, S: int) -> int:
     return int(n.value)
 
 
+@_lib.nvtx("xattn_prepare_kv")
 def prepare_kv(key: torch.Tensor, value: torch.Tensor, cols, out: Optional[torch.Tensor] = None) -> PreparedKV:
     """key, value: [B, H, S, D] (views of the [B, S, H*D] projections); cols: ascending active key columns of the compact
     region map (``compact_region_map(W)[1]``).  ``out``: optional uint8 device buffer to (re)fill in place (static buffers
@@ -274,6 +277,7 @@ def prepare_kv(key: torch.Tensor, value: torch.Tensor, cols, out: Optional[torch
     return PreparedKV(out, cols, B, H, D, S, k.dtype)
 
 
+@_lib.nvtx("xattn_call_prepared")
 def region_attention_prepared(
     query: torch.Tensor,  # [B, H, L, D]
     kv: PreparedKV,

@@ -16,6 +16,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
+from . import _lib
 from ._lib import check, lib
 
 
@@ -52,6 +53,7 @@ def _spans(ids: Optional[Sequence[int]], phrases: List[List[int]]):
     return out, found
 
 
+@_lib.nvtx("region_downsample")
 def downsample_regions(maps: torch.Tensor, w_r: int, h_r: int):
     """maps: uint8 [R, Hpx, Wpx] on the device (255 = outside).  Returns (ds uint8 [R, h_r*w_r], any uint32 [R])."""
     if not maps.is_cuda or maps.dtype != torch.uint8 or maps.dim() != 3:
@@ -66,6 +68,7 @@ def downsample_regions(maps: torch.Tensor, w_r: int, h_r: int):
     return ds, any_set
 
 
+@_lib.nvtx("region_accumulate")
 def accumulate_regions(ds, any_set, weight, mask_outsides, spans, n_tok: int) -> torch.Tensor:
     """W[L_r, n_tok] fp32 on the device from the per-region binary maps and the token spans."""
     device = ds.device

@@ -45,6 +45,7 @@ def sigma_to_t(sigma: torch.Tensor, log_sigmas: torch.Tensor) -> torch.Tensor:
     return ((1 - w) * low_idx + w * high_idx).view(sigma.shape)
 
 
+@_lib.nvtx("dpmpp2m_step")
 def dpmpp2m_step(x: torch.Tensor, eps_uc: torch.Tensor, den_prev: torch.Tensor,
                  unet_in_next: Optional[torch.Tensor], sigma_prev: float, sigma: float, sigma_next: float,
                  cfg: float, first: bool) -> None:

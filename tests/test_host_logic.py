@@ -144,3 +144,17 @@ def test_static_region_maps_must_be_padded_device_tensors():
     proc = RegionAttnProcessor()
     with pytest.raises(ValueError):
         proc.register_static_map(torch.zeros(1, 8, 77))  # CPU / dense: would be copied at first use, i.e. frozen in a graph
+
+
+def test_nvtx_ranges_are_off_by_default_and_wrap_when_enabled(monkeypatch):
+    """DSC_NVTX=1 wraps the kernel entry points in NVTX ranges; by default the functions are returned as they are."""
+    from diffusionspatialcontrol_b200 import _lib
+
+    def f(x):
+        return x + 1
+
+    monkeypatch.setattr(_lib, "NVTX", False)
+    assert _lib.nvtx("k")(f) is f
+    monkeypatch.setattr(_lib, "NVTX", True)
+    g = _lib.nvtx("k")(f)
+    assert g is not f and g.__wrapped__ is f and g.__name__ == "f"
