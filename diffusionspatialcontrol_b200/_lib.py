@@ -42,6 +42,12 @@ SIGNATURES = {
          c_int, c_void_p, c_int, POINTER(ctypes.c_int32), c_void_p, c_float, c_void_p, c_void_p, POINTER(c_int64)]
         + [c_int] * 5 + [c_float, c_int, c_void_p],
     ),
+    "dsc_xattn_call_masked": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), c_void_p, c_int,
+         c_int, c_void_p, POINTER(c_int64), c_void_p, c_float, c_void_p, c_void_p, POINTER(c_int64)]
+        + [c_int] * 5 + [c_float, c_int, c_void_p],
+    ),
     "dsc_xattn_call": (
         c_int,
         [c_void_p, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), c_void_p, c_int,

@@ -99,17 +99,22 @@ def _check_inputs(query, key):
 
 @_lib.nvtx("xattn_stats")
 def score_stats(query: torch.Tensor, key: torch.Tensor, scale: Optional[float] = None,
-                workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+                workspace: Optional[torch.Tensor] = None, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Pass 1 alone.  Returns the workspace (uint8); bytes 8..12 hold the fp32 unbiased std of
-    ``scale * Q K^T`` over the whole call, see ``read_stats``.  Asynchronous."""
+    ``scale * Q K^T (+ attn_mask)`` over the whole call, see ``read_stats``.  Asynchronous.  ``attn_mask``: additive float
+    mask broadcastable to [B, H, L, S] (handed over as the dense fp32 tensor ``dsc_xattn_stats`` takes)."""
     _check_inputs(query, key)
     q, k = _as_bhxd(query, "query"), _as_bhxd(key, "key")
     B, H, L, D = q.shape
     S = k.shape[2]
     scale = 1.0 / math.sqrt(D) if scale is None else float(scale)
     ws = _checked_workspace(workspace, q.device, workspace_bytes(B, H, L, D, S))
+    dense = None
+    if attn_mask is not None:
+        dense = _mask_arg(attn_mask, B, H, L, S, q.device)[0].expand(B, H, L, S).contiguous()
     with torch.cuda.device(q.device):
-        check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), _I64x4(*q.stride()), _I64x4(*k.stride()), None,
+        check(lib.dsc_xattn_stats(q.data_ptr(), k.data_ptr(), _I64x4(*q.stride()), _I64x4(*k.stride()),
+                                  None if dense is None else dense.data_ptr(),
                                   B, H, L, D, S, scale, _DTYPES[q.dtype], ws.data_ptr(), _stream_ptr(q.device)))
     return ws
 
@@ -191,11 +196,18 @@ def region_attention(
     workspace: Optional[torch.Tensor] = None,
     compact=None,  # optional (Wc, cols) from compact_region_map(region_state)
 ) -> torch.Tensor:
-    """softmax(scale*QK^T + sigma*std(scale*QK^T)*W) V  ->  [B, H, L, D] (a view of a fresh [B, L, H*D])."""
+    """softmax(a + sigma*std(a)*W) V with a = scale*QK^T (+ M)  ->  [B, H, L, D] (a view of a fresh [B, L, H*D]).
+
+    ``attn_mask``: optional ADDITIVE float mask M, any shape that broadcasts to [B, H, L, S] (``[S]``, ``[L, S]``,
+    ``[B, H, 1, S]`` ...).  The std is taken over the masked scores, as the reference's weight_func sees them
+    (attention_modify.py:90-95; baddbmm variant :39-70).  A BOOL mask is ignored: the reference function never applies
+    one (:86-87 rewrites the mask tensor and adds nothing) -- its output with a bool mask equals its output without.
+    This function accepts every broadcastable float mask; which masks reach it is the processors' business (the reference's
+    SDPA-style processor raises for its own 4-D mask, the baddbmm one adds it: see ``RegionAttnProcessor._region_mask``).
+    Masked calls run as two launches on the mma.sync kernels (``dsc_xattn_call_masked``)."""
     _check_inputs(query, key)
-    if attn_mask is not None:
-        raise NotImplementedError("additive attention masks are not implemented on the region path "
-                                  "(SD-1.5 cross-attention never passes one)")
+    if attn_mask is not None and attn_mask.dtype == torch.bool:
+        attn_mask = None  # reference :86-87: never added to the bias
     q, k, v = _as_bhxd(query, "query"), _as_bhxd(key, "key"), _as_bhxd(value, "value")
     B, H, L, D = q.shape
     S = k.shape[2]
@@ -227,10 +239,33 @@ def region_attention(
                 raise ValueError("compact region map must be a contiguous fp32 [B', L, 20] tensor on the query's device")
             wc_ptr, n_act = Wc.data_ptr(), len(cols)
             cols_arr = (ctypes.c_int32 * n_act)(*cols)
+        if attn_mask is not None:
+            m, m_str = _mask_arg(attn_mask, B, H, L, S, q.device)
+            check(lib.dsc_xattn_call_masked(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), W.shape[0],
+                                            W.stride(1), m.data_ptr(), _I64x3(*m_str), sigma_ptr, sigma_host, ws.data_ptr(),
+                                            out.data_ptr(), _I64x3(*out.stride()), B, H, L, D, S, scale, dt, st))
+            return out.view(B, L, H, D).transpose(1, 2)
         check(lib.dsc_xattn_call_cw(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, W.data_ptr(), W.shape[0],
                                     W.stride(1), wc_ptr, n_act, cols_arr, sigma_ptr, sigma_host, ws.data_ptr(),
                                     out.data_ptr(), _I64x3(*out.stride()), B, H, L, D, S, scale, dt, st))
     return out.view(B, L, H, D).transpose(1, 2)
+
+
+def _mask_arg(attn_mask: torch.Tensor, B: int, H: int, L: int, S: int, device):
+    """fp32 device copy of an additive mask that broadcasts to [B, H, L, S] + its (B, H, L) element strides (0 = broadcast)."""
+    if not attn_mask.is_floating_point():
+        raise TypeError(f"attn_mask must be a float (additive) or bool tensor, got {attn_mask.dtype}")
+    if attn_mask.dim() > 4:
+        raise ValueError(f"attn_mask must broadcast to [B, H, L, S], got {tuple(attn_mask.shape)}")
+    m = attn_mask.reshape((1,) * (4 - attn_mask.dim()) + tuple(attn_mask.shape))
+    for have, want, name in zip(m.shape, (B, H, L, S), "BHLS"):
+        if have not in (1, want):
+            raise ValueError(f"attn_mask {tuple(attn_mask.shape)} does not broadcast to [B={B}, H={H}, L={L}, S={S}] (dim {name})")
+    if m.shape[3] == 1:
+        m = m.expand(m.shape[0], m.shape[1], m.shape[2], S)
+    m = m.to(device=device, dtype=torch.float32).contiguous()
+    strides = [0 if m.shape[d] == 1 else m.stride(d) for d in range(3)]
+    return m, strides
 
 
 # ---- prepared K / V (the fast form for the SD-1.5 shapes) ---------------------------------------------------------------

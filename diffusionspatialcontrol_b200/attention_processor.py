@@ -212,6 +212,19 @@ class RegionAttnProcessor:
     ) -> torch.Tensor:
         return self._forward(attn, hidden_states, encoder_hidden_states, attention_mask, temb, region_prompt)
 
+    def _region_mask(self, attention_mask, query):
+        """The mask as the reference's SDPA-style region function treats it (attention_modify.py:84-89), probed on the
+        unmodified module (tests/test_oracle_attention.py): a BOOL mask is never applied (:86-87 only rewrites the mask
+        tensor), and a float mask is added IN PLACE into a [L, S] bias (:89) -- which raises for the 4-D
+        [B, heads, -1, S] tensor this processor builds (:452), whatever its values.  Same behaviour here: None for a bool
+        mask, the reference's RuntimeError for a float one.  (The baddbmm processor adds its mask: see the subclass.)"""
+        if attention_mask is None or attention_mask.dtype == torch.bool:
+            return None
+        L, S = query.shape[-2], attention_mask.shape[-1]
+        raise RuntimeError(f"output with shape [{L}, {S}] doesn't match the broadcast shape {list(attention_mask.shape[:2]) + [L, S]}"
+                           " (the reference adds a float attention mask in place into its [L, S] bias, attention_modify.py:89;"
+                           " use the baddbmm processor or region_attention(attn_mask=...) for an additive mask)")
+
     def _forward(self, attn, hidden_states, encoder_hidden_states, attention_mask, temb, region_prompt, ip_branch=None):
         """The processor body (reference attention_modify.py:425-503).  ``ip_branch(hidden, query, batch, head_dim)``,
         when given, adds the IP-Adapter image-prompt terms before the output projection (:640-682)."""
@@ -268,9 +281,11 @@ class RegionAttnProcessor:
             self._check_weight_func(weight_func)
             w = region_state[img_sequence_length]  # KeyError for an unknown resolution, like the reference (:481)
             w_dev = self._device_map(w, query.device)
+            attention_mask = self._region_mask(attention_mask, query)  # what this processor's region branch does with a mask
             if self._map_is_zero(w, query.device):
                 hidden_states = F.scaled_dot_product_attention(
-                    query, key, value, attn_mask=attention_mask, dropout_p=0.0, is_causal=False)
+                    query, key, value, attn_mask=attention_mask, dropout_p=0.0, is_causal=False,
+                    scale=self._score_scale(attn, head_dim))
             else:
                 compact = self._map_compact(w, query.device)
                 if (attention_mask is None and compact is not None and query.dtype in (torch.float16, torch.bfloat16)
@@ -322,6 +337,17 @@ class RegionAttnProcessorBaddbmm(RegionAttnProcessor):
 
     def _score_scale(self, attn, head_dim: int) -> Optional[float]:
         return float(attn.scale)
+
+    def _region_mask(self, attention_mask, query):
+        """``get_attention_scores`` (:39-70) takes the prepared mask as the ``baddbmm`` input with beta = 1: a real additive
+        mask M, a = M + scale Q K^T, and the weight_func's std is over that (:166).  A mask of another dtype than the query
+        (a bool mask included) makes ``torch.baddbmm`` raise in the reference; here too."""
+        if attention_mask is None:
+            return None
+        if attention_mask.dtype != query.dtype:
+            raise RuntimeError(f"expected the attention mask in the query's dtype {query.dtype}, got {attention_mask.dtype} "
+                               "(torch.baddbmm input, attention_modify.py:57-63)")
+        return attention_mask
 
 
 def ip_mask_downsample(mask: torch.Tensor, batch_size: int, num_queries: int, value_embed_dim: int) -> torch.Tensor:

@@ -153,12 +153,47 @@ int dsc_xattn_workspace_bytes(int B, int H, int L, int D, int S, size_t* out) {
   return DSC_OK;
 }
 
+}  // extern "C"
+
+namespace dsc {
+// Additive attention mask of a call: fp32, element (b, h, l, s) at m[b * sb + h * sh + l * sl + s] (0 = broadcast).
+struct MaskArg {
+  const float* m = nullptr;
+  long long sb = 0, sh = 0, sl = 0;
+};
+static int check_mask(const MaskArg& mk) {
+  if (!mk.m) return DSC_OK;
+  if ((reinterpret_cast<uintptr_t>(mk.m) & 3) != 0) return fail(DSC_ERR_LAYOUT, "mask must be 4-byte aligned");
+  if (mk.sb < 0 || mk.sh < 0 || mk.sl < 0) return fail(DSC_ERR_LAYOUT, "mask strides must be >= 0 (0 broadcasts a dimension)");
+  return DSC_OK;
+}
+static int stats_impl(const void* q, const void* k, const int64_t q_str[4], const int64_t k_str[4], const MaskArg& mk, int B, int H,
+                      int L, int D, int S, float scale, int dtype, void* workspace, void* stream);
+}  // namespace dsc
+
+extern "C" {
+
 int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const int64_t k_str[4],
                     const void* mask_or_null, int B, int H, int L, int D, int S, float scale, int dtype,
                     void* workspace, void* stream) {
+  MaskArg mk;
+  if (mask_or_null) {  // dense fp32 [B, H, L, S]
+    mk.m = static_cast<const float*>(mask_or_null);
+    mk.sl = S;
+    mk.sh = static_cast<long long>(L) * S;
+    mk.sb = static_cast<long long>(H) * L * S;
+  }
+  return stats_impl(q, k, q_str, k_str, mk, B, H, L, D, S, scale, dtype, workspace, stream);
+}
+
+}  // extern "C"
+
+namespace dsc {
+static int stats_impl(const void* q, const void* k, const int64_t q_str[4], const int64_t k_str[4], const MaskArg& mk, int B, int H,
+                      int L, int D, int S, float scale, int dtype, void* workspace, void* stream) {
   int rc = check_dims(B, H, L, D, S, dtype);
   if (rc) return rc;
-  if (mask_or_null) return fail(DSC_ERR_UNSUPPORTED, "additive attention masks are not implemented");
+  if ((rc = check_mask(mk))) return rc;
   if (!workspace) return fail(DSC_ERR_INVALID_ARGUMENT, "workspace is null");
   if ((rc = check_bhxd("q", q, q_str, D))) return rc;
   if ((rc = check_bhxd("k", k, k_str, D))) return rc;
@@ -171,6 +206,10 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
   p.k_sb = k_str[0];
   p.k_ss = k_str[2];
   p.scale = scale;
+  p.mask = mk.m;  // with a mask: the mma.sync kernels, a = scale * Q K^T + M summed per element
+  p.m_sb = mk.sb;
+  p.m_sh = mk.sh;
+  p.m_sl = mk.sl;
   p.ws = static_cast<Workspace*>(workspace);
   const int C = n_chunks(S);
   if (static_cast<long long>(stats_grid(p.total)) * C > kMaxPartials)
@@ -180,7 +219,8 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
   cudaError_t e = cudaSuccess;
   if (C == 1) {
     const bool gram = config().stats_impl == kImplGram;
-    if (gram && gram_supports(D, S)) e = run_stats_gram(p, D, dtype, static_cast<cudaStream_t>(stream));
+    if (mk.m) e = run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
+    else if (gram && gram_supports(D, S)) e = run_stats_gram(p, D, dtype, static_cast<cudaStream_t>(stream));
     else
       e = use_tc5(D, true) ? run_stats_tc5(p, D, dtype, static_cast<cudaStream_t>(stream))
                            : run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
@@ -190,12 +230,16 @@ int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4], const 
       p.k = static_cast<const char*>(k) + static_cast<size_t>(c) * DSC_MAX_KEYS * k_str[2] * esz;
       p.S = (c == C - 1) ? S - c * DSC_MAX_KEYS : DSC_MAX_KEYS;
       p.chunk = c;
+      p.m_col0 = c * DSC_MAX_KEYS;
       p.fold_chunks = (c == C - 1) ? C : 0;
       e = run_stats(p, D, dtype, static_cast<cudaStream_t>(stream));
     }
   }
   return e == cudaSuccess ? DSC_OK : cuda_fail(e, "dsc_xattn_stats");
 }
+}  // namespace dsc
+
+extern "C" {
 
 // Which form dsc_xattn_call takes: 0 = two launches, 1 = single launch with Q resident in shared memory (mma.sync family,
 // small problems), 2 = single launch, two phases over the tile list (tcgen05 family, D = 40 / 80).
@@ -221,8 +265,9 @@ static int forward_impl(const void* q, const void* k, const void* v, const int64
                         const int64_t v_str[4], const float* W, int Bw, int w_pitch, const float* sigma_dev_or_null,
                         float sigma_host, const void* workspace, void* out, const int64_t o_str[3], int B, int H, int L, int D,
                         int S, float scale, int dtype, void* stream, bool with_stats, const char* who,
-                        const CompactW& cw = CompactW()) {
+                        const CompactW& cw = CompactW(), const MaskArg& mk = MaskArg()) {
   int rc = check_dims(B, H, L, D, S, dtype);
+  if (!rc) rc = check_mask(mk);
   if (cw.wc != nullptr && cw.n > 0) {
     if (cw.n > DSC_MAX_COMPACT_COLS || !cw.cols || !aligned16(cw.wc))
       return fail(DSC_ERR_INVALID_ARGUMENT, "compact map: need 1..%d columns, a column list and a 16-byte aligned base", DSC_MAX_COMPACT_COLS);
@@ -267,6 +312,10 @@ static int forward_impl(const void* q, const void* k, const void* v, const int64
   p.o_sb = o_str[0];
   p.o_sl = o_str[1];
   p.ws = const_cast<Workspace*>(static_cast<const Workspace*>(workspace));
+  p.mask = mk.m;
+  p.m_sb = mk.sb;
+  p.m_sh = mk.sh;
+  p.m_sl = mk.sl;
   if (cw.wc != nullptr && cw.n > 0) {
     p.wc = cw.wc;
     p.n_active = cw.n;
@@ -276,7 +325,7 @@ static int forward_impl(const void* q, const void* k, const void* v, const int64
   cudaError_t e = cudaSuccess;
   if (with_stats) {
     // one attention call: a single cooperative launch when the problem fits on chip, else pass 1 then pass 2
-    const int form = call_form(B, H, L, D, S);
+    const int form = mk.m ? 0 : call_form(B, H, L, D, S);  // a mask: pass 1 then pass 2 on the mma.sync kernels
     if (form != 0) {
       p.n_total = static_cast<double>(B) * H * static_cast<double>(L) * S;
       p.fold_chunks = 1;
@@ -285,11 +334,11 @@ static int forward_impl(const void* q, const void* k, const void* v, const int64
       (void)cudaGetLastError();  // the device cannot hold the whole grid right now (e.g. shared with another context):
       e = cudaSuccess;           // nothing was launched -- take the two-launch form below
     }
-    rc = dsc_xattn_stats(q, k, q_str, k_str, nullptr, B, H, L, D, S, scale, dtype, const_cast<void*>(workspace), stream);
+    rc = stats_impl(q, k, q_str, k_str, mk, B, H, L, D, S, scale, dtype, const_cast<void*>(workspace), stream);
     if (rc) return rc;
   }
   if (C == 1) {
-    e = use_tc5(D, false) ? run_forward_tc5(p, D, dtype, st) : run_forward(p, D, dtype, st);
+    e = (!mk.m && use_tc5(D, false)) ? run_forward_tc5(p, D, dtype, st) : run_forward(p, D, dtype, st);
   } else {
     // per key chunk: softmax over the chunk's keys (with the std of the WHOLE call) -> dense chunk output + log2-sum-exp
     // in the workspace (layout: stats | C chunk outputs | C lse planes; see dsc_xattn_workspace_bytes); then one merge
@@ -302,6 +351,7 @@ static int forward_impl(const void* q, const void* k, const void* v, const int64
       p.v = static_cast<const char*>(v) + static_cast<size_t>(c) * DSC_MAX_KEYS * v_str[2] * 2;
       p.S = (c == C - 1) ? S - c * DSC_MAX_KEYS : DSC_MAX_KEYS;
       p.w_col0 = c * DSC_MAX_KEYS;
+      p.m_col0 = c * DSC_MAX_KEYS;
       p.out = chunk_out + c * chunk_out_bytes(B, H, L, D);
       p.o_sb = static_cast<long long>(L) * H * D;
       p.o_sl = static_cast<long long>(H) * D;
@@ -347,6 +397,20 @@ int dsc_xattn_call_cw(const void* q, const void* k, const void* v, const int64_t
   cw.cols = active_cols;
   return forward_impl(q, k, v, q_str, k_str, v_str, W, Bw, w_pitch, sigma_dev_or_null, sigma_host, workspace, out, o_str, B, H,
                       L, D, S, scale, dtype, stream, true, "dsc_xattn_call_cw", cw);
+}
+
+int dsc_xattn_call_masked(const void* q, const void* k, const void* v, const int64_t q_str[4], const int64_t k_str[4],
+                          const int64_t v_str[4], const float* W, int Bw, int w_pitch, const float* mask, const int64_t mask_str[3],
+                          const float* sigma_dev_or_null, float sigma_host, void* workspace, void* out, const int64_t o_str[3], int B,
+                          int H, int L, int D, int S, float scale, int dtype, void* stream) {
+  if (!mask || !mask_str) return fail(DSC_ERR_INVALID_ARGUMENT, "dsc_xattn_call_masked: mask / mask_str is null (use dsc_xattn_call)");
+  MaskArg mk;
+  mk.m = mask;
+  mk.sb = mask_str[0];
+  mk.sh = mask_str[1];
+  mk.sl = mask_str[2];
+  return forward_impl(q, k, v, q_str, k_str, v_str, W, Bw, w_pitch, sigma_dev_or_null, sigma_host, workspace, out, o_str, B, H, L, D,
+                      S, scale, dtype, stream, true, "dsc_xattn_call_masked", CompactW(), mk);
 }
 
 int dsc_xattn_prepared_supported(int H, int D, int S) { return x3_supports(H, D, S) ? 1 : 0; }

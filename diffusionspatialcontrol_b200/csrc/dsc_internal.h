@@ -78,7 +78,13 @@ struct XattnParams {
   // [b * tiles_q + min(b, tiles_r), +tiles_q + (b < tiles_r))
   uint32_t tiles_q, tiles_r;
   FastDiv div_nsl, div_nhg;
-  int handoff;           // 3-warpgroup tcgen05 kernels, both passes of one call: the std goes from pass 1 to pass 2 through the handoff slots
+  int handoff;           // 3-warpgroup tcgen05 kernels, both passes of one call: the std goes from pass 1 to pass 2 through the handoff slots  // additive attention mask M (optional; mma.sync kernels, dsc_xattn_call_masked): fp32, element (b, h, l, s) at
+  // mask[b * m_sb + h * m_sh + l * m_sl + m_col0 + s]; a zero stride broadcasts that dimension.  a = qk_scale * Q K^T + M:
+  // pass 1 then sums a itself (and finalises with scale = 1), pass 2 adds M next to beta * W
+  const float* mask;
+  long long m_sb, m_sh, m_sl;
+  int m_col0;      // first mask column of this key chunk (long prompts)
+  float qk_scale;  // masked pass 1: the score scale (p.scale is 1 there: the partial sums are already scaled)
 };
 
 // Kernel-selection overrides (A/B runs, tests).  Filled ONCE from the environment when the library is loaded

@@ -230,7 +230,9 @@ __device__ __forceinline__ void publish_stats(const XattnParams& p, double dsum,
 // =============================================================================================
 // pass 1
 // =============================================================================================
-template <typename T, int D>
+// MASKED: a = qk_scale * Q K^T + M (additive attention mask, attention_modify.py:39-70 / :84-91) -- the sums are taken
+// over a itself (p.scale is 1 for the fold), M read per element through its (b, h, l) strides.
+template <typename T, int D, bool MASKED = false>
 __global__ void __launch_bounds__(256, 1)
 xattn_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k) {
   using TL = Tile<D>;
@@ -305,7 +307,21 @@ xattn_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q
         float acc[10][4];
         qk_tile<T, D>(acc, qs + h * D * 2, sK + h * D * 2, lane);
         float fs = 0.f, fq = 0.f;
-        if (rows == TL::ROWS) {
+        if constexpr (MASKED) {
+          // pad keys and rows beyond L are not scores: they carry no mask value and drop out here
+          const float* mb = p.mask + sg.b * p.m_sb + static_cast<long long>(sg.hg * TL::G + h) * p.m_sh +
+                            static_cast<long long>(l0) * p.m_sl + p.m_col0;
+#pragma unroll
+          for (int j = 0; j < 10; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int col = 8 * j + 2 * (lane & 3) + (i & 1), row = (lane >> 2) + 8 * (i >> 1);
+              float v = 0.f;
+              if (row < rows && col < p.S) v = fmaf(acc[j][i], p.qk_scale, __ldg(mb + row * p.m_sl + col));
+              fs += v;
+              fq = fmaf(v, v, fq);
+            }
+        } else if (rows == TL::ROWS) {
 #pragma unroll
           for (int j = 0; j < 10; ++j)
 #pragma unroll
@@ -507,10 +523,13 @@ xattn_gram_stats_kernel(const XattnParams p, const __grid_constant__ CUtensorMap
 // One 16-row slice, all heads of the group: logits = S*scale + beta*W (log2 domain), softmax over the keys, O = P V.
 // Q_h columns of the slice (shared memory, qsm / sQ) are overwritten by O_h.  lse0: optional log2-sum-exp output of
 // (first head of the group, first row of the slice); heads are L floats apart.
-template <typename T, int D>
+// MASKED: the additive attention mask of (first head of the group, first row of the slice, first key of the chunk) is at
+// m0; heads are m_sh, rows m_sl floats apart (0 = broadcast); logits = S*scale + M + beta*W.
+template <typename T, int D, bool MASKED = false>
 __device__ __forceinline__ void softmax_pv_slice(int nheads, int S, float beta_l2, float scale_l2, uint32_t sQ, uint32_t sK,
                                                  uint32_t sV, const float* wsm, int wp, unsigned char* qsm, float* lse0, int L,
-                                                 int rows, int lane) {
+                                                 int rows, int lane, const float* m0 = nullptr, long long m_sh = 0,
+                                                 long long m_sl = 0) {
   using TL = Tile<D>;
   constexpr int PITCH = TL::PITCH;
   constexpr int ND = TL::ND;
@@ -538,6 +557,13 @@ __device__ __forceinline__ void softmax_pv_slice(int nheads, int S, float beta_l
       acc[j][1] = fmaf(acc[j][1], scale_l2, bw[j][1]);
       acc[j][2] = fmaf(acc[j][2], scale_l2, bw[j][2]);
       acc[j][3] = fmaf(acc[j][3], scale_l2, bw[j][3]);
+      if constexpr (MASKED) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = 8 * j + 2 * t + (i & 1), row = g + 8 * (i >> 1);
+          if (row < rows && col < S) acc[j][i] = fmaf(__ldg(m0 + h * m_sh + row * m_sl + col), kLog2e, acc[j][i]);
+        }
+      }
       mx0 = fmaxf(mx0, fmaxf(acc[j][0], acc[j][1]));
       mx1 = fmaxf(mx1, fmaxf(acc[j][2], acc[j][3]));
     }
@@ -587,7 +613,7 @@ __device__ __forceinline__ void softmax_pv_slice(int nheads, int S, float beta_l
 // =============================================================================================
 // pass 2
 // =============================================================================================
-template <typename T, int D>
+template <typename T, int D, bool MASKED = false>
 __global__ void __launch_bounds__(256, 1)
 xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_w) {
@@ -689,9 +715,12 @@ xattn_forward_kernel(const XattnParams p, const __grid_constant__ CUtensorMap tm
         beta_l2 = sigma * __ldcg(&p.ws->std_unbiased) * kLog2e;
         have_beta = true;
       }
-      softmax_pv_slice<T, D>(sg.nheads, p.S, beta_l2, scale_l2, sQ, sK, sV, wsm, wp, qsm,
-                             p.lse ? p.lse + (static_cast<long long>(sg.b) * p.H + sg.hg * TL::G) * p.L + l0 : nullptr, p.L, rows,
-                             lane);
+      const float* m0 = nullptr;
+      if constexpr (MASKED)
+        m0 = p.mask + sg.b * p.m_sb + static_cast<long long>(sg.hg * TL::G) * p.m_sh + static_cast<long long>(l0) * p.m_sl + p.m_col0;
+      softmax_pv_slice<T, D, MASKED>(sg.nheads, p.S, beta_l2, scale_l2, sQ, sK, sV, wsm, wp, qsm,
+                                     p.lse ? p.lse + (static_cast<long long>(sg.b) * p.H + sg.hg * TL::G) * p.L + l0 : nullptr, p.L,
+                                     rows, lane, m0, p.m_sh, p.m_sl);
 
       // O slice: shared -> global through the TMA, one row per lane
       fence_proxy_async();
@@ -889,14 +918,19 @@ static bool make_map_w16(CUtensorMap* m, const XattnParams& p, int box_cols, int
   return true;
 }
 
-template <typename T, int D>
-static cudaError_t launch_stats(const XattnParams& p, cudaStream_t st) {
+template <typename T, int D, bool MASKED>
+static cudaError_t launch_stats_m(const XattnParams& p_in, cudaStream_t st) {
   using TL = Tile<D>;
+  XattnParams p = p_in;
+  if (MASKED) {  // the kernel sums a = qk_scale * Q K^T + M itself: the fold must not scale again
+    p.qk_scale = p_in.scale;
+    p.scale = 1.f;
+  }
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(xattn_stats_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(xattn_stats_kernel<T, D, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TL::STATS_SMEM);
     if (e != cudaSuccess) return e;
     configured_dev = dev;
@@ -905,8 +939,12 @@ static cudaError_t launch_stats(const XattnParams& p, cudaStream_t st) {
   if (!make_map32(&tm_q, p.q, p.H * D, p.L, p.B, p.q_sl, p.q_sb, TL::PITCH / 4, TL::ROWS) ||
       !make_map32(&tm_k, p.k, p.H * D, p.S, p.B, p.k_ss, p.k_sb, TL::PITCH / 4, TL::KV_ROWS))
     return cudaErrorInvalidValue;
-  xattn_stats_kernel<T, D><<<grid_for(p.total), 256, TL::STATS_SMEM, st>>>(p, tm_q, tm_k);
+  xattn_stats_kernel<T, D, MASKED><<<grid_for(p.total), 256, TL::STATS_SMEM, st>>>(p, tm_q, tm_k);
   return cudaGetLastError();
+}
+template <typename T, int D>
+static cudaError_t launch_stats(const XattnParams& p, cudaStream_t st) {
+  return p.mask ? launch_stats_m<T, D, true>(p, st) : launch_stats_m<T, D, false>(p, st);
 }
 
 template <typename T, int D>
@@ -987,15 +1025,15 @@ static cudaError_t launch_fused(const XattnParams& p_in, cudaStream_t st) {
   return cudaLaunchKernelEx(&cfg, xattn_fused_kernel<T, D>, p, tm_q, tm_k, tm_v, tm_w);
 }
 
-template <typename T, int D>
-static cudaError_t launch_forward(const XattnParams& p_in, cudaStream_t st) {
+template <typename T, int D, bool MASKED>
+static cudaError_t launch_forward_m(const XattnParams& p_in, cudaStream_t st) {
   XattnParams p = p_in;
   using TL = Tile<D>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(xattn_forward_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(xattn_forward_kernel<T, D, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TL::FWD_SMEM);
     if (e != cudaSuccess) return e;
     configured_dev = dev;
@@ -1018,7 +1056,11 @@ static cudaError_t launch_forward(const XattnParams& p_in, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = config().no_pdl ? 0 : 1;  // may overlap the tail of pass 1 (griddepcontrol.wait before beta)
-  return cudaLaunchKernelEx(&cfg, xattn_forward_kernel<T, D>, p, tm_q, tm_k, tm_v, tm_w);
+  return cudaLaunchKernelEx(&cfg, xattn_forward_kernel<T, D, MASKED>, p, tm_q, tm_k, tm_v, tm_w);
+}
+template <typename T, int D>
+static cudaError_t launch_forward(const XattnParams& p, cudaStream_t st) {
+  return p.mask ? launch_forward_m<T, D, true>(p, st) : launch_forward_m<T, D, false>(p, st);
 }
 
 int heads_per_group(int D) {

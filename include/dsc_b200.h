@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSC_VERSION 107 /* major*10000 + minor*100 + patch */
+#define DSC_VERSION 108 /* major*10000 + minor*100 + patch */
 
 #define DSC_DTYPE_F16 0
 #define DSC_DTYPE_BF16 1
@@ -75,10 +75,11 @@ int dsc_xattn_workspace_bytes(int B, int H, int L, int D, int S, size_t* out /*H
  * multiples of 8 elements, base pointers 16-byte aligned -- i.e. the [B, L, H*D] projection output
  * viewed as heads, which is exactly what the reference processor produces
  * (attention_modify.py:471-474).  D in {40,64,80,128,160}; 1 <= S <= DSC_MAX_KEYS_TOTAL.
- * mask_or_null: additive attention mask (attention_modify.py:84-89); only NULL is accepted, anything else is refused
- * with DSC_ERR_UNSUPPORTED on every entry point of the region path.  Decision, not omission: SD-1.5 never passes one,
- * and the reference's own behaviour with one is not worth reproducing (a -inf mask makes qk.std() NaN and the
- * beta-term poisons every row; a finite mask changes the std of the masked scores in both passes). */
+ * mask_or_null: additive attention mask M as a dense fp32 [B, H, L, S] device tensor, or NULL (every SD-1.5 call).  With a
+ * mask the statistics are those of a = scale * Q K^T + M (the tensor the reference's weight_func sees: attention_modify.py:90-95,
+ * baddbmm variant :39-70 with beta = 1); pad keys and rows beyond L carry no mask value.  Masked calls run on the mma.sync
+ * kernels (xattn_kernels.cu).  See dsc_xattn_call_masked for strided / broadcast masks and for what the reference's two
+ * processors do with a mask. */
 int dsc_xattn_stats(const void* q, const void* k, const int64_t q_str[4] /*HOST*/, const int64_t k_str[4] /*HOST*/,
                     const void* mask_or_null, int B, int H, int L, int D, int S, float scale, int dtype,
                     void* workspace, void* stream);
@@ -128,6 +129,25 @@ int dsc_xattn_call_cw(const void* q, const void* k, const void* v, const int64_t
                       const float* Wc, int n_active, const int32_t* active_cols /*HOST*/, const float* sigma_dev_or_null,
                       float sigma_host, void* workspace, void* out, const int64_t o_str[3] /*HOST*/, int B, int H, int L,
                       int D, int S, float scale, int dtype, void* stream);
+
+/* dsc_xattn_call with an additive attention mask: out = softmax(a + sigma * std(a) * W) V, a = scale Q K^T + M.
+ * mask: fp32 device pointer, element (b, h, l, s) at mask[b * mask_str[0] + h * mask_str[1] + l * mask_str[2] + s] (element
+ * strides >= 0; 0 broadcasts the dimension: {0, 0, 0} is one [S] key bias, {H*S, S, 0} the [B*H, 1, S] tensor diffusers'
+ * prepare_attention_mask returns, {H*L*S, L*S, S} a dense [B, H, L, S]); 4-byte aligned; values may be -inf (a fully masked
+ * row is NaN, as in the reference).  The std is taken over a INCLUDING M, exactly as the reference does: its weight_func
+ * receives the masked scores (attention_modify.py:90-95; baddbmm variant :39-70, :166).
+ * What the reference's processors do with a mask (probed on the unmodified module, tests/test_oracle_attention.py):
+ *   AttnProcessor (baddbmm, :107-207): M is the baddbmm input, beta = 1 -- this entry point.
+ *   AttnProcessor2_0 (:414-503): a BOOL mask is never applied (:86-87 only rewrites the mask itself), a float mask is added
+ *   in place into a [L, S] bias (:89), which raises for the 4-D tensor the processor builds (:452) and works only for masks
+ *   that broadcast into [L, S] through the bare function (:74) -- mask_str = {0, 0, S or 0}.
+ * Two launches (pass 1, pass 2) on the mma.sync kernels, any supported D and S; M is read per element through the strides
+ * (a rarely used path: SD-1.5 passes no cross-attention mask). */
+int dsc_xattn_call_masked(const void* q, const void* k, const void* v, const int64_t q_str[4] /*HOST*/,
+                          const int64_t k_str[4] /*HOST*/, const int64_t v_str[4] /*HOST*/, const float* W, int Bw, int w_pitch,
+                          const float* mask, const int64_t mask_str[3] /*HOST*/, const float* sigma_dev_or_null, float sigma_host,
+                          void* workspace, void* out, const int64_t o_str[3] /*HOST*/, int B, int H, int L, int D, int S,
+                          float scale, int dtype, void* stream);
 
 /* ---- prepared K / V: the fast form of the call for the SD-1.5 shapes ---------------------------------------------------
  * K and V of a cross-attention layer are projections of the text embeddings: they do not change during a generation

@@ -63,15 +63,22 @@ def score_std(query: torch.Tensor, key: torch.Tensor, scale: Optional[float] = N
     return (query @ key.transpose(-2, -1) * scale_factor).std()
 
 
-def processor_forward(attn, hidden_states, encoder_hidden_states=None, region_prompt=None, ip_branch=None):
-    """attention_modify.py:414-503 for the SD-1.5 case (3-D input, no mask, no norms).
+def processor_forward(attn, hidden_states, encoder_hidden_states=None, region_prompt=None, ip_branch=None,
+                      attention_mask=None):
+    """attention_modify.py:414-503 for the SD-1.5 case (3-D input, no norms).
 
-    ``attn`` is duck-typed: to_q/to_k/to_v/to_out, heads, residual_connection, rescale_output_factor.
+    ``attn`` is duck-typed: to_q/to_k/to_v/to_out, heads, residual_connection, rescale_output_factor (and
+    prepare_attention_mask when a mask is given: :448-452 -- the mask reaches the region function as a 4-D
+    [B, heads, -1, S] tensor, which that function ignores when bool (:86-87) and cannot add when float (:89 raises)).
     """
     residual = hidden_states
     img_sequence_length = hidden_states.shape[1]
     is_xattn = encoder_hidden_states is not None and region_prompt is not None
     batch_size = hidden_states.shape[0]
+    if attention_mask is not None:
+        sequence_length = (hidden_states if encoder_hidden_states is None else encoder_hidden_states).shape[1]
+        attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
+        attention_mask = attention_mask.view(batch_size, attn.heads, -1, attention_mask.shape[-1])
     query = attn.to_q(hidden_states)
     ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
     key, value = attn.to_k(ctx), attn.to_v(ctx)
@@ -82,9 +89,10 @@ def processor_forward(attn, hidden_states, encoder_hidden_states=None, region_pr
     value = value.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
     if is_xattn and isinstance(region_prompt["region_state"], dict):
         w = region_prompt["region_state"][img_sequence_length].to(query.device)
-        out = region_attention(query, key, value, w, region_prompt["sigma"], weight_fn=region_prompt["weight_func"])
+        out = region_attention(query, key, value, w, region_prompt["sigma"], attn_mask=attention_mask,
+                               weight_fn=region_prompt["weight_func"])
     else:
-        out = F.scaled_dot_product_attention(query, key, value, dropout_p=0.0, is_causal=False)
+        out = F.scaled_dot_product_attention(query, key, value, attn_mask=attention_mask, dropout_p=0.0, is_causal=False)
     out = out.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
     if ip_branch is not None:  # IP-Adapter image-prompt terms (attention_modify.py:640-682), see oracle/ip_adapter.py
         out = ip_branch(out, query, batch_size, head_dim)
@@ -95,15 +103,20 @@ def processor_forward(attn, hidden_states, encoder_hidden_states=None, region_pr
     return out / getattr(attn, "rescale_output_factor", 1.0)
 
 
-def processor_forward_baddbmm(attn, hidden_states, encoder_hidden_states=None, region_prompt=None):
+def processor_forward_baddbmm(attn, hidden_states, encoder_hidden_states=None, region_prompt=None, attention_mask=None):
     """attention_modify.py:107-207 (``AttnProcessor``, the ``torch.baddbmm`` variant) with ``get_attention_scores``
-    (:39-70) for the SD-1.5 case (3-D input, no mask, no norms, no upcasts).  Differences from the SDPA-style processor
+    (:39-70) for the SD-1.5 case (3-D input, no norms, no upcasts).  A mask (prepared by ``attn.prepare_attention_mask``,
+    :144: [B*heads, 1 or L, S] in the query's dtype) is the ``baddbmm`` input with beta = 1 (:52-63): a true additive mask,
+    and the std the weight_func sees is over the masked scores (:166).  Differences from the SDPA-style processor
     that are part of the contract: scores are ``alpha = attn.scale`` times ``Q K^T`` formed by ``torch.baddbmm`` over a
     [B*H, L, S] batch (the std the weight_func sees is over that tensor: same numbers, another shape), softmax + ``bmm``.
     """
     residual = hidden_states
     img_sequence_length = hidden_states.shape[1]
     is_xattn = encoder_hidden_states is not None and region_prompt is not None
+    if attention_mask is not None:
+        sequence_length = (hidden_states if encoder_hidden_states is None else encoder_hidden_states).shape[1]
+        attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size=hidden_states.shape[0])
     query = attn.to_q(hidden_states)
     ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
     key, value = attn.to_k(ctx), attn.to_v(ctx)
@@ -113,8 +126,11 @@ def processor_forward_baddbmm(attn, hidden_states, encoder_hidden_states=None, r
         return t.reshape(b, n, attn.heads, c // attn.heads).permute(0, 2, 1, 3).reshape(b * attn.heads, n, c // attn.heads)
 
     query, key, value = head_to_batch_dim(query), head_to_batch_dim(key), head_to_batch_dim(value)
-    empty = torch.empty(query.shape[0], query.shape[1], key.shape[1], dtype=query.dtype, device=query.device)
-    scores = torch.baddbmm(empty, query, key.transpose(-1, -2), beta=0, alpha=attn.scale).to(query.dtype)  # :39-70
+    if attention_mask is None:
+        empty = torch.empty(query.shape[0], query.shape[1], key.shape[1], dtype=query.dtype, device=query.device)
+        scores = torch.baddbmm(empty, query, key.transpose(-1, -2), beta=0, alpha=attn.scale).to(query.dtype)  # :39-70
+    else:
+        scores = torch.baddbmm(attention_mask, query, key.transpose(-1, -2), beta=1, alpha=attn.scale).to(query.dtype)
     if is_xattn and isinstance(region_prompt["region_state"], dict):
         w = region_prompt["region_state"][img_sequence_length].to(query.device)
         cw = region_prompt["weight_func"](w, region_prompt["sigma"], scores)

@@ -7,6 +7,7 @@ the reference tree does not exist.  Everything is seeded; re-running reproduces 
   attn_*.npz     inputs (fp16-representable, stored as float16) + fp32 output of the reference's
                  scaled_dot_product_attention_regionstate (attention_modify.py:74-103) with the
                  reference weight_func (app.py:1004), and the std it saw
+  procm_baddbmm_*.npz the same with an additive attention mask ([B*heads, 1, S], the baddbmm input with beta = 1)
   proc_baddbmm_*.npz  module weights + inputs (float16) + fp32 output of the reference's ``AttnProcessor`` (the
                  torch.baddbmm variant, attention_modify.py:107-207) on the region path
   region_*.npz   inputs (uint8 maps, strengths, token ids) + the fp32 maps returned by the reference's
@@ -167,8 +168,11 @@ def gen_proc_baddbmm():
         def prepare_attention_mask(self, m, *_a, **_k):
             return m
 
-    for name, C, H, D, B, L, sigma in (("proc_baddbmm_L256_D40", 320, 8, 40, 2, 256, 5.0),
-                                       ("proc_baddbmm_L64_D160", 1280, 8, 160, 2, 64, 11.0)):
+    # procm_*: the same with an additive attention mask in the form diffusers' prepare_attention_mask hands over
+    # ([B*heads, 1, S], :144): the baddbmm input with beta = 1 (:52-63) -- key biases per (batch, head), finite values
+    for name, C, H, D, B, L, sigma, masked in (("proc_baddbmm_L256_D40", 320, 8, 40, 2, 256, 5.0, False),
+                                               ("proc_baddbmm_L64_D160", 1280, 8, 160, 2, 64, 11.0, False),
+                                               ("procm_baddbmm_L144_D80", 640, 8, 80, 2, 144, 7.0, True)):
         attn = Attn(C, H, D)
         seed = len(name) + L
         load_numpy_weights(attn, seed)
@@ -180,10 +184,17 @@ def gen_proc_baddbmm():
         W[:, L // 3 :, 6] += 0.7
         W[:, L // 4 : L // 2, 3] = -0.25
         rp = {"region_state": {L: W.clone()}, "sigma": torch.tensor(sigma), "weight_func": weight_func}
+        extra = {}
+        mask = None
+        if masked:
+            mask = torch.randn(B * H, 1, 77, generator=g) * 0.75
+            mask[:, :, 60:] -= 4.0  # "padding" keys pushed down, still finite
+            mask = mask.half().float()
+            extra["mask"] = mask.half().numpy()
         with torch.no_grad():
-            out = ref.AttnProcessor()(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)
+            out = ref.AttnProcessor()(attn, hs, encoder_hidden_states=ctx, attention_mask=mask, region_prompt=rp)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), hs=hs.half().numpy(), ctx=ctx.half().numpy(), W=W.numpy(),
-                            sigma=np.float32(sigma), heads=H, head_dim=D, weight_seed=seed, out=out.numpy())
+                            sigma=np.float32(sigma), heads=H, head_dim=D, weight_seed=seed, out=out.numpy(), **extra)
         print(name, tuple(out.shape))
 
 

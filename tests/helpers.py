@@ -133,3 +133,8 @@ def baddbmm_fixture(path):
     rp = {"region_state": {hs.shape[1]: torch.from_numpy(z["W"]).clone()}, "sigma": torch.tensor(float(z["sigma"])),
           "weight_func": weight_func}
     return attn, hs, ctx, rp, torch.from_numpy(z["out"])
+
+
+def baddbmm_mask_fixture(path):
+    """baddbmm_fixture + the additive attention mask ([B*heads, 1, S] fp32) of a tests/golden/procm_baddbmm_*.npz fixture."""
+    return (*baddbmm_fixture(path), torch.from_numpy(np.load(path)["mask"]).float())

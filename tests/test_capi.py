@@ -31,7 +31,7 @@ def test_version_and_workspace_size():
     from diffusionspatialcontrol_b200 import _lib
     from diffusionspatialcontrol_b200.attention import workspace_bytes
 
-    assert _lib.lib.dsc_version() == 107
+    assert _lib.lib.dsc_version() == 108
     assert workspace_bytes(16, 8, 4096, 40, 77) >= 64 + 16 * 148
     n = ctypes.c_size_t(0)
     assert _lib.lib.dsc_xattn_workspace_bytes(0, 8, 64, 40, 77, ctypes.byref(n)) == _lib.ERR_INVALID_ARGUMENT
@@ -51,8 +51,15 @@ def test_argument_validation_returns_codes_not_crashes():
     assert lib.dsc_xattn_stats(fake, fake, ok_q, ok_k, None, 2, 8, 4096, 40, 481, 0.1, 0, fake, None) == _lib.ERR_UNSUPPORTED
     assert lib.dsc_xattn_stats(fake, fake, ok_q, ok_k, None, 2, 8, 4096, 40, 77, 0.1, 7, fake, None) == _lib.ERR_INVALID_ARGUMENT
     assert lib.dsc_xattn_stats(fake, fake, ok_q, ok_k, None, 2, 8, 0, 40, 77, 0.1, 0, fake, None) == _lib.ERR_INVALID_ARGUMENT
-    # additive mask: not implemented, says so
-    assert lib.dsc_xattn_stats(fake, fake, ok_q, ok_k, fake, 2, 8, 4096, 40, 77, 0.1, 0, fake, None) == _lib.ERR_UNSUPPORTED
+    # additive mask: fp32, 4-byte aligned, non-negative strides; the masked call needs a mask
+    assert lib.dsc_xattn_stats(fake, fake, ok_q, ok_k, ctypes.c_void_p(0x1002), 2, 8, 4096, 40, 77, 0.1, 0, fake, None) == _lib.ERR_LAYOUT
+    I3m = ctypes.c_int64 * 3
+    rc = lib.dsc_xattn_call_masked(fake, fake, fake, ok_q, ok_k, ok_k, fake, 2, 80, fake, I3m(0, -77, 0), None, 1.0, fake, fake,
+                                   I3m(4096 * 320, 320, 1), 2, 8, 4096, 40, 77, 0.1, 0, None)
+    assert rc == _lib.ERR_LAYOUT and b"mask strides" in lib.dsc_last_error()
+    rc = lib.dsc_xattn_call_masked(fake, fake, fake, ok_q, ok_k, ok_k, fake, 2, 80, None, I3m(0, 0, 0), None, 1.0, fake, fake,
+                                   I3m(4096 * 320, 320, 1), 2, 8, 4096, 40, 77, 0.1, 0, None)
+    assert rc == _lib.ERR_INVALID_ARGUMENT
     # layout contract
     bad = I4(4096 * 320, 4096 * 40, 40, 1)  # contiguous [B,H,L,D]: stride(H) != D
     assert lib.dsc_xattn_stats(fake, fake, bad, ok_k, None, 2, 8, 4096, 40, 77, 0.1, 0, fake, None) == _lib.ERR_LAYOUT

@@ -227,8 +227,10 @@ def test_layout_normalisation_and_errors():
         dsc.region_attention(q.cpu(), k.cpu(), v.cpu(), W.cpu(), 1.0)
     with pytest.raises(TypeError):
         dsc.region_attention(q.float(), k.float(), v.float(), W, 1.0)
-    with pytest.raises(NotImplementedError):
-        dsc.region_attention(q, k, v, W, 1.0, attn_mask=torch.zeros(64, 77, device="cuda"))
+    with pytest.raises(ValueError):  # additive masks must broadcast to [B, H, L, S] (tests/test_gpu_masks.py covers the rest)
+        dsc.region_attention(q, k, v, W, 1.0, attn_mask=torch.zeros(63, 77, device="cuda"))
+    with pytest.raises(TypeError):
+        dsc.region_attention(q, k, v, W, 1.0, attn_mask=torch.zeros(64, 77, device="cuda", dtype=torch.int32))
 
 
 class _Attn(nn.Module):

@@ -147,3 +147,78 @@ def test_oracle_baddbmm_processor_matches_golden(path):
     with torch.no_grad():
         got = oa.processor_forward_baddbmm(attn, hs, ctx, rp)
     assert torch.allclose(got, want, atol=1e-6, rtol=1e-5)
+
+
+# ------------------------------------------------------------------ additive attention masks (a = Q K^T + M)
+@needs_ref
+def test_reference_function_mask_semantics_are_what_the_product_mirrors():
+    """attention_modify.py:84-89 on the unmodified module: a BOOL mask is never applied (:86-87 only rewrites the mask
+    tensor), a float mask is added in place into a [L, S] bias (:89) -- fine for masks that broadcast INTO [L, S], a
+    RuntimeError for the 4-D tensor the processor builds (:452).  The oracle restates exactly that."""
+    ref = ref_loader.attention_modify()
+    f = ref.scaled_dot_product_attention_regionstate
+    B, H, L, D, S = 2, 8, 64, 40, 77
+    q, k, v = (t.float() for t in make_qkv(B, H, L, D, S, seed=21))
+    W, sig = synthetic_w(B, L, S), torch.tensor(3.0)
+    base = f(q, k, v, weight_func=weight_func, region_state=W.clone(), sigma=sig)
+    mb = torch.ones(B, H, 1, S, dtype=torch.bool)
+    mb[..., 40:] = False
+    assert torch.equal(f(q, k, v, attn_mask=mb.clone(), weight_func=weight_func, region_state=W.clone(), sigma=sig), base)
+    assert torch.equal(oa.region_attention(q, k, v, W.clone(), sig, attn_mask=mb.clone()), base)
+    for shape in ((B, H, 1, S), (B, H, L, S), (1, 1, 1, S)):
+        with pytest.raises(RuntimeError):
+            f(q, k, v, attn_mask=torch.zeros(shape), weight_func=weight_func, region_state=W.clone(), sigma=sig)
+        with pytest.raises(RuntimeError):
+            oa.region_attention(q, k, v, W.clone(), sig, attn_mask=torch.zeros(shape))
+    g = torch.Generator().manual_seed(2)
+    for shape in ((L, S), (1, S), (S,)):
+        m = torch.randn(shape, generator=g)
+        m[..., 60:] -= 5.0
+        a = f(q, k, v, attn_mask=m.clone(), weight_func=weight_func, region_state=W.clone(), sigma=sig)
+        b = oa.region_attention(q, k, v, W.clone(), sig, attn_mask=m.clone())
+        assert torch.equal(a, b) and not torch.allclose(a, base, atol=1e-3)
+
+
+@needs_ref
+def test_reference_processors_with_a_mask():
+    """The SDPA-style processor (:414-503) ignores a bool mask and raises for a float one on the region path; the baddbmm
+    processor (:107-207) adds its mask (baddbmm input, beta = 1) and the oracle's restatement is bit-identical to it."""
+    ref = ref_loader.attention_modify()
+    torch.manual_seed(12)
+    C, H, D, L, B = 320, 8, 40, 96, 2
+    attn = AttnModule(C, H, D)
+    hs, ctx = torch.randn(B, L, C), torch.randn(B, 77, 768)
+    rp = {"region_state": {L: synthetic_w(B, L, 77)}, "sigma": torch.tensor(3.0), "weight_func": weight_func}
+    m = torch.randn(B * H, 1, 77) * 0.5
+    m[:, :, 50:] -= 6.0
+    with torch.no_grad():
+        base = ref.AttnProcessor2_0()(attn, hs, encoder_hidden_states=ctx, region_prompt=rp)
+        mb = torch.ones(B * H, 1, 77, dtype=torch.bool)
+        mb[..., 30:] = False
+        assert torch.equal(ref.AttnProcessor2_0()(attn, hs, encoder_hidden_states=ctx, attention_mask=mb.clone(), region_prompt=rp), base)
+        assert torch.equal(oa.processor_forward(attn, hs, ctx, rp, attention_mask=mb.clone()), base)
+        with pytest.raises(RuntimeError):
+            ref.AttnProcessor2_0()(attn, hs, encoder_hidden_states=ctx, attention_mask=m.clone(), region_prompt=rp)
+        with pytest.raises(RuntimeError):
+            oa.processor_forward(attn, hs, ctx, rp, attention_mask=m.clone())
+        for mask in (m, m.expand(B * H, L, 77).contiguous() + torch.randn(B * H, L, 77) * 0.1):
+            a = ref.AttnProcessor()(attn, hs, encoder_hidden_states=ctx, attention_mask=mask.clone(), region_prompt=rp)
+            b = oa.processor_forward_baddbmm(attn, hs, ctx, rp, attention_mask=mask.clone())
+            assert torch.equal(a, b) and not torch.allclose(a, base, atol=1e-3)
+        # a -inf entry: the std of the masked scores is NaN and the beta term poisons every row, in the reference too
+        m_inf = m.clone()
+        m_inf[:, :, 70:] = float("-inf")
+        a = ref.AttnProcessor()(attn, hs, encoder_hidden_states=ctx, attention_mask=m_inf.clone(), region_prompt=rp)
+        assert torch.isnan(a).all() and torch.isnan(oa.processor_forward_baddbmm(attn, hs, ctx, rp, attention_mask=m_inf)).all()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "procm_baddbmm_*.npz"))))
+def test_oracle_baddbmm_processor_with_mask_matches_golden(path):
+    from .helpers import baddbmm_mask_fixture
+
+    attn, hs, ctx, rp, want, mask = baddbmm_mask_fixture(path)
+    with torch.no_grad():
+        got = oa.processor_forward_baddbmm(attn, hs, ctx, rp, attention_mask=mask)
+        unmasked = oa.processor_forward_baddbmm(attn, hs, ctx, rp)
+    assert torch.allclose(got, want, atol=1e-6, rtol=1e-5)
+    assert not torch.allclose(unmasked, want, atol=1e-3)  # the mask matters in this fixture
