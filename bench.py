@@ -214,6 +214,56 @@ def _time_call_shape(device, B, H, L, D, S, flush, peak, n_timed=30, eager_reps=
     return rec
 
 
+def _time_call_shape_in_graph(device, B, H, L, D, S, peak, footprint=512 << 20):
+    """The call as the pipeline issues it: kernel nodes of ONE CUDA graph, back to back.  3 x n_sets calls over n_sets rotating
+    input sets whose footprint exceeds the L2 four times over (inputs larger than L2 instead of a flush kernel between the
+    calls: when a set comes round again its lines have been evicted), one CUDA-event pair around the replay; per-call time =
+    elapsed / calls, the gaps between consecutive launches included."""
+    from diffusionspatialcontrol_b200 import attention as att
+
+    vw = lambda t: t.view(B, -1, H, D).transpose(1, 2)
+    per_set = 2 * B * L * H * D * 2 + B * L * 20 * 4
+    n_sets = max(4, min(48, -(-footprint // per_set)))
+    sets = []
+    for i in range(n_sets):
+        q = torch.randn(B, L, H * D, device=device, dtype=torch.float16)
+        k = torch.randn(B, S, H * D, device=device, dtype=torch.float16)
+        v = torch.randn(B, S, H * D, device=device, dtype=torch.float16)
+        W = torch.zeros(B, L, S, device=device)
+        W[:, : L // 2, 1:3] = 0.5
+        compact = att.compact_region_map(att.padded_region_map(W))
+        if not att.prepared_supported(H, D, S, len(compact[1])):
+            return None
+        sets.append((q, compact, att.prepare_kv(vw(k), vw(v), compact[1]), torch.empty_like(q)))
+    sigma = torch.tensor(7.0, device=device)
+    ws = torch.zeros(att.workspace_bytes(B, H, L, D, S), dtype=torch.uint8, device=device)
+    call = lambda t: att.region_attention_prepared(vw(t[0]), t[2], t[1], sigma, workspace=ws, out=t[3])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for t in sets:
+            call(t)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    n, g = 3 * n_sets, torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(n):
+            call(sets[i % n_sets])
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b) / n)
+    ms = sum(ts) / len(ts)
+    nbytes = 2 * B * H * L * D * 3 + 2 * B * H * S * D * 3 + 4 * B * L * S
+    del g
+    return {"ms_call": ms, "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "bytes": nbytes, "calls_per_replay": n, "replays": len(ts),
+            "input_sets": n_sets, "footprint_bytes": n_sets * per_set}
+
+
 def attention_roofline(device, sweep=True):
     """Live CUDA-event timing of the attention call (L2 flushed before every launch) on the dominant layer shape of the
     workload, the byte-weighted figure over all 16 layers of one UNet step, and (BASELINE configs[4] / configs[2]) the
@@ -233,6 +283,11 @@ def attention_roofline(device, sweep=True):
     tot_b = sum(per_shape[s]["bytes"] for s in layer_shapes)
     tot_t = sum(per_shape[s]["ms_call"] for s in layer_shapes)
     tot_e = sum(per_shape[s]["ms_eager_reference"] for s in layer_shapes)
+    in_graph = {}
+    for (L, D) in sorted(set(layer_shapes), reverse=True):
+        r = _time_call_shape_in_graph(device, B, H, L, D, S, peak)
+        if r is not None:
+            in_graph[(L, D)] = r
     traffic, traffic_src = None, None  # dram__bytes_read.sum + dram__bytes_write.sum of both passes, ncu --set full
     tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.isfile(tpath):
@@ -254,6 +309,16 @@ def attention_roofline(device, sweep=True):
         "per_shape": {f"{L}x{D}": {k: v[k] for k in ("ms_call", "bytes", "launches", "frac", "path", "ms_eager_reference",
                                                     "speedup_vs_eager")}
                       for (L, D), v in sorted(per_shape.items(), reverse=True)},
+        "in_graph": None if len(in_graph) != len(set(layer_shapes)) else {
+            "what": "the same call as kernel nodes of ONE CUDA graph (how the pipeline issues it), back to back over rotating input "
+                    "sets with a footprint of >= 4 x L2 (inputs larger than L2, no flush kernel), one event pair around each replay; "
+                    "per-call time = elapsed / calls, launch gaps included",
+            "frac": in_graph[(L0, D0)]["frac"], "achieved": in_graph[(L0, D0)]["bytes"] / (in_graph[(L0, D0)]["ms_call"] * 1e-3) / 1e9,
+            "avg_ms_call": in_graph[(L0, D0)]["ms_call"],
+            "all_16_layers": {"ms_per_unet_step": (tg := sum(in_graph[s]["ms_call"] for s in layer_shapes)),
+                              "frac": tot_b / (tg * 1e-3) / 1e9 / peak},
+            "per_shape": {f"{L}x{D}": {k: v[k] for k in ("ms_call", "frac", "calls_per_replay", "replays", "input_sets", "footprint_bytes")}
+                          for (L, D), v in sorted(in_graph.items(), reverse=True)}},
         "l2": "flushed before every timed call (512 MiB write, then a 256 MiB read so that L2 holds clean lines); two input "
               "sets alternate, so no timed call reads buffers the previous one touched; warm-up calls first",
     }
