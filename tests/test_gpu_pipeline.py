@@ -150,3 +150,32 @@ def test_cuda_graph_step_matches_eager_on_a_non_square_image():
     # the replayed graph really carries the region weights (a graph captured over zeroed static maps would not)
     assert torch.nn.functional.cosine_similarity(off.flatten(), g1.flatten(), dim=0) < 0.9999
     assert len(graph_pipe._graphs) == 2
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 320, 64, 64), (4, 640, 16, 16), (2, 1280, 8, 8), (1, 960, 32, 32)])
+@pytest.mark.parametrize("mode", ["per_channel", "welford", "two_pass"])
+@pytest.mark.parametrize("silu", [False, True])
+def test_host_groupnorm_channels_last_matches_f_group_norm(N, C, H, W, mode, silu, monkeypatch):
+    """The UNet host's GroupNorm (plain PyTorch ops, stays in channels_last) against ``F.group_norm`` evaluated in fp32 on the
+    same fp16 data: every statistics formulation, a non-zero mean (the cancellation case), with and without the fused SiLU."""
+    import torch.nn.functional as F
+
+    from diffusionspatialcontrol_b200 import unet_sd15
+
+    monkeypatch.setattr(unet_sd15.GroupNorm, "PER_CHANNEL_BYTES", 0 if mode == "per_channel" else 1 << 60)
+    monkeypatch.setattr(unet_sd15.GroupNorm, "ONE_PASS_STATS", mode != "two_pass")
+    torch.manual_seed(C + H)
+    gn = unet_sd15.GroupNorm(32, C, eps=1e-5).cuda().half()
+    with torch.no_grad():
+        gn.weight.copy_(torch.randn(C) * 0.5 + 1.0)
+        gn.bias.copy_(torch.randn(C) * 0.3)
+    x = (torch.randn(N, C, H, W, device="cuda") * 1.7 + 2.5).half().contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        got = gn(x, silu=silu)
+        want = F.group_norm(x.float(), 32, gn.weight.float(), gn.bias.float(), 1e-5)
+        want = F.silu(want) if silu else want
+    assert got.shape == x.shape and got.is_contiguous(memory_format=torch.channels_last)
+    err = (got.float() - want).abs().max().item()
+    assert err <= 4e-3 * max(1.0, want.abs().max().item()), err  # fp16 output rounding of values up to ~6
+    # 16-bit scale / shift per (sample, channel) + the 16-bit output: about 7e-4 in the norm, whatever the statistics path
+    assert (got.float() - want).norm().item() <= 1.5e-3 * want.norm().item()
