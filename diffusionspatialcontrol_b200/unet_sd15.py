@@ -157,9 +157,25 @@ class GroupNorm(nn.GroupNorm):
     # the rows of the [N, H*W, C] view: long coalesced rows, fp32 results) and fold the channels of a group afterwards on
     # [N, C] -- the one-pass Welford reduction over (H*W, C/G) of the [N, H*W, G, C/G] view runs at a tenth of the HBM rate
     # on the large activations (95 / 183 / 287 us for 40 / 80 / 120 MB against 66 / 71 / 104 us) and returns 16-bit results;
-    # UNet step at batch 16 in a graph: 28.11 ms (Welford everywhere) -> 26.69 ms (per channel everywhere), cosine
-    # 0.999999 (profiles/r2_unet_host_gn_stats_ab.jsonl, r2_unet_host_gn_mode_ab.log)
+    # UNet step at batch 16 in a graph: 28.11 ms (Welford everywhere) -> 26.69 ms (per channel everywhere) -> 25.64 ms (10
+    # instead of 16 small kernels per normalisation), cosine 0.999999 (profiles/r2_unet_host_gn_stats_ab.jsonl,
+    # r2_unet_host_gn_mode_ab.log)
     PER_CHANNEL_BYTES = int(os.environ.get("DSC_GN_PER_CHANNEL_BYTES", "0"))
+
+    def _affine32(self):
+        """fp32 [1, G, C/G] views of weight / bias, converted once per parameter version (not once per call)."""
+        key = (self.weight._version, self.bias._version, self.weight.data_ptr(), self.weight.device)
+        if getattr(self, "_a32_key", None) != key:
+            G = self.num_groups
+            self._a32 = (self.weight.detach().float().view(1, G, -1), self.bias.detach().float().view(1, G, -1))
+            self._a32_key = key
+        return self._a32
+
+    def _eps_t(self, device):
+        t = getattr(self, "_eps_tensor", None)
+        if t is None or t.device != device:
+            t = self._eps_tensor = torch.full((1,), float(self.eps), dtype=torch.float32, device=device)
+        return t
 
     def forward(self, x: torch.Tensor, silu: bool = False) -> torch.Tensor:
         if (x.is_cuda and x.dim() == 4 and x.dtype != torch.float32 and not x.is_contiguous()
@@ -170,11 +186,24 @@ class GroupNorm(nn.GroupNorm):
             xl = x.permute(0, 2, 3, 1)                      # [N, H, W, C] view of the same memory, contiguous
             xv = xl.reshape(N, H * W, G, Cg)
             if x.numel() * x.element_size() >= self.PER_CHANNEL_BYTES:
+                # the [N, G]-sized arithmetic behind the two big reductions is launch-bound (61 normalisations per UNet
+                # step): 10 small kernels instead of 16 -- 1/n folded into the fused multiply-adds, fp32 copies of weight /
+                # bias kept, scale / shift written straight into their 16-bit tensors
                 xc = xl.reshape(N, H * W, C)
-                n = float(H * W * Cg)
-                mean = xc.sum(dim=1, dtype=torch.float32).view(N, G, Cg).sum(-1) / n                 # [N, G]
-                ex2 = torch.linalg.vector_norm(xc, dim=1, dtype=torch.float32).square().view(N, G, Cg).sum(-1) / n
-                rstd = torch.rsqrt((ex2 - mean * mean).clamp_min(0.0) + self.eps)
+                inv_n = 1.0 / float(H * W * Cg)
+                a = xc.sum(dim=1, dtype=torch.float32).view(N, G, Cg).sum(-1, keepdim=True)           # sum x      [N, G, 1]
+                q = torch.linalg.vector_norm(
+                    torch.linalg.vector_norm(xc, dim=1, dtype=torch.float32).view(N, G, Cg), dim=-1, keepdim=True)  # sqrt(sum x^2)
+                u = torch.addcmul(q * q, a, a, value=-inv_n).clamp_min_(0.0)                          # n * var
+                rstd = torch.rsqrt(torch.add(self._eps_t(x.device), u, alpha=inv_n))                  # [N, G, 1]
+                w32, b32 = self._affine32()
+                ss = torch.empty((2, N, G, Cg), dtype=x.dtype, device=x.device)
+                torch.mul(rstd, w32, out=ss[0])                                                       # scale
+                torch.addcmul(b32, a * rstd, w32, value=-inv_n, out=ss[1])                            # shift = b - mean * scale
+                y = torch.addcmul(ss[1].view(N, 1, 1, C), xl, ss[0].view(N, 1, 1, C))
+                if silu:
+                    y = F.silu(y, inplace=True)
+                return y.permute(0, 3, 1, 2)
             elif self.ONE_PASS_STATS:
                 # ONE reduction over the activation (Welford, fp32 accumulation inside the kernel; the results come back in
                 # the activation's 16-bit type: the mean is off by <= 2^-11 |mean|, below the activation's own rounding
