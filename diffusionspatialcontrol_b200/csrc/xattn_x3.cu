@@ -376,8 +376,14 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 // Debug build only: cycles per phase of the pass-2 consumer loop, accumulated in registers (no stores inside the loop), written
 // once at the end by lane 0 of every consumer warp of blocks 0..3 -> g_x3_phase[block][warp][phase]
 __device__ unsigned int g_x3_phase[4][12][8];
+// (-DDSC_PHASE_SKIP_FIRST: the warp's first item -- pass 2's start-up: first tile, first record, the std -- is left out)
+#ifdef DSC_PHASE_SKIP_FIRST
+#define X3_PH_DECL long long ph_t = clock64(); unsigned int ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}; bool ph_on = false;
+#define X3_PH(k) do { const long long ph_c = clock64(); if (ph_on) ph[k] += static_cast<unsigned int>(ph_c - ph_t); ph_t = ph_c; if ((k) == 7) ph_on = true; } while (0)
+#else
 #define X3_PH_DECL long long ph_t = clock64(); unsigned int ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define X3_PH(k) do { const long long ph_c = clock64(); ph[k] += static_cast<unsigned int>(ph_c - ph_t); ph_t = ph_c; } while (0)
+#endif
 #define X3_PH_FLUSH do { if (!STATS && lane == 0 && blockIdx.x < 4 && warp < 12) { for (int k = 0; k < 8; ++k) g_x3_phase[blockIdx.x][warp][k] = ph[k]; } } while (0)
 #else
 #define X3_PH_DECL
