@@ -47,6 +47,9 @@
 
 namespace dsc {
 
+#ifndef X3_LATE_PVWAIT
+#define X3_LATE_PVWAIT 0  // pass 2: wait for P V of the previous item right before the first P store instead of before the exponentials (A/B: no change, 37.7 us)
+#endif
 #ifndef X3_TURNS
 #define X3_TURNS 2      // pass 2, 3 warpgroups: at most this many of the three warps that share an SM sub-partition exponentiate at a time (0 = off)
 #endif
@@ -1031,7 +1034,7 @@ __device__ __forceinline__ uint32_t x3_phase(const XattnParams& p, const CUtenso
           // P V of the previous item was issued when that item published P: long finished after the S read, W and row max
           // above; its completion proves P(previous) has been consumed, so this item's P may go in
           X3_PH(3);
-          pv_done();
+          if constexpr (!X3_LATE_PVWAIT) pv_done();
           X3_PH(4);
           if constexpr (C::TURNS > 0) {
             const uint32_t seq = static_cast<uint32_t>(j);
@@ -1062,6 +1065,7 @@ __device__ __forceinline__ uint32_t x3_phase(const XattnParams& p, const CUtenso
               pw[c] = c < 38 ? Mma<T>::pack(ex2_approx(e0), ex2_approx(e1)) : Mma<T>::pack(ex2_approx(e0), 0.f);
             }
             if (c == 23) {  // keys 0..47 are done: first part of P
+              if constexpr (X3_LATE_PVWAIT) pv_done();  // (only now is P(previous) about to be overwritten)
               tmem_st_x16(tw + P_COL, pw);
               tmem_st_x8(tw + P_COL + 16, pw + 16);
             }
