@@ -341,18 +341,27 @@ def attention_roofline(device, sweep=True):
                          "consecutive launches included; single_call_flushed = the round-1 method, for comparison")
         out["all_16_layers"]["frac_in_graph"] = g["all_16_layers"]["frac"]
         out["all_16_layers"]["ms_per_unet_step_in_graph"] = g["all_16_layers"]["ms_per_unet_step"]
+    def graph_cols(Bs, L, D):
+        g = in_graph.get((L, D)) if Bs == B else _time_call_shape_in_graph(device, Bs, H, L, D, S, peak, footprint=768 << 20)
+        return {} if g is None else {"ms_call_in_graph": g["ms_call"], "frac_in_graph": g["frac"]}
+
     if sweep:
         rows = []
         for (L, D) in sorted(set(layer_shapes), reverse=True):  # BASELINE configs[4]: every shape x attention batch 2..32
             for Bs in (2, 8, 16, 32):
                 r = per_shape[(L, D)] if Bs == B else _time_call_shape(device, Bs, H, L, D, S, flush, peak, n_timed=20, eager_reps=2)
                 rows.append({"config": 4, **{k: r[k] for k in ("B", "L", "D", "ms_call", "frac", "path", "launches",
-                                                               "ms_eager_reference", "speedup_vs_eager")}})
+                                                               "ms_eager_reference", "speedup_vs_eager")},
+                             **graph_cols(Bs, L, D)})
         for (L, D) in ((9216, 40), (2304, 80), (576, 160), (144, 160)):  # BASELINE configs[2]: 768 x 768, batch 4 (+ CFG twin)
             r = _time_call_shape(device, 8, H, L, D, S, flush, peak, n_timed=20, eager_reps=2)
             rows.append({"config": 2, **{k: r[k] for k in ("B", "L", "D", "ms_call", "frac", "path", "launches",
-                                                           "ms_eager_reference", "speedup_vs_eager")}})
+                                                           "ms_eager_reference", "speedup_vs_eager")},
+                         **graph_cols(8, L, D)})
         out["sweep"] = rows
+        out["sweep_columns"] = ("ms_call / frac: one L2-flushed call between its own event pair (single_call_flushed method); "
+                                "ms_call_in_graph / frac_in_graph: the call as a graph kernel node over inputs larger than L2 (the "
+                                "method of roofline.frac)")
     return out
 
 
